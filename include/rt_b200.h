@@ -1,0 +1,205 @@
+/* rt_b200.h - C ABI of the B200-native backend for simd-raytracer's kd_tree_simd_accel hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types.  The reference has no FFI of its
+ * own - its plugin point is the C++20 concept `accelerator<A,F>` (/root/reference/include/raytracer/render/accel/
+ * accel.hpp:8-12) plus the implicit `scene_ptr` member (render/render.hpp:21,113,136) - so each entry point below
+ * names the reference interface it stands in for.  include/b200_accel.hpp is the header-only C++ adapter that
+ * satisfies that concept on top of this ABI; INTEGRATION.md shows the reference-side binding.
+ *
+ * Every function returns an rt_status (0 = ok) and never throws across the boundary.  The reference's query is
+ * `noexcept` and reports a miss as std::nullopt (kd_tree_simd.hpp:188,230-232); here a miss is tri == -1.
+ *
+ * There is no CPU fallback: compute entry points fail with RT_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RT_API __attribute__((visibility("default")))
+#else
+#define RT_API
+#endif
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_BAD_ARG = 1,
+    RT_ERR_NO_DEVICE = 2,      /* no CUDA device / not an sm_100 part / host-only scene used for compute */
+    RT_ERR_CUDA = 3,           /* a CUDA runtime call failed; see rt_last_error() */
+    RT_ERR_IO = 4,             /* scene / texture file could not be read */
+    RT_ERR_PARSE = 5,          /* malformed .crtscene / RTSC; unknown material or texture type */
+    RT_ERR_OOM = 6,
+    RT_ERR_UNSUPPORTED = 7     /* e.g. a bitmap format the loader cannot decode */
+} rt_status;
+
+/* ---- scene description: what io/json/loader.hpp:235-265 produces, flattened -------------------------------- */
+
+enum { RT_TEX_ALBEDO = 0, RT_TEX_EDGES = 1, RT_TEX_CHECKER = 2, RT_TEX_BITMAP = 3 };      /* scene/texture/texture.hpp:11 */
+enum { RT_MAT_DIFFUSE = 0, RT_MAT_REFLECTIVE = 1, RT_MAT_REFRACTIVE = 2, RT_MAT_CONSTANT = 3,
+       RT_MAT_TEXTURE = 4 };                                                              /* scene/material/material.hpp:11-12 */
+
+typedef struct rt_light_desc { float position[3]; float intensity; } rt_light_desc;       /* scene/light.hpp:5-9 */
+
+typedef struct rt_texture_desc {     /* scene/texture/{albedo,edge,checker,bitmap}.hpp */
+    uint32_t kind;
+    float c0[3];                     /* albedo | edge_color  | color_A */
+    float c1[3];                     /*        | inner_color | color_B */
+    float scalar;                    /*        | edge_width  | square_size */
+    uint32_t bmp_w, bmp_h, bmp_off;  /* bitmap: size and byte offset of its RGB8 texels in rt_scene_desc.texels */
+} rt_texture_desc;
+
+typedef struct rt_material_desc {    /* scene/material/ headers */
+    uint32_t kind;
+    float albedo[3];
+    float ior;
+    uint32_t smooth_shading;
+    int32_t texture;                 /* RT_MAT_TEXTURE: index into textures[] (the reference keys by name) */
+} rt_material_desc;
+
+typedef struct rt_mesh_desc {        /* scene/object/mesh.hpp:14-21 as loaded by loader.hpp:149-233 */
+    uint32_t material;
+    uint32_t n_vertices, n_uvs, n_triangles;
+    const float* vertices;           /* 3 * n_vertices */
+    const float* uvs;                /* 2 * n_uvs (may be null when n_uvs == 0) */
+    const uint32_t* triangles;       /* 3 * n_triangles vertex indices */
+} rt_mesh_desc;
+
+typedef struct rt_scene_desc {       /* scene/scene.hpp:14-22 */
+    float background[3];
+    uint32_t width, height, bucket_size;   /* scene/settings.hpp:7-13 */
+    float camera_position[3];
+    float camera_matrix[9];                /* row major, used transposed (render/render.hpp:60) */
+    uint32_t n_lights;    const rt_light_desc* lights;
+    uint32_t n_textures;  const rt_texture_desc* textures;
+    uint32_t n_materials; const rt_material_desc* materials;
+    uint32_t n_meshes;    const rt_mesh_desc* meshes;
+    uint64_t n_texel_bytes; const uint8_t* texels;
+} rt_scene_desc;
+
+/* The accel's template arguments (kd_tree_simd.hpp:63-67) become run-time options. */
+typedef struct rt_build_opts {
+    uint32_t kd_max_depth;           /* default 8  (kd_tree_simd.hpp:65) */
+    uint32_t kd_max_leaf_size;       /* default 64 (kd_tree_simd.hpp:66) */
+    int32_t device;                  /* CUDA ordinal; RT_DEVICE_HOST_ONLY builds tree + layout without a GPU */
+} rt_build_opts;
+#define RT_DEVICE_HOST_ONLY (-1)
+
+/* config.hpp:6-17 as run-time parameters, plus the tile / sample slice used for multi-GPU sharding. */
+typedef struct rt_params {
+    double fov_degrees;              /* config.hpp:6 */
+    float epsilon;                   /* config.hpp:8 (narrowed to float as src/main.cpp:37) */
+    float shadow_bias;               /* config.hpp:9  */
+    float reflection_bias;           /* config.hpp:10 */
+    float refraction_bias;           /* config.hpp:11 */
+    uint32_t samples_per_pixel;      /* config.hpp:13 - samples rendered by THIS call */
+    uint32_t max_ray_depth;          /* config.hpp:14 */
+    uint32_t diffuse_reflection_ray_count; /* config.hpp:15 */
+    uint32_t seed;                   /* config.hpp:17 fixed_rng_seed -> Philox key */
+    uint32_t sample_offset;          /* first global sample index of this slice */
+    uint32_t spp_total;              /* samples of the whole frame (0 = samples_per_pixel); ==1 -> pixel centres */
+    uint32_t x0, y0, x1, y1;         /* tile rectangle; x1 == 0 / y1 == 0 mean full width / height */
+    uint32_t flags;                  /* RT_FLAG_* */
+} rt_params;
+
+#define RT_FLAG_RAW_SUM       0x1u   /* write the slice's sample sum; the caller divides after combining ranks */
+#define RT_FLAG_FAST_MATH     0x2u   /* FMA-contracted traversal + intersection (not bit-exact) */
+#define RT_FLAG_ORDERED       0x4u   /* front-to-back kd traversal over the 8-byte nodes */
+
+typedef struct rt_hit {              /* the part of hit<F> (render/hit.hpp:9-21) that cannot be recomputed */
+    float t, u, v;
+    int32_t tri;                     /* global triangle index (mesh-order concatenation, kd_tree_simd.hpp:103-111); -1 = miss */
+} rt_hit;
+
+typedef struct rt_scene_info {
+    uint32_t width, height;
+    uint64_t n_triangles, n_vertices, n_nodes, n_leaves, n_leaf_refs, n_packets;
+    uint64_t max_leaf_refs, tree_depth;
+    uint64_t device_bytes;           /* resident scene bytes in HBM */
+    double build_seconds, flatten_seconds, upload_seconds;
+    int32_t device;
+} rt_scene_info;
+
+typedef struct rt_counters {         /* of the last rt_render_frame* call */
+    uint64_t primary, primary_hits;
+    uint64_t shadow, shadow_hits;            /* closest-hit queries issued by the is_occluded loops */
+    uint64_t secondary, secondary_hits;      /* reflection + refraction + GI */
+    uint64_t nodes_pool, shadow_pool;        /* wavefront pool high-water marks */
+    uint32_t kernel_launches;
+    uint32_t passes;
+    float ms_total;                  /* device time of the frame, CUDA events */
+    float ms_primary, ms_secondary, ms_shadow, ms_shade, ms_resolve;   /* by kernel class */
+} rt_counters;
+
+typedef struct rt_scene rt_scene;
+
+RT_API int rt_abi_version(void);
+RT_API const char* rt_status_string(int status);
+RT_API const char* rt_last_error(void);                         /* thread-local detail for the last non-zero status */
+
+RT_API void rt_default_build_opts(rt_build_opts* o);
+RT_API void rt_default_params(rt_params* p);                    /* the values of config.hpp:6-17 */
+
+/* kd_tree_simd_accel ctor (kd_tree_simd.hpp:100-115): host kd-tree build, flatten, upload. */
+RT_API int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_scene** out);
+/* parse_scene_file (io/json/loader.hpp:235-265) + the ctor above.  asset_root resolves relative bitmap paths
+ * (the reference resolves them against the CWD, README.md:32-35); may be null. */
+RT_API int rt_scene_create_from_crtscene(const char* path, const char* asset_root, const rt_build_opts* opts, rt_scene** out);
+/* same, from the flat RTSC container used by the test fixtures (tests/helpers/crtscene.py documents the layout) */
+RT_API int rt_scene_create_from_rtsc(const void* bytes, uint64_t n_bytes, const rt_build_opts* opts, rt_scene** out);
+RT_API void rt_scene_destroy(rt_scene* s);
+RT_API int rt_scene_get_info(const rt_scene* s, rt_scene_info* info);
+
+/* Host-side structures for builder / flattener parity checks (no GPU needed).  Null pointers are skipped.
+ *   node5  : 5 x u64 per node = parent, child0, child1, first_ref, ref_count (UINT64_MAX = none), as
+ *            kd_tree_simd_accel::node (kd_tree_simd.hpp:75-84) with packs counted in triangle refs
+ *   boxes  : 6 floats per node (min xyz, max xyz)
+ *   refs   : n_leaf_refs triangle indices (leaf lists, in order)                                              */
+RT_API int rt_scene_get_tree(const rt_scene* s, uint64_t* node5, float* boxes, uint32_t* refs);
+/*   nodes8 : the 8-byte device nodes (2 x u32 per node); packets: 40 x u32 per 4-triangle SoA packet          */
+RT_API int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets);
+/*   tri9 = v0,e1,e2 per triangle; face normals; vertex normals (mesh-concatenated vertex order)               */
+RT_API int rt_scene_get_geometry(const rt_scene* s, float* tri9, float* face_normals, float* vertex_normals);
+
+/* accel.intersect<cull>(ray) for a batch (kd_tree_simd.hpp:187-264; callers render.hpp:64,116,175,244,269,284,293).
+ * rays: 6 floats per ray (origin, direction); inv_direction is derived as ray3's ctor does (ray3.hpp:11-14).
+ * Host buffers: copies in, traces, copies out.  flags: RT_FLAG_FAST_MATH / RT_FLAG_ORDERED or 0.              */
+RT_API int rt_trace_closest(rt_scene* s, const float* rays, uint64_t n, int backface_culling, float epsilon,
+                     uint32_t flags, rt_hit* hits);
+/* is_occluded(accel, ray, max_t) for a batch (render/render.hpp:110-131), incl. refractive pass-through.       */
+RT_API int rt_trace_occluded(rt_scene* s, const float* rays, const float* max_t, uint64_t n, float epsilon,
+                      float shadow_bias, uint32_t flags, uint8_t* occluded);
+/* device-pointer variants (no copies; `stream` is a cudaStream_t or null for the scene's own stream)           */
+RT_API int rt_trace_closest_device(rt_scene* s, const float* d_rays, uint64_t n, int backface_culling, float epsilon,
+                            uint32_t flags, rt_hit* d_hits, void* stream);
+RT_API int rt_trace_occluded_device(rt_scene* s, const float* d_rays, const float* d_max_t, uint64_t n, float epsilon,
+                             float shadow_bias, uint32_t flags, uint8_t* d_occluded, void* stream);
+
+/* render_frame<A,F>(accel, schedule) (render/render.hpp:18-108): ray generation, traversal, shading, shadows,
+ * reflection / refraction / GI bounces, all on device.  rgb: height*width*3 floats, row major (image<F>);
+ * only the tile rectangle is written.                                                                         */
+RT_API int rt_render_frame(rt_scene* s, const rt_params* p, float* rgb);
+/* same + the PPM writer's quantisation uint8(255.999*clamp(c,0,1)) (io/image/ppm.hpp:17-19) fused on device.   */
+RT_API int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8);
+/* device framebuffer (for the multi-GPU combine): d_rgb = height*width*3 floats in HBM; asynchronous on stream */
+RT_API int rt_render_frame_device(rt_scene* s, const rt_params* p, float* d_rgb, void* stream);
+/* primary rays only: ray generation + intersect<true> (render.hpp:35-64); hits: one per pixel of the tile,
+ * row major over the tile.  Host buffer.                                                                      */
+RT_API int rt_trace_primary(rt_scene* s, const rt_params* p, rt_hit* hits);
+
+RT_API int rt_get_counters(rt_scene* s, rt_counters* c);        /* blocks until the last frame has finished */
+
+/* fused post-combine step for spp-sliced multi-GPU frames: d_rgb8 = quantise(d_sum / spp_total)               */
+RT_API int rt_resolve_sum_device(rt_scene* s, const float* d_sum, uint32_t spp_total, float* d_rgb_out, uint8_t* d_rgb8_out,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

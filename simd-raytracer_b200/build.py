@@ -1,0 +1,67 @@
+"""Builds simd-raytracer_b200/librt_b200.so (the C-ABI library of include/rt_b200.h) in-tree, for sm_100a only.
+
+    python simd-raytracer_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU.  Flags that are part of the numerical contract (DESIGN.md "Numerics"):
+  device: -fmad=false            no FMA contraction; the FAST variants spell fmaf() explicitly
+  host  : -ffp-contract=off      triangle / vertex normals feed shading and must equal the canonical reference build
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "librt_b200.so")
+BUILD = os.path.join(HERE, "build")
+
+CU = [os.path.join(HERE, "csrc", "rt_api.cu")]
+CPP = [os.path.join(HERE, "host", "kd_build.cpp"), os.path.join(HERE, "host", "scene_io.cpp")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("rt_device.cuh", "rt_wavefront.cuh")] + \
+       [os.path.join(HERE, "host", f) for f in ("kd_build.hpp", "scene.hpp", "json.hpp")] + \
+       [os.path.join(REPO, "include", "rt_b200.h"), os.path.abspath(__file__)]
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v"]
+CXX_FLAGS = ["-std=c++20", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden", "-Wall", "-Wextra"]
+
+
+def _stale(out: str, srcs) -> bool:
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    objs = []
+    for src in CU:
+        obj = os.path.join(BUILD, os.path.basename(src) + ".o")
+        if force or _stale(obj, [src] + DEPS):
+            cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            with open(os.path.join(BUILD, os.path.basename(src) + ".ptxas.log"), "w") as fh:
+                fh.write(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed: " + " ".join(cmd))
+            if verbose:
+                sys.stderr.write(r.stderr)
+        objs.append(obj)
+    for src in CPP:
+        obj = os.path.join(BUILD, os.path.basename(src) + ".o")
+        if force or _stale(obj, [src] + DEPS):
+            subprocess.check_call(["g++"] + CXX_FLAGS + ["-c", src, "-o", obj])
+        objs.append(obj)
+    if force or _stale(LIB, objs):
+        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
+                              ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

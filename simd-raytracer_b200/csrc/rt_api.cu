@@ -1,0 +1,752 @@
+// csrc/rt_api.cu - the extern "C" layer of include/rt_b200.h: scene upload, ray batches, frames, counters.
+//
+// Build (see simd-raytracer_b200/build.py): nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo.
+// -fmad=false is part of the numerical contract (rt_device.cuh); nothing in this file may be compiled with
+// --use_fast_math.  There is no CPU fallback: without a usable sm_100 device every compute entry point returns
+// RT_ERR_NO_DEVICE.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "../host/kd_build.hpp"
+#include "../host/scene.hpp"
+#include "rt_wavefront.cuh"
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& what) {
+    g_last_error = what;
+    return status;
+}
+
+struct cuda_error { cudaError_t e; const char* what; };
+#define CK(call)                                                   \
+    do {                                                           \
+        const cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) throw cuda_error{e_, #call};        \
+    } while (0)
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const rt_error& e) {
+        return fail(e.status, e.what());
+    } catch (const cuda_error& e) {
+        const int st = (e.e == cudaErrorMemoryAllocation) ? RT_ERR_OOM
+                       : (e.e == cudaErrorNoDevice || e.e == cudaErrorInsufficientDriver) ? RT_ERR_NO_DEVICE : RT_ERR_CUDA;
+        cudaGetLastError();
+        return fail(st, std::string(e.what) + ": " + cudaGetErrorString(e.e));
+    } catch (const std::bad_alloc&) {
+        return fail(RT_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(RT_ERR_BAD_ARG, e.what());
+    }
+}
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+struct DBuf {                       // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+T* upload(const void* src, size_t n_elems, uint64_t& total) {
+    T* d = nullptr;
+    const size_t bytes = std::max<size_t>(n_elems, 1) * sizeof(T);
+    CK(cudaMalloc(&d, bytes));
+    if (n_elems) CK(cudaMemcpy(d, src, n_elems * sizeof(T), cudaMemcpyHostToDevice));
+    total += bytes;
+    return d;
+}
+
+enum TimeClass { TC_PRIMARY = 0, TC_SECONDARY, TC_SHADOW, TC_SHADE, TC_RESOLVE, TC_N };
+
+}  // namespace
+
+struct rt_scene {
+    HostScene host;
+    Geometry geom;
+    KdTree tree;
+    DeviceLayout layout;
+    rt_scene_info info{};
+
+    int device = RT_DEVICE_HOST_ONLY;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    DScene d{};
+    std::vector<void*> owned;        // device allocations of the resident scene
+
+    // wavefront pools (grow-only, reused across frames)
+    DBuf<Ray> rays; DBuf<Hit> hits; DBuf<Rec> recs; DBuf<ShadowJob> jobs;
+    PassState* ps = nullptr;
+    FrameCounters* fc = nullptr;
+    uint32_t* h_flags = nullptr;     // pinned: pool_count, shadow_count, overflow of the last pass
+    FrameCounters* h_fc = nullptr;   // pinned
+    double pool_factor = 2.0, shadow_factor = 1.0;
+    DBuf<float> fb; DBuf<uint8_t> fb8;
+    DBuf<float> q_rays, q_maxt; DBuf<Hit> q_hits; DBuf<uint8_t> q_occ;
+
+    // counters of the last frame
+    rt_counters counters{};
+    struct Span { cudaEvent_t a, b; int cls; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    cudaEvent_t frame_a = nullptr, frame_b = nullptr;
+    bool counters_pending = false;
+    uint64_t pool_hwm = 0, shadow_hwm = 0;
+    uint32_t launches = 0, passes = 0;
+
+    std::mutex mtx;
+    int g_primary[4] = {0, 0, 0, 0}, g_trace[4] = {0, 0, 0, 0}, g_shadow[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g_shade[2] = {0, 0}, g_resolve = 0;
+
+    ~rt_scene() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            if (stream) cudaStreamSynchronize(stream);
+            for (void* p : owned) cudaFree(p);
+            rays.release(); hits.release(); recs.release(); jobs.release(); fb.release(); fb8.release();
+            q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
+            if (ps) cudaFree(ps);
+            if (fc) cudaFree(fc);
+            if (h_flags) cudaFreeHost(h_flags);
+            if (h_fc) cudaFreeHost(h_fc);
+            for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+            if (frame_a) cudaEventDestroy(frame_a);
+            if (frame_b) cudaEventDestroy(frame_b);
+            if (stream) cudaStreamDestroy(stream);
+        }
+    }
+    cudaEvent_t next_event() {
+        if (events_used == event_pool.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            event_pool.push_back(e);
+        }
+        return event_pool[events_used++];
+    }
+};
+
+namespace {
+
+void require_device(const rt_scene* s) {
+    if (!s) throw rt_error(RT_ERR_BAD_ARG, "null scene");
+    if (s->device < 0) throw rt_error(RT_ERR_NO_DEVICE, "scene was built host-only (RT_DEVICE_HOST_ONLY): no device to compute on");
+}
+
+void upload_scene(rt_scene* s) {
+    const double t0 = now_s();
+    int count = 0;
+    const cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw rt_error(RT_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    if (s->device >= count) throw rt_error(RT_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, s->device));
+    if (prop.major != 10) throw rt_error(RT_ERR_NO_DEVICE, std::string("device is not an sm_100 part: ") + prop.name);
+    s->n_sm = prop.multiProcessorCount;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+    const DeviceLayout& L = s->layout;
+    const HostScene& H = s->host;
+    uint64_t bytes = 0;
+    DScene& d = s->d;
+    auto keep = [&](auto* p) { s->owned.push_back((void*)p); return p; };
+    d.nodes8 = keep(upload<uint2>(L.nodes8.data(), L.nodes8.size() / 2, bytes));
+    d.nodes32 = keep(upload<float4>(L.nodes32.data(), L.nodes32.size() / 4, bytes));
+    d.packets = keep(upload<float4>(L.packets.data(), L.packets.size() / 4, bytes));
+    d.tri_index = keep(upload<uint4>(L.tri_index.data(), L.tri_index.size() / 4, bytes));
+    d.tri_normal = keep(upload<float4>(L.tri_normal.data(), L.tri_normal.size() / 4, bytes));
+    d.tri_uv = keep(upload<float4>(L.tri_uv.data(), L.tri_uv.size() / 4, bytes));
+    d.vnormals = keep(upload<float4>(L.vnormals.data(), L.vnormals.size() / 4, bytes));
+    static_assert(sizeof(DMaterial) == sizeof(rt_material_desc) && sizeof(DTexture) == sizeof(rt_texture_desc) &&
+                  sizeof(DLight) == sizeof(rt_light_desc), "device mirrors of the ABI structs");
+    d.materials = keep(upload<DMaterial>(H.materials.data(), H.materials.size(), bytes));
+    d.textures = keep(upload<DTexture>(H.textures.data(), H.textures.size(), bytes));
+    d.lights = keep(upload<DLight>(H.lights.data(), H.lights.size(), bytes));
+    d.texels = keep(upload<uint8_t>(H.texels.data(), H.texels.size(), bytes));
+    d.n_lights = uint32_t(H.lights.size());
+    d.n_nodes = uint32_t(s->tree.nodes.size());
+    d.width = H.width; d.height = H.height;
+    std::memcpy(d.bg, H.background, 12);
+    std::memcpy(d.cam_pos, H.camera_position, 12);
+    std::memcpy(d.cam_m, H.camera_matrix, 36);
+    std::memcpy(d.root_min, s->geom.root_min, 12);
+    std::memcpy(d.root_max, s->geom.root_max, 12);
+    d.has_transmissive = L.has_transmissive ? 1 : 0;
+
+    CK(cudaMalloc(&s->ps, sizeof(PassState)));
+    CK(cudaMalloc(&s->fc, sizeof(FrameCounters)));
+    CK(cudaMallocHost(&s->h_flags, 4 * sizeof(uint32_t)));
+    CK(cudaMallocHost(&s->h_fc, sizeof(FrameCounters)));
+    CK(cudaEventCreate(&s->frame_a));
+    CK(cudaEventCreate(&s->frame_b));
+    CK(cudaDeviceSynchronize());
+    s->info.device_bytes = bytes;
+    s->info.upload_seconds = now_s() - t0;
+}
+
+int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
+    rt_build_opts o;
+    rt_default_build_opts(&o);
+    if (opts) o = *opts;
+    if (o.kd_max_depth > 30) throw rt_error(RT_ERR_BAD_ARG, "kd_max_depth > 30");
+    if (o.kd_max_leaf_size == 0) throw rt_error(RT_ERR_BAD_ARG, "kd_max_leaf_size == 0");
+    double t0 = now_s();
+    s->geom = prepare_geometry(s->host);
+    s->tree = build_kd_tree(s->geom, o.kd_max_depth, o.kd_max_leaf_size);
+    s->info.build_seconds = now_s() - t0;
+    t0 = now_s();
+    s->layout = flatten(s->host, s->geom, s->tree);
+    s->info.flatten_seconds = now_s() - t0;
+    s->info.width = s->host.width; s->info.height = s->host.height;
+    s->info.n_triangles = s->geom.tris.size();
+    s->info.n_vertices = s->geom.vertex_normals.size() / 3;
+    s->info.n_nodes = s->tree.nodes.size();
+    s->info.n_leaves = s->tree.n_leaves;
+    s->info.n_leaf_refs = s->tree.refs.size();
+    s->info.n_packets = s->layout.n_packets;
+    s->info.max_leaf_refs = s->tree.max_leaf_refs;
+    s->info.tree_depth = s->tree.depth;
+    s->device = o.device;
+    s->info.device = o.device;
+    if (o.device >= 0) upload_scene(s);
+    *out = s;
+    return RT_OK;
+}
+
+template <class Loader>
+int create_with(Loader&& load, const rt_build_opts* opts, rt_scene** out) {
+    if (!out) return fail(RT_ERR_BAD_ARG, "null output handle");
+    *out = nullptr;
+    rt_scene* s = nullptr;
+    const int st = guarded([&] {
+        s = new rt_scene();
+        s->host = load();
+        return finish_create(s, opts, out);
+    });
+    if (st != RT_OK) { delete s; *out = nullptr; }
+    return st;
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------------------------
+struct Mode { bool fast, ordered; };
+Mode mode_of(uint32_t flags) { return Mode{(flags & RT_FLAG_FAST_MATH) != 0, (flags & RT_FLAG_ORDERED) != 0}; }
+
+template <class K>
+int grid_for(rt_scene* s, K kernel) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
+    return s->n_sm * std::max(per_sm, 1);
+}
+
+#define DISPATCH_MODE(m, CALL)                                      \
+    do {                                                            \
+        if (!(m).fast && !(m).ordered) { CALL(false, false); }      \
+        else if ((m).fast && !(m).ordered) { CALL(true, false); }   \
+        else if (!(m).fast && (m).ordered) { CALL(false, true); }   \
+        else { CALL(true, true); }                                  \
+    } while (0)
+
+void launch_trace_batch(rt_scene* s, const float* d_rays, uint64_t n, bool cull, float eps, Mode m, Hit* d_hits, cudaStream_t st) {
+    if (!n) return;
+    const int blocks = int(std::min<uint64_t>((n + 255) / 256, uint64_t(s->n_sm) * 64));
+#define CALL(F, O)                                                                                          \
+    if (cull) k_trace_batch<true, F, O><<<blocks, 256, 0, st>>>(s->d, d_rays, n, eps, d_hits);              \
+    else k_trace_batch<false, F, O><<<blocks, 256, 0, st>>>(s->d, d_rays, n, eps, d_hits)
+    DISPATCH_MODE(m, CALL);
+#undef CALL
+    CK(cudaGetLastError());
+}
+
+void launch_occluded_batch(rt_scene* s, const float* d_rays, const float* d_maxt, uint64_t n, float eps, float bias, Mode m,
+                           uint8_t* d_out, cudaStream_t st) {
+    if (!n) return;
+    const int blocks = int(std::min<uint64_t>((n + 255) / 256, uint64_t(s->n_sm) * 64));
+    const bool tr = s->d.has_transmissive != 0;
+#define CALL(F, O)                                                                                                   \
+    if (tr) k_occluded_batch<true, F, O><<<blocks, 256, 0, st>>>(s->d, d_rays, d_maxt, n, eps, bias, d_out);         \
+    else k_occluded_batch<false, F, O><<<blocks, 256, 0, st>>>(s->d, d_rays, d_maxt, n, eps, bias, d_out)
+    DISPATCH_MODE(m, CALL);
+#undef CALL
+    CK(cudaGetLastError());
+}
+
+__global__ void k_pass_init(PassState* ps, uint32_t n0) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(ps);
+    for (uint32_t i = threadIdx.x; i < sizeof(PassState) / 4; i += blockDim.x) w[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) { ps->pool_count = n0; ps->lv[0] = 0u; ps->lv[1] = n0; }
+}
+// end of a pass: publish the pool usage to pinned host memory and, if the pass is kept, fold its ray counts
+__global__ void k_pass_commit(const PassState* ps, FrameCounters* fc, uint32_t* out) {
+    out[0] = ps->pool_count; out[1] = ps->shadow_count; out[2] = ps->overflow; out[3] = 0u;
+    if (ps->overflow) return;
+    fc->primary += ps->pc.primary; fc->primary_hits += ps->pc.primary_hits;
+    fc->shadow += ps->pc.shadow; fc->shadow_hits += ps->pc.shadow_hits;
+    fc->secondary += ps->pc.secondary; fc->secondary_hits += ps->pc.secondary_hits;
+}
+
+struct Rect { uint32_t x0, y0, x1, y1; };
+
+Rect rect_of(const rt_scene* s, const rt_params& p) {
+    Rect r{p.x0, p.y0, p.x1 ? p.x1 : s->host.width, p.y1 ? p.y1 : s->host.height};
+    r.x1 = std::min(r.x1, s->host.width); r.y1 = std::min(r.y1, s->host.height);
+    if (r.x0 >= r.x1 || r.y0 >= r.y1) throw rt_error(RT_ERR_BAD_ARG, "empty tile rectangle");
+    return r;
+}
+
+FrameParams frame_params(const rt_scene* s, const rt_params& p, const Rect& r) {
+    FrameParams fp{};
+    // utils/convert.hpp:3-6 with F = double, then tan(fov_rad / 2) (render.hpp:55-57): host libm, as the reference
+    const double fov_rad = p.fov_degrees * (3.14159265358979323846 / 180.);
+    fp.tan_half_fov = std::tan(fov_rad / double(2.0f));
+    fp.eps = p.epsilon; fp.shadow_bias = p.shadow_bias; fp.reflection_bias = p.reflection_bias; fp.refraction_bias = p.refraction_bias;
+    fp.max_ray_depth = p.max_ray_depth; fp.gi_rays = p.diffuse_reflection_ray_count; fp.seed = p.seed;
+    fp.spp_total = p.spp_total ? p.spp_total : p.samples_per_pixel;
+    fp.x0 = r.x0; fp.y0 = r.y0; fp.tw = r.x1 - r.x0; fp.th = r.y1 - r.y0;
+    fp.tiles_x = (fp.tw + 7) / 8;
+    const uint64_t plane = uint64_t(fp.tiles_x) * ((fp.th + 3) / 4) * 32;
+    if (plane >= (1ull << 31)) throw rt_error(RT_ERR_BAD_ARG, "tile too large");
+    fp.plane = uint32_t(plane);
+    (void)s;
+    return fp;
+}
+
+void check_params(const rt_params& p) {
+    if (p.samples_per_pixel == 0) throw rt_error(RT_ERR_BAD_ARG, "samples_per_pixel == 0");
+    if (p.max_ray_depth > 64) throw rt_error(RT_ERR_BAD_ARG, "max_ray_depth > 64");
+    if (p.diffuse_reflection_ray_count > 1024) throw rt_error(RT_ERR_BAD_ARG, "diffuse_reflection_ray_count > 1024");
+}
+
+// levels a frame can reach: without a reflective / refractive material and without GI only level 0 has rays
+uint32_t level_count(const rt_scene* s, const rt_params& p) {
+    bool spawns = p.diffuse_reflection_ray_count > 0;
+    for (const auto& m : s->host.materials) spawns = spawns || m.kind == RT_MAT_REFLECTIVE || m.kind == RT_MAT_REFRACTIVE;
+    return spawns ? p.max_ray_depth + 1 : 1;
+}
+
+constexpr uint64_t PRIMARY_BUDGET = 1ull << 23;     // level-0 entries per pass
+
+// One frame (or tile / sample slice of one) into a device framebuffer of height*width*3 floats.
+void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t st) {
+    check_params(p);
+    const Rect rect = rect_of(s, p);
+    FrameParams fp = frame_params(s, p, rect);
+    const Mode m = mode_of(p.flags);
+    const bool has_gi = fp.gi_rays > 0;
+    const uint32_t levels = level_count(s, p);
+    const bool raw = (p.flags & RT_FLAG_RAW_SUM) != 0;
+
+    // finish the bookkeeping of the previous frame before its events are reused
+    if (s->counters_pending) { rt_counters c; rt_get_counters(s, &c); }
+    s->events_used = 0; s->spans.clear();
+    s->launches = 0; s->passes = 0; s->pool_hwm = 0; s->shadow_hwm = 0;
+    CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
+    CK(cudaEventRecord(s->frame_a, st));
+
+    const uint32_t spp = p.samples_per_pixel;
+    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp, PRIMARY_BUDGET / fp.plane)));
+    auto timed = [&](int cls, auto&& launch) {
+        rt_scene::Span sp{s->next_event(), s->next_event(), cls};
+        CK(cudaEventRecord(sp.a, st));
+        launch();
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(sp.b, st));
+        s->spans.push_back(sp);
+        ++s->launches;
+    };
+
+    int (&g_primary)[4] = s->g_primary, (&g_trace)[4] = s->g_trace, (&g_shadow)[8] = s->g_shadow, (&g_shade)[2] = s->g_shade;
+    int& g_resolve = s->g_resolve;                                                   // persistent grid sizes
+    const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0);
+    const bool tr = s->d.has_transmissive != 0;
+    if (!g_resolve) g_resolve = grid_for(s, k_resolve);
+    if (!g_shade[has_gi]) g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
+#define CALL(F, O)                                                                         \
+    if (!g_primary[mi]) g_primary[mi] = grid_for(s, k_primary<F, O>);                      \
+    if (!g_trace[mi]) g_trace[mi] = grid_for(s, k_trace_level<F, O>);                      \
+    if (!g_shadow[mi * 2 + tr]) g_shadow[mi * 2 + tr] = tr ? grid_for(s, k_shadow<true, F, O>) : grid_for(s, k_shadow<false, F, O>)
+    DISPATCH_MODE(m, CALL);
+#undef CALL
+
+    uint32_t done = 0;
+    while (done < spp) {
+        const uint32_t ns = std::min(per_pass, spp - done);
+        fp.n_samples = ns;
+        fp.sample_first = p.sample_offset + done;
+        const uint64_t n0 = uint64_t(fp.plane) * ns;
+        for (int attempt = 0;; ++attempt) {
+            const uint64_t pool_cap = std::max<uint64_t>(uint64_t(double(n0) * (levels > 1 ? s->pool_factor : 1.0)) + 1024, n0);
+            const uint64_t shadow_cap = uint64_t(double(n0) * s->shadow_factor * std::max<size_t>(s->host.lights.size(), 1)) + 1024;
+            if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
+            s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
+            fp.pool_cap = uint32_t(std::min<uint64_t>(s->rays.cap, 0xFFFFFFFFull));
+            fp.shadow_cap = uint32_t(std::min<uint64_t>(s->jobs.cap, 0xFFFFFFFFull));
+
+            int slot = 0;
+            k_pass_init<<<1, 256, 0, st>>>(s->ps, uint32_t(n0));
+            CK(cudaGetLastError());
+            timed(TC_PRIMARY, [&] {
+#define CALL(F, O) k_primary<F, O><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot)
+                DISPATCH_MODE(m, CALL);
+#undef CALL
+            });
+            ++slot;
+            for (uint32_t lvl = 0; lvl < levels; ++lvl) {
+                if (lvl > 0) {
+                    timed(TC_SECONDARY, [&] {
+#define CALL(F, O) k_trace_level<F, O><<<g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot)
+                        DISPATCH_MODE(m, CALL);
+#undef CALL
+                    });
+                    ++slot;
+                }
+                timed(TC_SHADE, [&] {
+                    if (has_gi) k_shade<true><<<g_shade[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
+                    else k_shade<false><<<g_shade[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
+                });
+                ++slot;
+            }
+            if (!s->host.lights.empty()) {
+                timed(TC_SHADOW, [&] {
+#define CALL(F, O)                                                                                               \
+    if (tr) k_shadow<true, F, O><<<g_shadow[mi * 2 + 1], 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);  \
+    else k_shadow<false, F, O><<<g_shadow[mi * 2], 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot)
+                    DISPATCH_MODE(m, CALL);
+#undef CALL
+                });
+                ++slot;
+            }
+            for (int lvl = int(levels) - 1; lvl >= 0; --lvl) {
+                timed(TC_RESOLVE, [&] { k_resolve<<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot); });
+                ++slot;
+            }
+            k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, s->h_flags);
+            CK(cudaGetLastError());
+            // the accumulate kernel skips itself on the device when the pass overflowed its pools
+            timed(TC_RESOLVE, [&] {
+                k_accumulate<<<(fp.plane + 255) / 256, 256, 0, st>>>(s->d, fp, s->recs.p, d_rgb, s->ps, done == 0 ? 1 : 0,
+                                                                      (!raw && done + ns == spp) ? 1 : 0);
+            });
+            CK(cudaStreamSynchronize(st));
+            const uint64_t used_pool = s->h_flags[0], used_shadow = s->h_flags[1];
+            if (s->h_flags[2] == 0) {
+                s->pool_hwm = std::max(s->pool_hwm, used_pool);
+                s->shadow_hwm = std::max(s->shadow_hwm, used_shadow);
+                break;
+            }
+            if (attempt >= 24) throw rt_error(RT_ERR_OOM, "wavefront pools keep overflowing");
+            // the counts of a truncated pass are lower bounds: grow past them and render the pass again (it is deterministic)
+            if (s->h_flags[2] & 1u) s->pool_factor = std::max(s->pool_factor * 1.5, double(used_pool) / double(n0) * 1.25);
+            if (s->h_flags[2] & 2u)
+                s->shadow_factor = std::max(s->shadow_factor * 1.5, double(used_shadow) / double(n0 * std::max<size_t>(s->host.lights.size(), 1)) * 1.25);
+        }
+        done += ns;
+        ++s->passes;
+    }
+    CK(cudaEventRecord(s->frame_b, st));
+    CK(cudaMemcpyAsync(s->h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    s->counters_pending = true;
+}
+
+}  // namespace
+
+// ======================================================================================================================
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+const char* rt_status_string(int status) {
+    switch (status) {
+        case RT_OK: return "ok";
+        case RT_ERR_BAD_ARG: return "bad argument";
+        case RT_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+        case RT_ERR_CUDA: return "CUDA runtime error";
+        case RT_ERR_IO: return "i/o error";
+        case RT_ERR_PARSE: return "parse error";
+        case RT_ERR_OOM: return "out of memory";
+        case RT_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+const char* rt_last_error(void) { return g_last_error.c_str(); }
+
+void rt_default_build_opts(rt_build_opts* o) {
+    if (!o) return;
+    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0;
+}
+
+void rt_default_params(rt_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->fov_degrees = 90.;
+    p->epsilon = float(1e-6);
+    p->shadow_bias = float(1e-4); p->reflection_bias = float(1e-4); p->refraction_bias = float(1e-4);
+    p->samples_per_pixel = 1; p->max_ray_depth = 5; p->diffuse_reflection_ray_count = 0; p->seed = 42;
+}
+
+int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_scene** out) {
+    if (!desc) return fail(RT_ERR_BAD_ARG, "null scene description");
+    return create_with([&] { return scene_from_desc(*desc); }, opts, out);
+}
+
+int rt_scene_create_from_crtscene(const char* path, const char* asset_root, const rt_build_opts* opts, rt_scene** out) {
+    if (!path) return fail(RT_ERR_BAD_ARG, "null path");
+    return create_with([&] { return scene_from_crtscene(path, asset_root ? asset_root : ""); }, opts, out);
+}
+
+int rt_scene_create_from_rtsc(const void* bytes, uint64_t n_bytes, const rt_build_opts* opts, rt_scene** out) {
+    if (!bytes) return fail(RT_ERR_BAD_ARG, "null buffer");
+    return create_with([&] { return scene_from_rtsc(bytes, n_bytes); }, opts, out);
+}
+
+void rt_scene_destroy(rt_scene* s) { delete s; }
+
+int rt_scene_get_info(const rt_scene* s, rt_scene_info* info) {
+    if (!s || !info) return fail(RT_ERR_BAD_ARG, "null argument");
+    *info = s->info;
+    return RT_OK;
+}
+
+int rt_scene_get_tree(const rt_scene* s, uint64_t* node5, float* boxes, uint32_t* refs) {
+    if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
+    const auto& nodes = s->tree.nodes;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const KdNode& n = nodes[i];
+        if (node5) { node5[5 * i] = n.parent; node5[5 * i + 1] = n.child0; node5[5 * i + 2] = n.child1; node5[5 * i + 3] = n.first_ref; node5[5 * i + 4] = n.first_ref == KD_NONE ? 0 : n.ref_count; }
+        if (boxes) { std::memcpy(boxes + 6 * i, n.bmin, 12); std::memcpy(boxes + 6 * i + 3, n.bmax, 12); }
+    }
+    if (refs && !s->tree.refs.empty()) std::memcpy(refs, s->tree.refs.data(), s->tree.refs.size() * 4);
+    return RT_OK;
+}
+
+int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets) {
+    if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
+    if (nodes8) std::memcpy(nodes8, s->layout.nodes8.data(), s->layout.nodes8.size() * 4);
+    if (packets) std::memcpy(packets, s->layout.packets.data(), size_t(s->layout.n_packets) * PACKET_WORDS * 4);
+    return RT_OK;
+}
+
+int rt_scene_get_geometry(const rt_scene* s, float* tri9, float* face_normals, float* vertex_normals) {
+    if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
+    const auto& tris = s->geom.tris;
+    for (size_t i = 0; i < tris.size(); ++i) {
+        if (tri9) { std::memcpy(tri9 + 9 * i, tris[i].v0, 12); std::memcpy(tri9 + 9 * i + 3, tris[i].e1, 12); std::memcpy(tri9 + 9 * i + 6, tris[i].e2, 12); }
+        if (face_normals) std::memcpy(face_normals + 3 * i, tris[i].normal, 12);
+    }
+    if (vertex_normals && !s->geom.vertex_normals.empty())
+        std::memcpy(vertex_normals, s->geom.vertex_normals.data(), s->geom.vertex_normals.size() * 4);
+    return RT_OK;
+}
+
+int rt_trace_closest_device(rt_scene* s, const float* d_rays, uint64_t n, int backface_culling, float epsilon, uint32_t flags,
+                            rt_hit* d_hits, void* stream) {
+    return guarded([&] {
+        require_device(s);
+        if (n && (!d_rays || !d_hits)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        CK(cudaSetDevice(s->device));
+        static_assert(sizeof(rt_hit) == sizeof(Hit), "rt_hit layout");
+        launch_trace_batch(s, d_rays, n, backface_culling != 0, epsilon, mode_of(flags), reinterpret_cast<Hit*>(d_hits),
+                           stream ? static_cast<cudaStream_t>(stream) : s->stream);
+        return RT_OK;
+    });
+}
+
+int rt_trace_occluded_device(rt_scene* s, const float* d_rays, const float* d_max_t, uint64_t n, float epsilon, float shadow_bias,
+                             uint32_t flags, uint8_t* d_occluded, void* stream) {
+    return guarded([&] {
+        require_device(s);
+        if (n && (!d_rays || !d_max_t || !d_occluded)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        CK(cudaSetDevice(s->device));
+        launch_occluded_batch(s, d_rays, d_max_t, n, epsilon, shadow_bias, mode_of(flags), d_occluded,
+                              stream ? static_cast<cudaStream_t>(stream) : s->stream);
+        return RT_OK;
+    });
+}
+
+int rt_trace_closest(rt_scene* s, const float* rays, uint64_t n, int backface_culling, float epsilon, uint32_t flags, rt_hit* hits) {
+    return guarded([&] {
+        require_device(s);
+        if (n && (!rays || !hits)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        if (!n) return int(RT_OK);
+        std::lock_guard<std::mutex> lock(s->mtx);    // called concurrently by the reference's tile workers (render.hpp:93-101)
+        CK(cudaSetDevice(s->device));
+        s->q_rays.reserve(6 * n); s->q_hits.reserve(n);
+        CK(cudaMemcpyAsync(s->q_rays.p, rays, 24 * n, cudaMemcpyHostToDevice, s->stream));
+        launch_trace_batch(s, s->q_rays.p, n, backface_culling != 0, epsilon, mode_of(flags), s->q_hits.p, s->stream);
+        CK(cudaMemcpyAsync(hits, s->q_hits.p, sizeof(Hit) * n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return int(RT_OK);
+    });
+}
+
+int rt_trace_occluded(rt_scene* s, const float* rays, const float* max_t, uint64_t n, float epsilon, float shadow_bias, uint32_t flags,
+                      uint8_t* occluded) {
+    return guarded([&] {
+        require_device(s);
+        if (n && (!rays || !max_t || !occluded)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        if (!n) return int(RT_OK);
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        s->q_rays.reserve(6 * n); s->q_maxt.reserve(n); s->q_occ.reserve(n);
+        CK(cudaMemcpyAsync(s->q_rays.p, rays, 24 * n, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->q_maxt.p, max_t, 4 * n, cudaMemcpyHostToDevice, s->stream));
+        launch_occluded_batch(s, s->q_rays.p, s->q_maxt.p, n, epsilon, shadow_bias, mode_of(flags), s->q_occ.p, s->stream);
+        CK(cudaMemcpyAsync(occluded, s->q_occ.p, n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return int(RT_OK);
+    });
+}
+
+int rt_render_frame_device(rt_scene* s, const rt_params* p, float* d_rgb, void* stream) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !d_rgb) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        render_device(s, *p, d_rgb, stream ? static_cast<cudaStream_t>(stream) : s->stream);
+        return int(RT_OK);
+    });
+}
+
+int rt_render_frame(rt_scene* s, const rt_params* p, float* rgb) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !rgb) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        const size_t n = size_t(s->host.width) * s->host.height * 3;
+        s->fb.reserve(n);
+        const Rect r = rect_of(s, *p);
+        render_device(s, *p, s->fb.p, s->stream);
+        // only the tile rectangle is defined on the device and only it is written to the caller's image
+        const size_t row_bytes = size_t(r.x1 - r.x0) * 12;
+        CK(cudaMemcpy2DAsync(rgb + (size_t(r.y0) * s->host.width + r.x0) * 3, size_t(s->host.width) * 12,
+                             s->fb.p + (size_t(r.y0) * s->host.width + r.x0) * 3, size_t(s->host.width) * 12, row_bytes, r.y1 - r.y0,
+                             cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return int(RT_OK);
+    });
+}
+
+int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !rgb8) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        if (p->flags & RT_FLAG_RAW_SUM) throw rt_error(RT_ERR_BAD_ARG, "RT_FLAG_RAW_SUM cannot be quantised");
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        const size_t n = size_t(s->host.width) * s->host.height * 3;
+        s->fb.reserve(n); s->fb8.reserve(n);
+        const Rect r = rect_of(s, *p);
+        render_device(s, *p, s->fb.p, s->stream);
+        const size_t first = size_t(r.y0) * s->host.width * 3, count = size_t(r.y1 - r.y0) * s->host.width * 3;
+        k_quantise<<<unsigned((count + 255) / 256), 256, 0, s->stream>>>(s->fb.p + first, s->fb8.p + first, count);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy2DAsync(rgb8 + (size_t(r.y0) * s->host.width + r.x0) * 3, size_t(s->host.width) * 3,
+                             s->fb8.p + (size_t(r.y0) * s->host.width + r.x0) * 3, size_t(s->host.width) * 3, size_t(r.x1 - r.x0) * 3,
+                             r.y1 - r.y0, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return int(RT_OK);
+    });
+}
+
+int rt_trace_primary(rt_scene* s, const rt_params* p, rt_hit* hits) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !hits) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        check_params(*p);
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        const Rect r = rect_of(s, *p);
+        FrameParams fp = frame_params(s, *p, r);
+        fp.n_samples = 1; fp.sample_first = p->sample_offset;
+        const size_t n = size_t(fp.tw) * fp.th;
+        s->q_hits.reserve(n);
+        const Mode m = mode_of(p->flags);
+#define CALL(F, O) k_primary_hits<F, O><<<(fp.plane + 255) / 256, 256, 0, s->stream>>>(s->d, fp, s->q_hits.p)
+        DISPATCH_MODE(m, CALL);
+#undef CALL
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hits, s->q_hits.p, n * sizeof(Hit), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return int(RT_OK);
+    });
+}
+
+int rt_get_counters(rt_scene* s, rt_counters* c) {
+    return guarded([&] {
+        require_device(s);
+        if (!c) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        if (s->counters_pending) {
+            CK(cudaSetDevice(s->device));
+            CK(cudaEventSynchronize(s->frame_b));
+            CK(cudaDeviceSynchronize());
+            rt_counters k{};
+            k.primary = s->h_fc->primary; k.primary_hits = s->h_fc->primary_hits;
+            k.shadow = s->h_fc->shadow; k.shadow_hits = s->h_fc->shadow_hits;
+            k.secondary = s->h_fc->secondary; k.secondary_hits = s->h_fc->secondary_hits;
+            k.nodes_pool = s->pool_hwm; k.shadow_pool = s->shadow_hwm;
+            k.kernel_launches = s->launches; k.passes = s->passes;
+            CK(cudaEventElapsedTime(&k.ms_total, s->frame_a, s->frame_b));
+            float by_class[TC_N] = {0, 0, 0, 0, 0};
+            for (const auto& sp : s->spans) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+                by_class[sp.cls] += ms;
+            }
+            k.ms_primary = by_class[TC_PRIMARY]; k.ms_secondary = by_class[TC_SECONDARY]; k.ms_shadow = by_class[TC_SHADOW];
+            k.ms_shade = by_class[TC_SHADE]; k.ms_resolve = by_class[TC_RESOLVE];
+            s->counters = k;
+            s->counters_pending = false;
+        }
+        *c = s->counters;
+        return int(RT_OK);
+    });
+}
+
+int rt_resolve_sum_device(rt_scene* s, const float* d_sum, uint32_t spp_total, float* d_rgb_out, uint8_t* d_rgb8_out, void* stream) {
+    return guarded([&] {
+        require_device(s);
+        if (!d_sum || spp_total == 0) throw rt_error(RT_ERR_BAD_ARG, "bad argument");
+        CK(cudaSetDevice(s->device));
+        const size_t n = size_t(s->host.width) * s->host.height * 3;
+        k_resolve_sum<<<unsigned((n + 255) / 256), 256, 0, stream ? static_cast<cudaStream_t>(stream) : s->stream>>>(
+            d_sum, float(spp_total), d_rgb_out, d_rgb8_out, n);
+        CK(cudaGetLastError());
+        return int(RT_OK);
+    });
+}
+
+}  // extern "C"
