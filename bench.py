@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py - Mrays/s and ms/frame of the kd_tree_simd_accel hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--mode exact|ordered|fast|fast+ordered]
+    python bench.py --impl reference ...      the reference's own CPU path (oracle/_ref, else the oracle port) on the host cores
+
+A step = one frame of the workload through the whole wavefront (ray generation, primary / secondary / shadow closest-hit
+queries, shading, resolve).  Default workload = BASELINE.json configs[1]: scenes/hw09/scene5.crtscene, 1920x1080, 1 spp,
+max_ray_depth 5 (2,073,600 primary + 652,885 shadow/reflection queries per frame).
+
+value  : all closest-hit queries of the K timed frames / device time (CUDA events on the launching stream, L2 flushed
+         between frames outside the events); scene resident in HBM, frame left in HBM.
+e2e    : the same frames through rt_render_frame (include/rt_b200.h) with a pinned HOST framebuffer - params in, frame out,
+         wall clock around the C-ABI call (what src/main.cpp:16-20 of the reference times).
+N > 1  : one process per GPU, scene replicated, each rank renders its own sample of every pixel (weak scaling: the N-GPU
+         job is the same frame at spp = N), framebuffers combined by ONE NCCL reduce(sum) + the fused divide/quantise
+         kernel on rank 0; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import importlib
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    "cfg1": "cfg1_hw15_scene2", "cfg2": "cfg2_hw09_scene5", "cfg3": "cfg3_hw11_scene8_d10", "cfg3d5": "cfg3_hw11_scene8_d5",
+    "cfg4": "cfg4_hw12_scene4",
+}
+MODES = {"exact": 0, "fast": 2, "ordered": 4, "fast+ordered": 6}
+
+
+def load_workload(name: str) -> dict:
+    with open(os.path.join(REPO, "tests", "golden", "workloads.json")) as fh:
+        w = json.load(fh)[WORKLOADS[name]]
+    w["key"] = WORKLOADS[name]
+    with gzip.open(os.path.join(REPO, "tests", "golden", "scenes", w["scene"] + ".rtsc.gz"), "rb") as fh:
+        w["rtsc"] = fh.read()
+    return w
+
+
+def measured_peaks() -> tuple[dict, str]:
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except OSError:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (NVML; falls back to nvidia-smi)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "display_clock_setting": 0x100}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.reasons |= {k for k, bit in names.items() if r & bit}
+                time.sleep(0.02)
+        except Exception:  # noqa: BLE001
+            import subprocess
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                                   "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                                   "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                                   "--format=csv,noheader,nounits"], text=True, timeout=5).strip().split(", ")
+                    self.samples.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+                    for k, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:]):
+                        if v.strip() == "Active":
+                            self.reasons.add(k)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.1)
+
+    def __enter__(self):
+        self._th.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._th.join(timeout=10)
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on the host cores
+# ------------------------------------------------------------------------------------------------------------------------
+def cpu_reference_frames(w: dict, frames: int, warmup: int) -> dict:
+    """Times `frames` full frames of the workload with the UNMODIFIED reference compiled into oracle/_ref (speed build:
+    -O3, FMA contraction on, widest ISA the host has; all host threads, BUCKET_TILES), falling back to the oracle port.
+    This is the one place bench.py executes oracle/ code, as the baseline - never as the thing measured."""
+    from tests.helpers import refimpl
+    rays = w["rays"]
+    variant = dict(fp="speed", isa="v4" if refimpl.cpu_has_avx512() else "v3", spp=w["spp"], depth=w["max_ray_depth"], gi=w["gi_rays"])
+    if not refimpl.available(**variant):
+        variant = dict(fp="speed", isa="v3", spp=w["spp"], depth=w["max_ray_depth"], gi=w["gi_rays"])
+    if not refimpl.available(**variant):
+        variant = dict(fp="canon", isa="v3", spp=w["spp"], depth=w["max_ray_depth"], gi=w["gi_rays"])
+    times = []
+    if refimpl.available(**variant):
+        with tempfile.NamedTemporaryFile(suffix=".rtsc") as tf:
+            tf.write(w["rtsc"])
+            tf.flush()
+            ref = refimpl.RefImpl(tf.name, **variant)
+            for i in range(warmup + frames):
+                _, sec = ref.render(want_image=False)
+                if i >= warmup:
+                    times.append(sec)
+            kind, cores = "reference", ref.threads
+            sample = (f"{frames} full frames of {w['key']} by render_frame(BUCKET_TILES) of the reference headers "
+                      f"({os.path.basename(ref.path)}, W={ref.W}), wall clock around render_frame as src/main.cpp:16-20")
+            ref.close()
+    else:
+        from tests.helpers import oracle
+        o = oracle.Oracle(w["rtsc"])
+        p = oracle.default_params(spp=w["spp"], max_ray_depth=w["max_ray_depth"], gi_rays=w["gi_rays"])
+        for i in range(warmup + frames):
+            t0 = time.perf_counter()
+            o.render(p)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind, cores = "port", os.cpu_count()
+        sample = f"{frames} full frames of {w['key']} by oracle/rt_oracle.c (C port, all host threads); oracle/_ref was not built"
+    mean = sum(times) / len(times)
+    return {"value": rays / mean / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": kind, "sample": sample,
+            "ms_per_frame": 1e3 * mean, "ms_per_frame_best": 1e3 * min(times)}
+
+
+def run_reference_arm(args, w: dict) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference_frames(w, max(args.steps, 1), max(args.warmup, 1))
+    line = {"impl": "reference", "metric": "Mrays/s", "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic camera rays over the reference's own scene file (fixture copy)",
+            "config": workload_config(w, args, int(os.environ.get("WORLD_SIZE", "1"))),
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w: dict, args, world: int) -> dict:
+    return {"workload": f"{w['key']}: scenes/{w['scene'].replace('_', '/', 1)}.crtscene {w['width']}x{w['height']}, "
+                        f"spp {w['spp']} per GPU, max_ray_depth {w['max_ray_depth']}, gi_rays {w['gi_rays']}, kd<8,64>",
+            "rays_per_frame_per_gpu": w["rays"], "mode": args.mode, "sharding": "replicated scene, 1 sample slice per GPU" if world > 1 else "none",
+            "l2": "flushed between timed frames (256 MiB write, outside the CUDA events)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="exact", choices=sorted(MODES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = load_workload(args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the backend has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt = importlib.import_module("simd-raytracer_b200")
+    scene = rt.Scene.from_rtsc(w["rtsc"], device=local)
+    H, W = scene.height, scene.width
+    flags = MODES[args.mode]
+    spp_total = w["spp"] * world
+    first, count = rt.spp_slice(spp_total, rank, world)
+    params = rt.default_params(samples_per_pixel=count, sample_offset=first, spp_total=spp_total, max_ray_depth=w["max_ray_depth"],
+                               diffuse_reflection_ray_count=w["gi_rays"], flags=flags | (rt.FLAG_RAW_SUM if world > 1 else 0))
+    stream = torch.cuda.current_stream()
+    fb = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    rgb8 = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+    host = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def frame_device():
+        scene.render_frame_device(params, fb.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
+            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                scene.resolve_sum_device(fb.data_ptr(), spp_total, d_rgb=fb.data_ptr(), d_rgb8=rgb8.data_ptr(), stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        frame_device()
+    barrier()
+    c0 = scene.counters()
+    rays_frame = c0.primary + c0.shadow + c0.secondary
+
+    # ---- timed: device ------------------------------------------------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    acc = {k: 0.0 for k in ("ms_primary", "ms_secondary", "ms_shadow", "ms_shade", "ms_resolve", "ms_total")}
+    launches = 0
+    barrier()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(stream)
+            frame_device()
+            b.record(stream)
+            c = scene.counters()            # blocks until the frame is done; reads the per-class CUDA events of this frame
+            for k in acc:
+                acc[k] += getattr(c, k)
+            launches += c.kernel_launches + (1 if world > 1 and rank == 0 else 0)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- timed: end to end through the C ABI with a host framebuffer (rank-local frame; N>1 adds the reduce above) -------
+    e2e_params = rt.default_params(samples_per_pixel=count, sample_offset=first, spp_total=spp_total, max_ray_depth=w["max_ray_depth"],
+                                   diffuse_reflection_ray_count=w["gi_rays"], flags=flags)
+    host_np = host.numpy()
+    for _ in range(3):
+        scene.render_frame(e2e_params, out=host_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scene.render_frame(e2e_params, out=host_np)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    t = torch.tensor([ms_dev, t_e2e, float(rays_frame)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_dev, t_e2e, rays_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        rays_all = float(rays_frame)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        K = args.steps
+        ms_step = ms_dev / K
+        kinds = w["kinds"]
+        cls = {"primary": acc["ms_primary"] / K, "secondary": acc["ms_secondary"] / K, "shadow": acc["ms_shadow"] / K}
+        dom = max(cls, key=cls.get)
+        # dominant kernel = the trace kernel class with the largest share of the frame; algorithmic bytes = the REFERENCE
+        # algorithm's node + triangle fetches for that ray kind (tests/golden/workloads.json)
+        dom_kernel = {"primary": "k_primary", "secondary": "k_trace_level", "shadow": "k_shadow"}[dom]
+        n_dom_launch = {"primary": 1, "secondary": max(1, w["max_ray_depth"]), "shadow": 1}[dom]
+        ach = kinds[dom]["alg_bytes"] / (cls[dom] * 1e-3) / 1e9 if cls[dom] > 0 else 0.0
+        fp32_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12          # T FP32 instr/s
+        line = {
+            "metric": "Mrays/s", "value": rays_all * K / (ms_dev * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic camera rays over the reference's own scene file (fixture copy)",
+            "config": workload_config(w, args, world),
+            "rays": {"primary_per_frame": int(c0.primary), "shadow_per_frame": int(c0.shadow), "secondary_per_frame": int(c0.secondary),
+                     "primary_mrays_s": c0.primary / cls["primary"] / 1e3 if cls["primary"] else None,
+                     "shadow_mrays_s": c0.shadow / cls["shadow"] / 1e3 if cls["shadow"] else None,
+                     "secondary_mrays_s": c0.secondary / cls["secondary"] / 1e3 if cls["secondary"] else None,
+                     "ms": {k: v / K for k, v in acc.items()}},
+            "e2e": {"value": rays_all * K / t_e2e / 1e6, "unit": "Mrays/s", "ms_per_frame": 1e3 * t_e2e / K,
+                    "h2d_bytes_per_step": int(np.dtype(np.uint8).itemsize * __import__("ctypes").sizeof(rt.Params)),
+                    "d2h_bytes_per_step": int(host.numel() * 4), "api": "rt_render_frame (host float framebuffer, pinned)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "launches_per_frame": n_dom_launch, "algorithmic_bytes_per_frame": kinds[dom]["alg_bytes"],
+                         "note": "algorithmic bytes = reference algorithm's 8 B/node + 36 B/triangle-test + ray/hit I/O for this ray "
+                                 "kind; the scene (<1 MB) is L1/L2-resident, so these bytes are served on-chip and DRAM traffic is "
+                                 "only the ray/hit/record streams - see roofline_fp32 for the issue-rate view"},
+            "roofline_fp32": {"kernel": dom_kernel, "achieved": kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12 if cls[dom] else 0.0,
+                              "peak": fp32_peak, "unit": "T FP32 op/s (no FMA in exact mode)",
+                              "frac": (kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12) / fp32_peak if cls[dom] else 0.0},
+            "clocks": clocks.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base = cpu_reference_frames(w, frames=20, warmup=2)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["ms_per_frame"] = base["ms_per_frame"]
+        print(json.dumps(line), flush=True)
+    scene.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

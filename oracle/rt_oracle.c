@@ -472,8 +472,10 @@ typedef struct {
 } ctx_t;
 
 static inline cand_t query(ctx_t* c, const ray* r, int cull, uint32_t kind) {
+    const uint64_t nodes_before = c->counts[6], tests_before = c->counts[7];
     const cand_t h = closest_hit(c->s, r, cull, c->p->eps, c->counts);
     const int slot = kind == RO_KIND_PRIMARY ? 0 : (kind == RO_KIND_SHADOW ? 2 : 4);
+    if (slot) { c->counts[6 + slot] += c->counts[6] - nodes_before; c->counts[7 + slot] += c->counts[7] - tests_before; }
     c->counts[slot]++;
     if (h.hit) c->counts[slot + 1]++;
     if (c->log && c->log_n < c->log_cap) {

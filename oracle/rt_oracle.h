@@ -51,8 +51,11 @@ typedef struct ro_record {
 } ro_record;
 
 /* counts[]: 0 primary, 1 primary hits, 2 shadow queries, 3 shadow-query hits, 4 secondary (reflect+refract+GI),
- *           5 secondary hits, 6 node visits (slab tests), 7 triangle tests (real, unpadded) */
-enum { RO_N_COUNTS = 8 };
+ *           5 secondary hits, 6 node visits (slab tests), 7 triangle tests (real, unpadded) - all kinds;
+ *           8 / 9 node visits / triangle tests of the shadow queries, 10 / 11 of the secondary queries
+ *           (primary = total - shadow - secondary).  These are the reference algorithm's own work counts: the
+ *           fixed denominators of the roofline. */
+enum { RO_N_COUNTS = 12 };
 
 void ro_default_params(ro_params* p);
 

@@ -139,6 +139,14 @@ def _load():
 lib = _load()
 
 
+def _stream(stream):
+    """None -> the scene's own stream (C ABI: null).  An integer is a cudaStream_t; 0 is CUDA's legacy default stream,
+    which the C ABI cannot tell from "none", so it is passed as cudaStreamLegacy (0x1)."""
+    if stream is None:
+        return None
+    return C.c_void_p(1 if int(stream) == 0 else int(stream))
+
+
 def _check(status: int) -> None:
     if status != RT_OK:
         raise RtError(status, (lib.rt_last_error() or b"").decode(errors="replace"))
@@ -299,13 +307,13 @@ class Scene:
         return out
 
     def trace_closest_device(self, d_rays: int, n: int, cull: bool, d_hits: int, eps: float = np.float32(1e-6), flags: int = 0,
-                             stream: int = 0) -> None:
-        _check(lib.rt_trace_closest_device(self.h, d_rays, n, 1 if cull else 0, C.c_float(eps), flags, d_hits, stream or None))
+                             stream: int | None = None) -> None:
+        _check(lib.rt_trace_closest_device(self.h, d_rays, n, 1 if cull else 0, C.c_float(eps), flags, d_hits, _stream(stream)))
 
     def trace_occluded_device(self, d_rays: int, d_max_t: int, n: int, d_out: int, eps: float = np.float32(1e-6),
-                              shadow_bias: float = np.float32(1e-4), flags: int = 0, stream: int = 0) -> None:
+                              shadow_bias: float = np.float32(1e-4), flags: int = 0, stream: int | None = None) -> None:
         _check(lib.rt_trace_occluded_device(self.h, d_rays, d_max_t, n, C.c_float(eps), C.c_float(shadow_bias), flags, d_out,
-                                            stream or None))
+                                            _stream(stream)))
 
     def trace_primary(self, params: Params | None = None) -> np.ndarray:
         p = params or default_params()
@@ -328,11 +336,11 @@ class Scene:
         _check(lib.rt_render_frame_rgb8(self.h, C.byref(p), img.ctypes.data))
         return img
 
-    def render_frame_device(self, params: Params, d_rgb: int, stream: int = 0) -> None:
-        _check(lib.rt_render_frame_device(self.h, C.byref(params), d_rgb, stream or None))
+    def render_frame_device(self, params: Params, d_rgb: int, stream: int | None = None) -> None:
+        _check(lib.rt_render_frame_device(self.h, C.byref(params), d_rgb, _stream(stream)))
 
-    def resolve_sum_device(self, d_sum: int, spp_total: int, d_rgb: int = 0, d_rgb8: int = 0, stream: int = 0) -> None:
-        _check(lib.rt_resolve_sum_device(self.h, d_sum, spp_total, d_rgb or None, d_rgb8 or None, stream or None))
+    def resolve_sum_device(self, d_sum: int, spp_total: int, d_rgb: int = 0, d_rgb8: int = 0, stream: int | None = None) -> None:
+        _check(lib.rt_resolve_sum_device(self.h, d_sum, spp_total, d_rgb or None, d_rgb8 or None, _stream(stream)))
 
     def counters(self) -> Counters:
         c = Counters()

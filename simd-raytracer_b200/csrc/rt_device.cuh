@@ -66,46 +66,63 @@ struct Hit { float t, u, v; int tri; };
 // into intersect_leaf's running closest (kd_tree_simd.hpp:266-302).  Using the traversal-wide best_t directly with
 // a strict `<` is equivalent to the reference's leaf-local candidate followed by `c->t < best_t` (:224): in both,
 // the first occurrence of the smallest t strictly below the incoming best wins.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Exact mode computes the reference's expressions in the reference's order, but only for triangles that can still
+// pass: u and v are first estimated with the 1-ulp MUFU reciprocal (relative error of the estimate < 1e-6) and a
+// triangle is dropped when the estimate is outside [0,1] by more than 1e-4 - the exactly rounded value is then
+// outside too, so the outcome is the reference's.  NaN estimates never drop anything (every compare is false).
 template <bool CULL, bool FAST>
 __device__ __forceinline__ void test_lane(float v0x, float v0y, float v0z, float e1x, float e1y, float e1z,
                                           float e2x, float e2y, float e2z, int id, V3 o, V3 d, float eps, Hit& best) {
-    float pvx, pvy, pvz, det;
+    constexpr float M = 1e-4f;
     if (FAST) {
-        pvx = fmaf(d.y, e2z, -(d.z * e2y)); pvy = fmaf(d.z, e2x, -(d.x * e2z)); pvz = fmaf(d.x, e2y, -(d.y * e2x));
-        det = fmaf(e1z, pvz, fmaf(e1y, pvy, e1x * pvx));
-    } else {
-        pvx = d.y * e2z - d.z * e2y;                                                                     // :27
-        pvy = d.z * e2x - d.x * e2z;                                                                     // :28
-        pvz = d.x * e2y - d.y * e2x;                                                                     // :29
-        det = e1x * pvx + e1y * pvy + e1z * pvz;                                                         // :31
+        const float pvx = fmaf(d.y, e2z, -(d.z * e2y)), pvy = fmaf(d.z, e2x, -(d.x * e2z)), pvz = fmaf(d.x, e2y, -(d.y * e2x));
+        const float det = fmaf(e1z, pvz, fmaf(e1y, pvy, e1x * pvx));
+        if (!(CULL ? (eps <= det) : (eps <= fabsf(det)))) return;
+        const float inv_det = __frcp_rn(det);
+        const float tx = o.x - v0x, ty = o.y - v0y, tz = o.z - v0z;
+        const float u = fmaf(tz, pvz, fmaf(ty, pvy, tx * pvx)) * inv_det;
+        if (!((0.0f <= u) & (u <= 1.0f))) return;
+        const float qx = fmaf(ty, e1z, -(tz * e1y)), qy = fmaf(tz, e1x, -(tx * e1z)), qz = fmaf(tx, e1y, -(ty * e1x));
+        const float v = fmaf(d.z, qz, fmaf(d.y, qy, d.x * qx)) * inv_det;
+        if (!((0.0f <= v) & (u + v <= 1.0f))) return;
+        const float t = fmaf(e2z, qz, fmaf(e2y, qy, e2x * qx)) * inv_det;
+        if ((eps < t) & (t < best.t)) { best.t = t; best.u = u; best.v = v; best.tri = id; }
+        return;
     }
-    const bool ok_det = CULL ? (eps <= det) : (eps <= fabsf(det));                                       // :33-38
-    if (!ok_det) return;
-    const float inv_det = FAST ? __frcp_rn(det) : __fdiv_rn(1.0f, det);                                  // :40
+    const float pvx = d.y * e2z - d.z * e2y;                                                             // :27
+    const float pvy = d.z * e2x - d.x * e2z;                                                             // :28
+    const float pvz = d.x * e2y - d.y * e2x;                                                             // :29
+    const float det = e1x * pvx + e1y * pvy + e1z * pvz;                                                 // :31
+    if (!(CULL ? (eps <= det) : (eps <= fabsf(det)))) return;                                            // :33-38
     const float tx = o.x - v0x, ty = o.y - v0y, tz = o.z - v0z;                                          // :42-44
-    float u, v, t, qx, qy, qz;
-    if (FAST) {
-        u = fmaf(tz, pvz, fmaf(ty, pvy, tx * pvx)) * inv_det;
-        qx = fmaf(ty, e1z, -(tz * e1y)); qy = fmaf(tz, e1x, -(tx * e1z)); qz = fmaf(tx, e1y, -(ty * e1x));
-        v = fmaf(d.z, qz, fmaf(d.y, qy, d.x * qx)) * inv_det;
-        t = fmaf(e2z, qz, fmaf(e2y, qy, e2x * qx)) * inv_det;
-    } else {
-        u = (tx * pvx + ty * pvy + tz * pvz) * inv_det;                                                  // :46
-        qx = ty * e1z - tz * e1y;                                                                        // :49
-        qy = tz * e1x - tx * e1z;                                                                        // :50
-        qz = tx * e1y - ty * e1x;                                                                        // :51
-        v = (d.x * qx + d.y * qy + d.z * qz) * inv_det;                                                  // :53
-        t = (e2x * qx + e2y * qy + e2z * qz) * inv_det;                                                  // :56
-    }
+    const float un = tx * pvx + ty * pvy + tz * pvz;                                                     // :46 (numerator)
+    const float r = rcp_approx(det);
+    const float ua = un * r;
+    if ((ua < -M) | (ua > 1.0f + M)) return;
+    const float qx = ty * e1z - tz * e1y;                                                                // :49
+    const float qy = tz * e1x - tx * e1z;                                                                // :50
+    const float qz = tx * e1y - ty * e1x;                                                                // :51
+    const float vn = d.x * qx + d.y * qy + d.z * qz;                                                     // :53 (numerator)
+    const float va = vn * r;
+    if ((va < -M) | (ua + va > 1.0f + 3.0f * M)) return;
+    const float inv_det = __fdiv_rn(1.0f, det);                                                          // :40
+    const float u = un * inv_det;                                                                        // :46
+    const float v = vn * inv_det;                                                                        // :53
+    const float t = (e2x * qx + e2y * qy + e2z * qz) * inv_det;                                          // :56
     const bool ok = (0.0f <= u) & (u <= 1.0f) & (0.0f <= v) & (u + v <= 1.0f) & (eps < t);               // :47,:54,:57
     if (ok && t < best.t) { best.t = t; best.u = u; best.v = v; best.tri = id; }                         // :284-298, :224
 }
 
 template <bool CULL, bool FAST>
 __device__ __forceinline__ void test_packets(const float4* __restrict__ pk, uint32_t count, V3 o, V3 d, float eps,
-                                             Hit& best, float t_stop = -1.0f) {
+                                             Hit& best) {
     for (uint32_t p = 0; p < count; ++p, pk += 10) {
-        if (best.t <= t_stop) return;     // any-hit early out (see occluded_query); never taken for t_stop < 0
         const float4 v0x = __ldg(pk + 0), v0y = __ldg(pk + 1), v0z = __ldg(pk + 2);
         const float4 e1x = __ldg(pk + 3), e1y = __ldg(pk + 4), e1z = __ldg(pk + 5);
         const float4 e2x = __ldg(pk + 6), e2y = __ldg(pk + 7), e2z = __ldg(pk + 8);
@@ -144,133 +161,145 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, V3 o, V3 inv, float& 
 
 constexpr int KD_STACK = 32;   // kd_max_depth is capped at 30 by the host
 
-// ---- closest hit, reference visit order ---------------------------------------------------------------------------
-// kd_tree_simd_accel::intersect<bf> (kd_tree_simd.hpp:187-229): LIFO stack, child0 pushed before child1 (child1 is
-// visited first), every popped node slab-tested against its own box, pruned when best_t < box.t_min (strict).
-// Returns the closest hit with t < t_limit (FLT_MAX for a plain query).
+// ---- leaf test, one ray per WARP ------------------------------------------------------------------------------------
+// The direct analogue of the reference's W-wide packet (kd_tree_simd.hpp:25-60): one ray against 32 triangles of the
+// leaf at a time, lane k testing triangles k, k+32, ... of the leaf's list, then a (t, position) min-reduction over
+// the lanes - "first triangle in list order among the smallest t", exactly what intersect_leaf's pack loop keeps
+// (:276-298: first pack wins ties, lowest lane inside a pack).  Padding lanes of the last packet repeat the leaf's
+// last triangle at a higher position and can only tie with it.
+// `limit`: only candidates with t < limit are of interest (the caller's running closest).
 template <bool CULL, bool FAST>
-__device__ __forceinline__ Hit trace_reference_order(const DScene& sc, V3 o, V3 d, float eps, float t_stop = -1.0f) {
+__device__ __forceinline__ bool leaf_warp(const float* __restrict__ packets, uint32_t first_packet, uint32_t n_packets, V3 o, V3 d,
+                                          float eps, float limit, Hit& out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    Hit c; c.t = limit; c.u = 0.0f; c.v = 0.0f; c.tri = -1;
+    uint32_t pos = 0xFFFFFFFFu;
+    const uint32_t n = n_packets * 4u;
+    for (uint32_t k = lane; k < n; k += 32u) {
+        const float* p = packets + (size_t(first_packet) + (k >> 2)) * 40u + (k & 3u);
+        const float before = c.t;
+        test_lane<CULL, FAST>(__ldg(p), __ldg(p + 4), __ldg(p + 8), __ldg(p + 12), __ldg(p + 16), __ldg(p + 20), __ldg(p + 24),
+                              __ldg(p + 28), __ldg(p + 32), __float_as_int(__ldg(p + 36)), o, d, eps, c);
+        if (c.t < before) pos = k;
+    }
+    if (!__ballot_sync(0xFFFFFFFFu, pos != 0xFFFFFFFFu)) return false;
+    float t = c.t;
+    uint32_t q = pos;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const float ot = __shfl_xor_sync(0xFFFFFFFFu, t, off);
+        const uint32_t oq = __shfl_xor_sync(0xFFFFFFFFu, q, off);
+        if (ot < t || (ot == t && oq < q)) { t = ot; q = oq; }
+    }
+    const int src = __ffs(__ballot_sync(0xFFFFFFFFu, pos == q)) - 1;       // positions are unique
+    out.t = t;
+    out.u = __shfl_sync(0xFFFFFFFFu, c.u, src);
+    out.v = __shfl_sync(0xFFFFFFFFu, c.v, src);
+    out.tri = __shfl_sync(0xFFFFFFFFu, c.tri, src);
+    return true;
+}
+
+// ---- closest hit ---------------------------------------------------------------------------------------------------------
+// kd_tree_simd_accel::intersect<bf> (kd_tree_simd.hpp:187-229) for the 32 rays of a warp.  Must be called by all 32
+// lanes (`active` = this lane has a ray).
+//
+// Inner nodes are walked per lane, exactly as the reference does per ray: LIFO stack, every popped node slab-tested
+// against its own box, pruned when best_t < box.t_min (strict).  ORDERED == false pushes child0 then child1 (child1
+// is visited first, the reference's order); ORDERED == true pushes the far child first so that the child on the
+// side the ray comes from is visited first - see the note on ties below.
+//
+// Leaves are where the time goes (up to 752 triangles per leaf with the reference's default <8,64> tree) and where a
+// one-ray-per-lane loop diverges, so they are handled by the warp: lanes that arrived at the SAME leaf (coherent
+// rays) and form a large enough group walk it one ray per lane, sharing every triangle fetch; any other leaf visit is
+// executed by all 32 lanes for its one ray (leaf_warp).
+//
+// Ties (ORDERED): the closest t is an order-independent minimum over the leaves the ray's slab tests admit; what the
+// reference's visit order decides is which of two DIFFERENT triangles with exactly equal t is reported - the one in
+// the leaf it visits first, i.e. the leaf with the higher node index (a later leaf needs a strictly smaller t,
+// :224), and inside a leaf the first in list order.  The ordered walk applies that rule explicitly.
+//
+// t_stop >= 0: the caller only needs to know whether closest.t <= t_stop; the running closest only decreases, so a
+// lane stops as soon as it holds such a candidate (occluded_query, non-transmissive scenes).
+constexpr int COHERENT_GROUP = 20;
+
+template <bool CULL, bool FAST, bool ORDERED>
+__device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V3 d, float eps, float t_stop = -1.0f) {
+    const uint32_t lane = threadIdx.x & 31u;
     const V3 inv = mk(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));                 // ray3.hpp:11-14
     Hit best; best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
+    uint32_t best_leaf = 0;
     uint32_t stack[KD_STACK];
     int sp = 0;
-    stack[sp++] = 0u;
-    while (sp) {
-        const uint32_t idx = stack[--sp];
-        const float4 lo = __ldg(sc.nodes32 + 2 * idx), hi = __ldg(sc.nodes32 + 2 * idx + 1);
-        float t_min;
-        if (!slab(lo, hi, o, inv, t_min) || best.t < t_min) continue;                                    // :202-205
-        const uint32_t word = __float_as_uint(hi.w);
-        if ((word & 3u) != 3u) {                                                                         // inner, :207-214
-            if (word & 4u) stack[sp++] = idx + 1u;
-            if (word & 8u) stack[sp++] = word >> 4;
-        } else {                                                                                         // leaf, :216-226
-            test_packets<CULL, FAST>(sc.packets + 10ull * __float_as_uint(lo.w), word >> 2, o, d, eps, best, t_stop);
-            if (best.t <= t_stop) return best;
-        }
-    }
-    return best;
-}
-
-// ---- closest hit, front-to-back over the 8-byte nodes ----------------------------------------------------------------
-// Same tree, same leaf test, different visit order: the child on the ray origin's side of the split plane first,
-// the subtree skipped when the ray's parametric interval inside the parent box does not reach it or starts beyond
-// the closest hit found so far.  The closest t is order independent; exact-t ties between DIFFERENT triangles are
-// resolved towards the lower triangle id (the rule that matched the reference on every tie observed, SURVEY.md
-// section 7).  Not the parity-gated mode; see DESIGN.md.
-template <bool CULL, bool FAST>
-__device__ __forceinline__ void test_packets_ordered(const float4* __restrict__ pk, uint32_t count, V3 o, V3 d,
-                                                     float eps, Hit& best) {
-    Hit local; local.t = FLT_MAX; local.u = 0.0f; local.v = 0.0f; local.tri = -1;
-    test_packets<CULL, FAST>(pk, count, o, d, eps, local);
-    if (local.tri >= 0 && (local.t < best.t || (local.t == best.t && local.tri < best.tri))) best = local;
-}
-
-template <bool CULL, bool FAST>
-__device__ __forceinline__ Hit trace_ordered(const DScene& sc, V3 o, V3 d, float eps, float t_stop = -1.0f) {
-    const V3 inv = mk(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
-    Hit best; best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
-    float t0;
-    {
-        const float4 lo = make_float4(sc.root_min[0], sc.root_min[1], sc.root_min[2], 0.0f);
-        const float4 hi = make_float4(sc.root_max[0], sc.root_max[1], sc.root_max[2], 0.0f);
-        if (!slab(lo, hi, o, inv, t0)) return best;
-    }
-    // exit distance of the root box (slab() only reports the entry)
-    float t1 = FLT_MAX;
-    {
-        const float ax = (sc.root_min[0] - o.x) * inv.x, bx = (sc.root_max[0] - o.x) * inv.x;
-        const float ay = (sc.root_min[1] - o.y) * inv.y, by = (sc.root_max[1] - o.y) * inv.y;
-        const float az = (sc.root_min[2] - o.z) * inv.z, bz = (sc.root_max[2] - o.z) * inv.z;
-        t1 = fminf(t1, fmaxf(ax, bx)); t1 = fminf(t1, fmaxf(ay, by)); t1 = fminf(t1, fmaxf(az, bz));
-    }
-    struct Entry { uint32_t node; float t0, t1; };
-    Entry stack[KD_STACK];
-    int sp = 0;
-    uint32_t idx = 0;
-    const float oa[3] = {o.x, o.y, o.z}, ia[3] = {inv.x, inv.y, inv.z}, da[3] = {d.x, d.y, d.z};
+    if (active) stack[sp++] = 0u;
+    const float* packets = reinterpret_cast<const float*>(sc.packets);
     for (;;) {
-        bool pop = false;
-        if (best.t < t0) pop = true;
-        else {
-            const uint2 n = __ldg(sc.nodes8 + idx);
-            const uint32_t axis = n.y & 3u;
-            if (axis == 3u) {
-                test_packets_ordered<CULL, FAST>(sc.packets + 10ull * n.x, n.y >> 2, o, d, eps, best);
-                if (best.t <= t_stop) return best;
-                pop = true;
-            } else {
-                const float split = __uint_as_float(n.x);
-                const float oc = axis == 0 ? oa[0] : (axis == 1 ? oa[1] : oa[2]);
-                const float ic = axis == 0 ? ia[0] : (axis == 1 ? ia[1] : ia[2]);
-                const float dc = axis == 0 ? da[0] : (axis == 1 ? da[1] : da[2]);
-                const float ts = (split - oc) * ic;
-                // child on the origin's side first; on the plane, the side the ray is heading to
-                const bool below = (oc < split) || (oc == split && dc <= 0.0f);
-                const uint32_t c0 = (n.y & 4u) ? idx + 1u : 0xFFFFFFFFu;
-                const uint32_t c1 = (n.y & 8u) ? (n.y >> 4) : 0xFFFFFFFFu;
-                const uint32_t near_c = below ? c0 : c1, far_c = below ? c1 : c0;
-                // every comparison is widened by `slack`, so rounding in ts / t0 / t1 can only ADD a visit
-                const float slack = 1e-6f * fmaxf(fabsf(ts), 1.0f);
-                bool go_near = true, go_far = true;
-                float near_t1 = t1, far_t0 = t0;
-                if (ts == ts) {                       // NaN: the ray lies in the split plane -> both, intervals kept
-                    if (ts > t1 + slack || ts < -slack) go_far = false;          // plane beyond the exit / behind the origin
-                    else if (ts < t0 - slack) go_near = false;                   // plane before the entry
-                    else { near_t1 = fminf(t1, ts + slack); far_t0 = fmaxf(t0, ts - slack); }
+        // ---- walk inner nodes until this lane stands at a leaf it has to test ----
+        uint32_t leaf_first = 0, leaf_count = 0, leaf_idx = 0;
+        bool want = false;
+        while (sp) {
+            const uint32_t idx = stack[--sp];
+            const float4 lo = __ldg(sc.nodes32 + 2 * idx), hi = __ldg(sc.nodes32 + 2 * idx + 1);
+            float t_min;
+            if (!slab(lo, hi, o, inv, t_min) || best.t < t_min) continue;                                // :202-205
+            const uint32_t word = __float_as_uint(hi.w);
+            const uint32_t axis = word & 3u;
+            if (axis != 3u) {                                                                            // inner, :207-214
+                const uint32_t c0 = idx + 1u, c1 = word >> 4;
+                bool c0_first_popped = false;
+                if (ORDERED) {
+                    const float da = axis == 0u ? d.x : (axis == 1u ? d.y : d.z);
+                    c0_first_popped = da >= 0.0f;              // travelling up the axis: child0 (the lower half) is nearer
                 }
-                go_near = go_near && near_c != 0xFFFFFFFFu;
-                go_far = go_far && far_c != 0xFFFFFFFFu;
-                if (go_near && go_far) {
-                    stack[sp].node = far_c; stack[sp].t0 = far_t0; stack[sp].t1 = t1; ++sp;
-                    idx = near_c; t1 = near_t1;
-                } else if (go_near) {
-                    idx = near_c; t1 = near_t1;
-                } else if (go_far) {
-                    idx = far_c; t0 = far_t0;
-                } else pop = true;
+                if (c0_first_popped) {
+                    if (word & 8u) stack[sp++] = c1;
+                    if (word & 4u) stack[sp++] = c0;
+                } else {
+                    if (word & 4u) stack[sp++] = c0;
+                    if (word & 8u) stack[sp++] = c1;
+                }
+            } else {                                                                                     // leaf, :216-226
+                leaf_first = __float_as_uint(lo.w); leaf_count = word >> 2; leaf_idx = idx;
+                want = true;
+                break;
             }
         }
-        if (pop) {
-            if (!sp) break;
-            --sp;
-            idx = stack[sp].node; t0 = stack[sp].t0; t1 = stack[sp].t1;
+        uint32_t pending = __ballot_sync(0xFFFFFFFFu, want);
+        if (!pending) break;
+        // ---- leaf tests ----
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const uint32_t lf = __shfl_sync(0xFFFFFFFFu, leaf_first, leader);
+            const uint32_t lc = __shfl_sync(0xFFFFFFFFu, leaf_count, leader);
+            const bool same = want && leaf_first == lf;
+            uint32_t group = __ballot_sync(0xFFFFFFFFu, same);
+            Hit cand; cand.t = FLT_MAX; cand.u = 0.0f; cand.v = 0.0f; cand.tri = -1;
+            bool have = false;
+            // candidates with t <= best.t matter to the ordered walk (ties), t < best.t to the reference walk
+            const float my_limit = (ORDERED && best.t < FLT_MAX) ? __uint_as_float(__float_as_uint(best.t) + 1u) : best.t;
+            if (__popc(group) >= COHERENT_GROUP) {
+                if (same) {
+                    cand.t = my_limit;
+                    test_packets<CULL, FAST>(sc.packets + 10ull * lf, lc, o, d, eps, cand);
+                    have = cand.tri >= 0;
+                }
+            } else {
+                group = 1u << leader;
+                const V3 ro = mk(__shfl_sync(0xFFFFFFFFu, o.x, leader), __shfl_sync(0xFFFFFFFFu, o.y, leader), __shfl_sync(0xFFFFFFFFu, o.z, leader));
+                const V3 rd = mk(__shfl_sync(0xFFFFFFFFu, d.x, leader), __shfl_sync(0xFFFFFFFFu, d.y, leader), __shfl_sync(0xFFFFFFFFu, d.z, leader));
+                const float limit = __shfl_sync(0xFFFFFFFFu, my_limit, leader);
+                Hit w;
+                const bool found = leaf_warp<CULL, FAST>(packets, lf, lc, ro, rd, eps, limit, w);
+                if (found && lane == uint32_t(leader)) { cand = w; have = true; }
+            }
+            if (have) {
+                if (cand.t < best.t || (ORDERED && (leaf_idx > best_leaf || best.tri < 0))) { best = cand; best_leaf = leaf_idx; }   // :224
+                if (best.t <= t_stop) sp = 0;
+            }
+            if (group & (1u << lane)) want = false;
+            pending &= ~group;
         }
     }
     return best;
-}
-
-template <bool CULL, bool FAST, bool ORDERED>
-__device__ __forceinline__ Hit trace_closest(const DScene& sc, V3 o, V3 d, float eps) {
-    if (ORDERED) return trace_ordered<CULL, FAST>(sc, o, d, eps);
-    return trace_reference_order<CULL, FAST>(sc, o, d, eps);
-}
-// same query, but the traversal may return as soon as it holds a candidate with t <= t_stop (the running closest
-// only decreases, so "closest.t <= t_stop" is already decided)
-template <bool CULL, bool FAST, bool ORDERED>
-__device__ __forceinline__ Hit trace_closest_stop(const DScene& sc, V3 o, V3 d, float eps, float t_stop) {
-    if (ORDERED) return trace_ordered<CULL, FAST>(sc, o, d, eps, t_stop);
-    return trace_reference_order<CULL, FAST>(sc, o, d, eps, t_stop);
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11) ---------------------------------------------------------------------------

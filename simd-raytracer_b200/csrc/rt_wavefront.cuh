@@ -155,15 +155,19 @@ __global__ void __launch_bounds__(256) k_primary(DScene sc, FrameParams fp, Ray*
         const uint32_t i = base + (threadIdx.x & 31u);
         const uint32_t s = i / fp.plane, j = i - s * fp.plane;
         uint32_t x, y;
-        Hit h; h.t = 0.0f; h.u = 0.0f; h.v = 0.0f; h.tri = TRI_INACTIVE;
-        if (level0_pixel(fp, j, x, y)) {
-            float rx, ry; uint2 key; V3 o, d;
+        const bool valid = level0_pixel(fp, j, x, y);
+        uint2 key = make_uint2(0u, 0u);
+        V3 o = mk(0, 0, 0), d = mk(0, 0, 0);
+        if (valid) {
+            float rx, ry;
             primary_sample(sc, fp, x, y, fp.sample_first + s, rx, ry, key);
             camera_ray(sc, fp.tan_half_fov, rx, ry, o, d);
-            h = trace_closest<true, FAST, ORDERED>(sc, o, d, fp.eps);                                    // render.hpp:64, culling ON
+        }
+        Hit h = trace_warp<true, FAST, ORDERED>(sc, valid, o, d, fp.eps);                                // render.hpp:64, culling ON
+        if (valid) {
             store_ray(rays + i, o, d, key);
             ++n_rays; n_hits += (h.tri >= 0);
-        }
+        } else h.tri = TRI_INACTIVE;
         store_hit(hits + i, h);
     }
     // one atomic per warp
@@ -185,10 +189,11 @@ __global__ void __launch_bounds__(256) k_trace_level(DScene sc, FrameParams fp, 
         const uint32_t base = claim32(&ps->work[work_slot]);
         if (base >= end - begin) break;
         const uint32_t i = begin + base + (threadIdx.x & 31u);
-        if (i < end) {
-            V3 o, d; uint2 key;
-            load_ray(rays + i, o, d, key);
-            const Hit h = trace_closest<false, FAST, ORDERED>(sc, o, d, fp.eps);
+        const bool valid = i < end;
+        V3 o = mk(0, 0, 0), d = mk(0, 0, 0); uint2 key;
+        if (valid) load_ray(rays + i, o, d, key);
+        const Hit h = trace_warp<false, FAST, ORDERED>(sc, valid, o, d, fp.eps);
+        if (valid) {
             store_hit(hits + i, h);
             ++n_rays; n_hits += (h.tri >= 0);
         }
@@ -203,24 +208,35 @@ __global__ void __launch_bounds__(256) k_trace_level(DScene sc, FrameParams fp, 
 // "closest.t <= max_t"; the running closest only ever decreases, so the traversal may stop as soon as it holds a
 // candidate with t <= max_t - same answer, same query count.
 template <bool TRANSMISSIVE, bool FAST, bool ORDERED>
-__device__ __forceinline__ bool occluded_query(const DScene& sc, V3 o, V3 d, float max_t, float eps, float shadow_bias,
+__device__ __forceinline__ bool occluded_query(const DScene& sc, bool active, V3 o, V3 d, float max_t, float eps, float shadow_bias,
                                                unsigned long long& n_q, unsigned long long& n_h) {
-    while (0.0f < max_t) {                                                                               // :115
-        ++n_q;
-        Hit h;
-        if (TRANSMISSIVE) h = trace_closest<false, FAST, ORDERED>(sc, o, d, eps);                        // :116
-        else h = trace_closest_stop<false, FAST, ORDERED>(sc, o, d, eps, max_t < FLT_MAX ? max_t : -1.0f);
-        if (h.tri < 0) return false;                                                                     // :117
-        ++n_h;
-        if (max_t < h.t) return false;                                                                   // :117-119
-        if (!TRANSMISSIVE) return true;
-        const uint32_t mat = __ldg(&sc.tri_index[h.tri]).w;
-        if (sc.materials[mat].kind != 2u) return true;                                                   // :121-124
-        const V3 pos = o + h.t * d;                                                                      // hit.position, kd_tree_simd.hpp:254
-        o = pos + shadow_bias * d;                                                                       // :126 (inv_direction is not refreshed, nor does it change)
-        max_t -= h.t;                                                                                    // :127
+    // called by all 32 lanes (the closest-hit query is warp-cooperative); a lane leaves the loop by clearing `active`
+    bool result = false;
+    active = active && (0.0f < max_t);                                                                   // :115
+    while (__ballot_sync(0xFFFFFFFFu, active)) {
+        const Hit h = trace_warp<false, FAST, ORDERED>(sc, active, o, d, eps,                            // :116
+                                                       (!TRANSMISSIVE && max_t < FLT_MAX) ? max_t : -1.0f);
+        if (active) {
+            ++n_q;
+            if (h.tri < 0) active = false;                                                               // :117
+            else {
+                ++n_h;
+                if (max_t < h.t) active = false;                                                         // :117-119
+                else if (!TRANSMISSIVE) { result = true; active = false; }
+                else {
+                    const uint32_t mat = __ldg(&sc.tri_index[h.tri]).w;
+                    if (sc.materials[mat].kind != 2u) { result = true; active = false; }                 // :121-124
+                    else {
+                        const V3 pos = o + h.t * d;                                                      // hit.position, kd_tree_simd.hpp:254
+                        o = pos + shadow_bias * d;                                                       // :126 (direction, hence inv_direction, unchanged)
+                        max_t -= h.t;                                                                    // :127
+                        active = 0.0f < max_t;                                                           // :115
+                    }
+                }
+            }
+        }
     }
-    return false;
+    return result;
 }
 
 template <bool TRANSMISSIVE, bool FAST, bool ORDERED>
@@ -233,13 +249,12 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, FrameParams fp, Shado
         const uint32_t base = claim32(&ps->work[work_slot]);
         if (base >= end) break;
         const uint32_t i = base + (threadIdx.x & 31u);
-        if (i < end) {
-            const float4* p = reinterpret_cast<const float4*>(jobs + i);
-            const float4 a = p[0], b = p[1];
-            const bool occ = occluded_query<TRANSMISSIVE, FAST, ORDERED>(sc, mk(a.x, a.y, a.z), mk(a.w, b.x, b.y), b.z, fp.eps,
-                                                                         fp.shadow_bias, n_q, n_h);
-            if (occ) jobs[i].max_t = -1.0f;
-        }
+        const bool valid = i < end;
+        float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+        if (valid) { const float4* p = reinterpret_cast<const float4*>(jobs + i); a = p[0]; b = p[1]; }
+        const bool occ = occluded_query<TRANSMISSIVE, FAST, ORDERED>(sc, valid, mk(a.x, a.y, a.z), mk(a.w, b.x, b.y), b.z, fp.eps,
+                                                                     fp.shadow_bias, n_q, n_h);
+        if (occ) jobs[i].max_t = -1.0f;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { n_q += __shfl_xor_sync(0xFFFFFFFFu, n_q, o); n_h += __shfl_xor_sync(0xFFFFFFFFu, n_h, o); }
@@ -517,34 +532,47 @@ __global__ void k_resolve_sum(const float* __restrict__ sum, float div, float* _
 template <bool CULL, bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_trace_batch(DScene sc, const float* __restrict__ rays6, unsigned long long n, float eps,
                                                      Hit* __restrict__ hits) {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const float* q = rays6 + 6 * i;
-        const Hit h = trace_closest<CULL, FAST, ORDERED>(sc, mk(q[0], q[1], q[2]), mk(q[3], q[4], q[5]), eps);
-        store_hit(hits + i, h);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounds = (n + stride - 1) / stride;                     // warp-uniform trip count
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
+        const bool valid = i < n;
+        V3 o = mk(0, 0, 0), d = mk(0, 0, 0);
+        if (valid) { const float* q = rays6 + 6 * i; o = mk(q[0], q[1], q[2]); d = mk(q[3], q[4], q[5]); }
+        const Hit h = trace_warp<CULL, FAST, ORDERED>(sc, valid, o, d, eps);
+        if (valid) store_hit(hits + i, h);
     }
 }
 template <bool TRANSMISSIVE, bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_occluded_batch(DScene sc, const float* __restrict__ rays6, const float* __restrict__ max_t,
                                                         unsigned long long n, float eps, float shadow_bias, uint8_t* __restrict__ out) {
     unsigned long long n_q = 0, n_h = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const float* q = rays6 + 6 * i;
-        out[i] = occluded_query<TRANSMISSIVE, FAST, ORDERED>(sc, mk(q[0], q[1], q[2]), mk(q[3], q[4], q[5]), max_t[i], eps, shadow_bias,
-                                                             n_q, n_h) ? 1 : 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounds = (n + stride - 1) / stride;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
+        const bool valid = i < n;
+        V3 o = mk(0, 0, 0), d = mk(0, 0, 0);
+        float mt = 0.0f;
+        if (valid) { const float* q = rays6 + 6 * i; o = mk(q[0], q[1], q[2]); d = mk(q[3], q[4], q[5]); mt = max_t[i]; }
+        const bool occ = occluded_query<TRANSMISSIVE, FAST, ORDERED>(sc, valid, o, d, mt, eps, shadow_bias, n_q, n_h);
+        if (valid) out[i] = occ ? 1 : 0;
     }
 }
 // primary rays only, hits in row-major tile order (rt_trace_primary)
 template <bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_primary_hits(DScene sc, FrameParams fp, Hit* __restrict__ hits) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= fp.plane) return;
-    uint32_t x, y;
-    if (!level0_pixel(fp, j, x, y)) return;
-    float rx, ry; uint2 key; V3 o, d;
-    primary_sample(sc, fp, x, y, fp.sample_first, rx, ry, key);
-    camera_ray(sc, fp.tan_half_fov, rx, ry, o, d);
-    const Hit h = trace_closest<true, FAST, ORDERED>(sc, o, d, fp.eps);
-    store_hit(hits + size_t(y - fp.y0) * fp.tw + (x - fp.x0), h);
+    uint32_t x = 0, y = 0;
+    const bool valid = j < fp.plane && level0_pixel(fp, j, x, y);
+    uint2 key; V3 o = mk(0, 0, 0), d = mk(0, 0, 0);
+    if (valid) {
+        float rx, ry;
+        primary_sample(sc, fp, x, y, fp.sample_first, rx, ry, key);
+        camera_ray(sc, fp.tan_half_fov, rx, ry, o, d);
+    }
+    const Hit h = trace_warp<true, FAST, ORDERED>(sc, valid, o, d, fp.eps);
+    if (valid) store_hit(hits + size_t(y - fp.y0) * fp.tw + (x - fp.x0), h);
 }
 
 }  // namespace rtb

@@ -14,7 +14,7 @@ LIB = os.path.join(ORACLE_DIR, "librt_oracle.so")
 
 RNG_MINSTD, RNG_PHILOX = 0, 1
 KIND_PRIMARY, KIND_SHADOW, KIND_REFLECT, KIND_REFRACT, KIND_GI = range(5)
-N_COUNTS = 8
+N_COUNTS = 12
 
 RECORD_DTYPE = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("t", "<f4"), ("u", "<f4"), ("v", "<f4"),
                          ("tri", "<i4"), ("cull", "<u4"), ("kind", "<u4")])
