@@ -1,0 +1,195 @@
+// b200_accel.hpp - header-only C++23 adapter that plugs the B200 backend (include/rt_b200.h, librt_b200.so) into
+// simd-raytracer where kd_tree_simd_accel sits today.
+//
+// Include it AFTER the reference's own headers (it uses scene<F>, ray3<F>, hit<F>, image<F>, the material / texture
+// variants and the config.hpp constants; it includes none of them itself):
+//
+//     #include <raytracer/render/render.hpp>
+//     #include <b200_accel.hpp>
+//     using A = b200_accel<float>;                       // was: kd_tree_simd_accel<F, static_cast<F>(epsilon)>   (src/main.cpp:37)
+//     auto accelerator = A(std::make_shared<const scene<float>>(scene));                                      // (src/main.cpp:41)
+//     auto image = render_frame<A, float>(accelerator, scheduling_type::BUCKET_TILES);                        // (src/main.cpp:17)
+//
+// What it provides, matched to the reference interface:
+//   * the accelerator<A,F> concept (render/accel/accel.hpp:8-12): intersect<true|false>(ray) -> std::optional<hit<F>>,
+//     noexcept and re-entrant like kd_tree_simd_accel::intersect (kd_tree_simd.hpp:187-264); one synchronous ray per
+//     call goes through rt_trace_closest as a batch of one - a conformance path, not a fast one;
+//   * the implicit `scene_ptr` member the render loops dereference (render/render.hpp:21,113,136);
+//   * construction from std::shared_ptr<const scene<F>> like kd_tree_simd_accel's ctor (kd_tree_simd.hpp:100);
+//   * an overload of render_frame for this accelerator type that runs the whole frame on the GPU (ray generation,
+//     traversal, shading, shadow / reflection / refraction / GI loops) through rt_render_frame and returns image<F>,
+//     so src/main.cpp's flow is unchanged.  The config.hpp constants are read here and passed as run-time parameters.
+//
+// F = float only: the device path is FP32 like the reference's shipped configuration (src/main.cpp:36).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <variant>
+#include <vector>
+
+#include "rt_b200.h"
+
+template <typename F>
+struct b200_accel {
+    static_assert(std::is_same_v<F, float>, "the B200 backend computes in FP32");
+
+    std::shared_ptr<const scene<F>> scene_ptr;          // render/render.hpp:21,113,136 read this member
+
+    struct handle_deleter { void operator()(rt_scene* s) const noexcept { rt_scene_destroy(s); } };
+    std::shared_ptr<rt_scene> handle;                   // shared: the reference copies accelerators by value in places
+    std::vector<std::size_t> mesh_first_triangle;       // global triangle id -> (mesh, local triangle)
+
+    explicit b200_accel(std::shared_ptr<const scene<F>> sp, std::uint32_t kd_max_depth = 8, std::uint32_t kd_max_leaf_size = 64,
+                        int device = 0)
+        : scene_ptr(std::move(sp)) {
+        const scene<F>& sc = *scene_ptr;
+        rt_scene_desc d{};
+        d.background[0] = sc.config.background_color.red; d.background[1] = sc.config.background_color.green;
+        d.background[2] = sc.config.background_color.blue;
+        d.width = static_cast<std::uint32_t>(sc.config.image_width);
+        d.height = static_cast<std::uint32_t>(sc.config.image_height);
+        d.bucket_size = static_cast<std::uint32_t>(sc.config.bucket_size);
+        d.camera_position[0] = sc.viewpoint.position.x; d.camera_position[1] = sc.viewpoint.position.y;
+        d.camera_position[2] = sc.viewpoint.position.z;
+        for (int i = 0; i < 9; ++i) d.camera_matrix[i] = sc.viewpoint.matrix.m[i];
+
+        std::vector<rt_light_desc> lights;
+        for (const auto& l : sc.lights) lights.push_back({{l.position.x, l.position.y, l.position.z}, l.intensity});
+
+        // textures: the reference keys them by name (scene/scene.hpp:19); the ABI indexes them
+        std::vector<rt_texture_desc> textures;
+        std::vector<std::uint8_t> texels;
+        std::unordered_map<std::string, std::int32_t> texture_index;
+        for (const auto& [name, tv] : sc.textures) {
+            rt_texture_desc t{};
+            std::visit([&](const auto& tex) {
+                using T = std::decay_t<decltype(tex)>;
+                auto put = [](float* dst, const color<F>& c) { dst[0] = c.red; dst[1] = c.green; dst[2] = c.blue; };
+                if constexpr (std::is_same_v<T, albedo_texture<F>>) { t.kind = RT_TEX_ALBEDO; put(t.c0, tex.albedo); }
+                else if constexpr (std::is_same_v<T, edge_texture<F>>) {
+                    t.kind = RT_TEX_EDGES; put(t.c0, tex.edge_color); put(t.c1, tex.inner_color); t.scalar = tex.edge_width;
+                } else if constexpr (std::is_same_v<T, checker_texture<F>>) {
+                    t.kind = RT_TEX_CHECKER; put(t.c0, tex.color_a); put(t.c1, tex.color_b); t.scalar = tex.square_size;
+                } else {
+                    // bitmap texels were stored as float(byte) * float(1/255) (scene/texture/bitmap.hpp:19-30): recover the bytes
+                    t.kind = RT_TEX_BITMAP;
+                    t.bmp_w = static_cast<std::uint32_t>(tex.texture.get_width());
+                    t.bmp_h = static_cast<std::uint32_t>(tex.texture.get_height());
+                    t.bmp_off = static_cast<std::uint32_t>(texels.size());
+                    for (std::size_t r = 0; r < tex.texture.get_height(); ++r)
+                        for (std::size_t c = 0; c < tex.texture.get_width(); ++c) {
+                            const color<F>& p = tex.texture.get_pixel(r, c);
+                            for (F ch : {p.red, p.green, p.blue}) texels.push_back(static_cast<std::uint8_t>(std::lround(ch * F(255))));
+                        }
+                }
+            }, tv);
+            texture_index.emplace(name, static_cast<std::int32_t>(textures.size()));
+            textures.push_back(t);
+        }
+
+        std::vector<rt_material_desc> materials;
+        for (const auto& mv : sc.materials) {
+            rt_material_desc m{};
+            m.texture = -1; m.ior = 1.0f;
+            std::visit([&](const auto& mat) {
+                using M = std::decay_t<decltype(mat)>;
+                m.smooth_shading = mat.smooth_shading ? 1u : 0u;
+                if constexpr (std::is_same_v<M, diffuse_material<F>>) m.kind = RT_MAT_DIFFUSE;
+                else if constexpr (std::is_same_v<M, reflective_material<F>>) m.kind = RT_MAT_REFLECTIVE;
+                else if constexpr (std::is_same_v<M, refractive_material<F>>) m.kind = RT_MAT_REFRACTIVE;
+                else if constexpr (std::is_same_v<M, constant_material<F>>) m.kind = RT_MAT_CONSTANT;
+                else m.kind = RT_MAT_TEXTURE;
+                if constexpr (requires { mat.albedo; }) { m.albedo[0] = mat.albedo.red; m.albedo[1] = mat.albedo.green; m.albedo[2] = mat.albedo.blue; }
+                if constexpr (requires { mat.ior; }) m.ior = mat.ior;
+                if constexpr (requires { mat.texture; }) m.texture = texture_index.at(mat.texture);
+            }, mv);
+            materials.push_back(m);
+        }
+
+        std::vector<rt_mesh_desc> meshes;
+        std::vector<std::vector<float>> vbuf(sc.meshes.size()), uvbuf(sc.meshes.size());
+        std::vector<std::vector<std::uint32_t>> tbuf(sc.meshes.size());
+        std::size_t first = 0;
+        for (std::size_t i = 0; i < sc.meshes.size(); ++i) {
+            const auto& mo = sc.meshes[i];
+            for (const auto& v : mo.vertices) { vbuf[i].push_back(v.x); vbuf[i].push_back(v.y); vbuf[i].push_back(v.z); }
+            for (const auto& uv : mo.uvs) { uvbuf[i].push_back(uv.x); uvbuf[i].push_back(uv.y); }
+            for (const auto& t : mo.triangles) for (std::size_t k : t.vertex_indices) tbuf[i].push_back(static_cast<std::uint32_t>(k));
+            rt_mesh_desc md{};
+            md.material = static_cast<std::uint32_t>(mo.material_idx);
+            md.n_vertices = static_cast<std::uint32_t>(mo.vertices.size());
+            md.n_uvs = static_cast<std::uint32_t>(mo.uvs.size());
+            md.n_triangles = static_cast<std::uint32_t>(mo.triangles.size());
+            md.vertices = vbuf[i].data(); md.uvs = uvbuf[i].empty() ? nullptr : uvbuf[i].data(); md.triangles = tbuf[i].data();
+            meshes.push_back(md);
+            mesh_first_triangle.push_back(first);       // global id = position in the mesh-order concatenation (kd_tree_simd.hpp:103-111)
+            first += mo.triangles.size();
+        }
+        mesh_first_triangle.push_back(first);
+
+        d.n_lights = static_cast<std::uint32_t>(lights.size()); d.lights = lights.data();
+        d.n_textures = static_cast<std::uint32_t>(textures.size()); d.textures = textures.data();
+        d.n_materials = static_cast<std::uint32_t>(materials.size()); d.materials = materials.data();
+        d.n_meshes = static_cast<std::uint32_t>(meshes.size()); d.meshes = meshes.data();
+        d.n_texel_bytes = texels.size(); d.texels = texels.data();
+
+        rt_build_opts o;
+        rt_default_build_opts(&o);
+        o.kd_max_depth = kd_max_depth; o.kd_max_leaf_size = kd_max_leaf_size; o.device = device;
+        rt_scene* raw = nullptr;
+        const int st = rt_scene_create(&d, &o, &raw);
+        if (st != RT_OK) throw std::runtime_error(std::string("b200_accel: ") + rt_status_string(st) + ": " + rt_last_error());
+        handle = std::shared_ptr<rt_scene>(raw, handle_deleter{});
+    }
+
+    // accel.intersect<bf>(ray) - kd_tree_simd.hpp:187-264.  A failed call reports a miss: the reference's query is noexcept.
+    template <bool backface_culling>
+    std::optional<hit<F>> intersect(const ray3<F>& ray) const noexcept {
+        const float r[6] = {ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y, ray.direction.z};
+        rt_hit h{};
+        if (rt_trace_closest(handle.get(), r, 1, backface_culling ? 1 : 0, static_cast<float>(epsilon), 0u, &h) != RT_OK || h.tri < 0)
+            return std::nullopt;
+        // hit assembly as kd_tree_simd.hpp:234-263, from the host scene
+        std::size_t mesh = 0;
+        while (mesh_first_triangle[mesh + 1] <= static_cast<std::size_t>(h.tri)) ++mesh;
+        const auto& mo = scene_ptr->meshes[mesh];
+        const auto& tri = mo.triangles[static_cast<std::size_t>(h.tri) - mesh_first_triangle[mesh]];
+        const F u = h.u, v = h.v, w = F(1.) - u - v;
+        const auto [i0, i1, i2] = tri.vertex_indices;
+        const vec3<F> n = normalized(u * mo.vertex_normals[i1] + v * mo.vertex_normals[i2] + w * mo.vertex_normals[i0]);
+        return hit<F>{ray, ray.origin + h.t * ray.direction, n, tri.normal, tri.uvs, h.t, u, v, w, tri.mesh_idx};
+    }
+};
+
+// render_frame for the B200 accelerator: same signature and result type as render/render.hpp:18-19, whole frame on device.
+// (A more specialised overload than the generic template, so `render_frame<b200_accel<F>, F>(accel, schedule)` picks it.)
+template <typename A, typename F>
+requires std::is_same_v<A, b200_accel<F>>
+image<F> render_frame(const b200_accel<F>& accel, const scheduling_type /* tiles are scheduled by the device */) {
+    rt_params p;
+    rt_default_params(&p);
+    p.fov_degrees = fov_degrees;                                               // config.hpp:6
+    p.epsilon = static_cast<float>(epsilon);                                   // config.hpp:8, narrowed as src/main.cpp:37
+    p.shadow_bias = static_cast<float>(shadow_bias);                           // config.hpp:9
+    p.reflection_bias = static_cast<float>(reflection_bias);                   // config.hpp:10
+    p.refraction_bias = static_cast<float>(refraction_bias);                   // config.hpp:11
+    p.samples_per_pixel = static_cast<std::uint32_t>(samples_per_pixel);       // config.hpp:13
+    p.max_ray_depth = static_cast<std::uint32_t>(max_ray_depth);               // config.hpp:14
+    p.diffuse_reflection_ray_count = static_cast<std::uint32_t>(diffuse_reflection_ray_count);   // config.hpp:15
+    if (fixed_rng_seed) p.seed = static_cast<std::uint32_t>(*fixed_rng_seed);  // config.hpp:17
+    const std::size_t h = accel.scene_ptr->config.image_height, w = accel.scene_ptr->config.image_width;
+    std::vector<float> rgb(h * w * 3);
+    const int st = rt_render_frame(accel.handle.get(), &p, rgb.data());
+    if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame: ") + rt_status_string(st) + ": " + rt_last_error());
+    std::vector<std::vector<color<F>>> pixels(h, std::vector<color<F>>(w));
+    for (std::size_t y = 0; y < h; ++y)
+        for (std::size_t x = 0; x < w; ++x) pixels[y][x] = color<F>{rgb[(y * w + x) * 3], rgb[(y * w + x) * 3 + 1], rgb[(y * w + x) * 3 + 2]};
+    return image<F>(h, w, std::move(pixels));
+}

@@ -364,3 +364,18 @@ def row_bands(height: int, bucket: int, rank: int, world: int) -> list[tuple[int
         if k % world == rank:
             out.append((y0, min(height, y0 + bucket)))
     return out
+
+
+def sharded_frame(render_slice, spp_total: int, rank: int, world: int, reduce_to_root, resolve):
+    """One frame over `world` ranks with a replicated scene: every rank renders the RAW SAMPLE SUM of its
+    own sample slice, ONE reduce(sum) brings the framebuffers to rank 0, which divides by spp_total (and quantises).
+
+    render_slice(first_sample, n_samples) -> framebuffer (whatever tensor type the caller's collective takes)
+    reduce_to_root(fb) -> None            in-place sum-reduction to rank 0 (torch.distributed.reduce over NCCL / gloo)
+    resolve(fb) -> frame                  rank 0 only: sum / spp_total
+    A rank whose slice is empty (world > spp_total) contributes zeros."""
+    first, count = spp_slice(spp_total, rank, world)
+    fb = render_slice(first, count)
+    if world > 1:
+        reduce_to_root(fb)
+    return resolve(fb) if rank == 0 else None
