@@ -88,6 +88,10 @@ typedef struct rt_build_opts {
     uint32_t kd_max_depth;           /* default 8  (kd_tree_simd.hpp:65) */
     uint32_t kd_max_leaf_size;       /* default 64 (kd_tree_simd.hpp:66) */
     int32_t device;                  /* CUDA ordinal; RT_DEVICE_HOST_ONLY builds tree + layout without a GPU */
+    /* the backend's own, deeper tree used by RT_FLAG_ORDERED (same builder, more depth, small leaves).
+     * 0 / 0 = automatic: depth min(max(kd_max_depth, ceil(log2(n_triangles)) + 4), 24), leaf size min(kd_max_leaf_size, 8) */
+    uint32_t accel_max_depth;
+    uint32_t accel_max_leaf_size;
 } rt_build_opts;
 #define RT_DEVICE_HOST_ONLY (-1)
 
@@ -110,7 +114,8 @@ typedef struct rt_params {
 
 #define RT_FLAG_RAW_SUM       0x1u   /* write the slice's sample sum; the caller divides after combining ranks */
 #define RT_FLAG_FAST_MATH     0x2u   /* FMA-contracted traversal + intersection (not bit-exact) */
-#define RT_FLAG_ORDERED       0x4u   /* front-to-back kd traversal over the 8-byte nodes */
+#define RT_FLAG_ORDERED       0x4u   /* accelerated query: front-to-back split-plane traversal over the 8-byte nodes of the
+                                        backend's own deeper kd-tree; same t/u/v bits, ties by lowest triangle index */
 
 typedef struct rt_hit {              /* the part of hit<F> (render/hit.hpp:9-21) that cannot be recomputed */
     float t, u, v;
@@ -124,6 +129,8 @@ typedef struct rt_scene_info {
     uint64_t device_bytes;           /* resident scene bytes in HBM */
     double build_seconds, flatten_seconds, upload_seconds;
     int32_t device;
+    uint32_t accel_max_depth, accel_max_leaf_size;       /* parameters the accelerated tree was built with */
+    uint64_t accel_n_nodes, accel_n_leaf_refs, accel_n_packets, accel_tree_depth;
 } rt_scene_info;
 
 typedef struct rt_counters {         /* of the last rt_render_frame* call */
@@ -164,6 +171,8 @@ RT_API int rt_scene_get_info(const rt_scene* s, rt_scene_info* info);
 RT_API int rt_scene_get_tree(const rt_scene* s, uint64_t* node5, float* boxes, uint32_t* refs);
 /*   nodes8 : the 8-byte device nodes (2 x u32 per node); packets: 40 x u32 per 4-triangle SoA packet          */
 RT_API int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets);
+/* same for the accelerated tree (sizes in rt_scene_info.accel_*); root6 = min xyz, max xyz of the root box                  */
+RT_API int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets, float* root6);
 /*   tri9 = v0,e1,e2 per triangle; face normals; vertex normals (mesh-concatenated vertex order)               */
 RT_API int rt_scene_get_geometry(const rt_scene* s, float* tri9, float* face_normals, float* vertex_normals);
 

@@ -94,6 +94,8 @@ struct rt_scene {
     Geometry geom;
     KdTree tree;
     DeviceLayout layout;
+    KdTree accel_tree;               // the backend's own deeper tree (RT_FLAG_ORDERED)
+    DeviceLayout accel_layout;
     rt_scene_info info{};
 
     int device = RT_DEVICE_HOST_ONLY;
@@ -181,7 +183,8 @@ void upload_scene(rt_scene* s) {
     uint64_t bytes = 0;
     DScene& d = s->d;
     auto keep = [&](auto* p) { s->owned.push_back((void*)p); return p; };
-    d.nodes8 = keep(upload<uint2>(L.nodes8.data(), L.nodes8.size() / 2, bytes));
+    d.a_nodes8 = keep(upload<uint32_t>(s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size(), bytes));
+    d.a_packets = reinterpret_cast<const float*>(keep(upload<float4>(s->accel_layout.packets.data(), s->accel_layout.packets.size() / 4, bytes)));
     d.nodes32 = keep(upload<float4>(L.nodes32.data(), L.nodes32.size() / 4, bytes));
     d.packets = keep(upload<float4>(L.packets.data(), L.packets.size() / 4, bytes));
     d.tri_index = keep(upload<uint4>(L.tri_index.data(), L.tri_index.size() / 4, bytes));
@@ -227,6 +230,19 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     s->info.build_seconds = now_s() - t0;
     t0 = now_s();
     s->layout = flatten(s->host, s->geom, s->tree);
+    {
+        const uint64_t n = std::max<uint64_t>(s->geom.tris.size(), 1);
+        uint32_t lg = 0;
+        while ((1ull << lg) < n) ++lg;
+        const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : std::min<uint32_t>(std::max<uint32_t>(o.kd_max_depth, lg + 4), 24);
+        const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : std::min<uint32_t>(o.kd_max_leaf_size, 8);
+        if (ad > 30) throw rt_error(RT_ERR_BAD_ARG, "accel_max_depth > 30");
+        s->accel_tree = build_kd_tree(s->geom, ad, al);
+        s->accel_layout = flatten_tree_only(s->geom, s->accel_tree);
+        s->info.accel_max_depth = ad; s->info.accel_max_leaf_size = al;
+        s->info.accel_n_nodes = s->accel_tree.nodes.size(); s->info.accel_n_leaf_refs = s->accel_tree.refs.size();
+        s->info.accel_n_packets = s->accel_layout.n_packets; s->info.accel_tree_depth = s->accel_tree.depth;
+    }
     s->info.flatten_seconds = now_s() - t0;
     s->info.width = s->host.width; s->info.height = s->host.height;
     s->info.n_triangles = s->geom.tris.size();
@@ -504,7 +520,7 @@ const char* rt_last_error(void) { return g_last_error.c_str(); }
 
 void rt_default_build_opts(rt_build_opts* o) {
     if (!o) return;
-    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0;
+    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_max_depth = 0; o->accel_max_leaf_size = 0;
 }
 
 void rt_default_params(rt_params* p) {
@@ -555,6 +571,14 @@ int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* pa
     if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
     if (nodes8) std::memcpy(nodes8, s->layout.nodes8.data(), s->layout.nodes8.size() * 4);
     if (packets) std::memcpy(packets, s->layout.packets.data(), size_t(s->layout.n_packets) * PACKET_WORDS * 4);
+    return RT_OK;
+}
+
+int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets, float* root6) {
+    if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
+    if (nodes8) std::memcpy(nodes8, s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size() * 4);
+    if (packets) std::memcpy(packets, s->accel_layout.packets.data(), size_t(s->accel_layout.n_packets) * PACKET_WORDS * 4);
+    if (root6) { std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12); }
     return RT_OK;
 }
 

@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "rt_kd8.cuh"
+
 namespace rtb {
 
 // ---- resident scene (all pointers into HBM) -------------------------------------------------------------------
@@ -21,7 +23,8 @@ struct DTexture { uint32_t kind; float c0[3], c1[3], scalar; uint32_t w, h, off;
 struct DLight { float pos[3], intensity; };                                                              // 16 B
 
 struct DScene {
-    const uint2* __restrict__ nodes8;       // 8-byte kd nodes (ordered traversal)
+    const uint32_t* __restrict__ a_nodes8;  // accelerated mode: 8-byte nodes of the backend's own deeper kd-tree (rt_kd8.cuh)
+    const float* __restrict__ a_packets;    //                   and its leaf packets
     const float4* __restrict__ nodes32;     // 2 x float4 per node: box + the same two words (reference-order traversal)
     const float4* __restrict__ packets;     // 10 x float4 per 4-triangle SoA packet
     const uint4* __restrict__ tri_index;    // vi0, vi1, vi2, material
@@ -203,38 +206,31 @@ __device__ __forceinline__ bool leaf_warp(const float* __restrict__ packets, uin
 // kd_tree_simd_accel::intersect<bf> (kd_tree_simd.hpp:187-229) for the 32 rays of a warp.  Must be called by all 32
 // lanes (`active` = this lane has a ray).
 //
-// Inner nodes are walked per lane, exactly as the reference does per ray: LIFO stack, every popped node slab-tested
-// against its own box, pruned when best_t < box.t_min (strict).  ORDERED == false pushes child0 then child1 (child1
-// is visited first, the reference's order); ORDERED == true pushes the far child first so that the child on the
-// side the ray comes from is visited first - see the note on ties below.
+// Inner nodes are walked per lane, exactly as the reference does per ray: LIFO stack, child0 pushed before child1
+// (so child1 is visited first), every popped node slab-tested against its own box, pruned when best_t < box.t_min
+// (strict).
 //
 // Leaves are where the time goes (up to 752 triangles per leaf with the reference's default <8,64> tree) and where a
 // one-ray-per-lane loop diverges, so they are handled by the warp: lanes that arrived at the SAME leaf (coherent
 // rays) and form a large enough group walk it one ray per lane, sharing every triangle fetch; any other leaf visit is
 // executed by all 32 lanes for its one ray (leaf_warp).
 //
-// Ties (ORDERED): the closest t is an order-independent minimum over the leaves the ray's slab tests admit; what the
-// reference's visit order decides is which of two DIFFERENT triangles with exactly equal t is reported - the one in
-// the leaf it visits first, i.e. the leaf with the higher node index (a later leaf needs a strictly smaller t,
-// :224), and inside a leaf the first in list order.  The ordered walk applies that rule explicitly.
-//
 // t_stop >= 0: the caller only needs to know whether closest.t <= t_stop; the running closest only decreases, so a
 // lane stops as soon as it holds such a candidate (occluded_query, non-transmissive scenes).
 constexpr int COHERENT_GROUP = 20;
 
-template <bool CULL, bool FAST, bool ORDERED>
+template <bool CULL, bool FAST>
 __device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V3 d, float eps, float t_stop = -1.0f) {
     const uint32_t lane = threadIdx.x & 31u;
     const V3 inv = mk(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));                 // ray3.hpp:11-14
     Hit best; best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
-    uint32_t best_leaf = 0;
     uint32_t stack[KD_STACK];
     int sp = 0;
     if (active) stack[sp++] = 0u;
     const float* packets = reinterpret_cast<const float*>(sc.packets);
     for (;;) {
         // ---- walk inner nodes until this lane stands at a leaf it has to test ----
-        uint32_t leaf_first = 0, leaf_count = 0, leaf_idx = 0;
+        uint32_t leaf_first = 0, leaf_count = 0;
         bool want = false;
         while (sp) {
             const uint32_t idx = stack[--sp];
@@ -244,21 +240,10 @@ __device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V
             const uint32_t word = __float_as_uint(hi.w);
             const uint32_t axis = word & 3u;
             if (axis != 3u) {                                                                            // inner, :207-214
-                const uint32_t c0 = idx + 1u, c1 = word >> 4;
-                bool c0_first_popped = false;
-                if (ORDERED) {
-                    const float da = axis == 0u ? d.x : (axis == 1u ? d.y : d.z);
-                    c0_first_popped = da >= 0.0f;              // travelling up the axis: child0 (the lower half) is nearer
-                }
-                if (c0_first_popped) {
-                    if (word & 8u) stack[sp++] = c1;
-                    if (word & 4u) stack[sp++] = c0;
-                } else {
-                    if (word & 4u) stack[sp++] = c0;
-                    if (word & 8u) stack[sp++] = c1;
-                }
+                if (word & 4u) stack[sp++] = idx + 1u;
+                if (word & 8u) stack[sp++] = word >> 4;
             } else {                                                                                     // leaf, :216-226
-                leaf_first = __float_as_uint(lo.w); leaf_count = word >> 2; leaf_idx = idx;
+                leaf_first = __float_as_uint(lo.w); leaf_count = word >> 2;
                 want = true;
                 break;
             }
@@ -274,8 +259,7 @@ __device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V
             uint32_t group = __ballot_sync(0xFFFFFFFFu, same);
             Hit cand; cand.t = FLT_MAX; cand.u = 0.0f; cand.v = 0.0f; cand.tri = -1;
             bool have = false;
-            // candidates with t <= best.t matter to the ordered walk (ties), t < best.t to the reference walk
-            const float my_limit = (ORDERED && best.t < FLT_MAX) ? __uint_as_float(__float_as_uint(best.t) + 1u) : best.t;
+            const float my_limit = best.t;                  // a later leaf needs a strictly smaller t (:224)
             if (__popc(group) >= COHERENT_GROUP) {
                 if (same) {
                     cand.t = my_limit;
@@ -292,7 +276,7 @@ __device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V
                 if (found && lane == uint32_t(leader)) { cand = w; have = true; }
             }
             if (have) {
-                if (cand.t < best.t || (ORDERED && (leaf_idx > best_leaf || best.tri < 0))) { best = cand; best_leaf = leaf_idx; }   // :224
+                if (cand.t < best.t) best = cand;                                                        // :224
                 if (best.t <= t_stop) sp = 0;
             }
             if (group & (1u << lane)) want = false;
@@ -300,6 +284,34 @@ __device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V
         }
     }
     return best;
+}
+
+// ---- one entry point for the kernels -----------------------------------------------------------------------------------
+// ACCEL == false: the reference's tree in the reference's order (bit-exact by construction, statistics included).
+//                 any_hit lets a lane stop once closest.t <= t_far is decided; t_far is otherwise ignored.
+// ACCEL == true : rt_kd8.cuh - the backend's own deeper tree, front-to-back, one ray per thread; nodes beyond t_far are
+//                 not visited at all (a hit beyond t_far and a miss mean the same to every caller that passes t_far).
+//                 Must be called by all 32 lanes (tie re-runs use the warp-cooperative query).
+template <bool CULL, bool FAST, bool ACCEL>
+__device__ __forceinline__ Hit trace_any(const DScene& sc, bool active, V3 o, V3 d, float eps, float t_far = FLT_MAX, bool any_hit = false) {
+    if (ACCEL) {
+        Hit h; h.t = FLT_MAX; h.u = 0.0f; h.v = 0.0f; h.tri = -1;
+        bool tie = false;
+        if (active) {
+            const KdHit k = kd8_trace<CULL, FAST>(sc.a_nodes8, sc.a_packets, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, eps,
+                                                  t_far, any_hit);
+            h.t = k.t; h.u = k.u; h.v = k.v; h.tri = k.tri;
+            tie = !any_hit && k.tri >= 0 && k.tie_t == k.t;
+        }
+        // two different triangles at exactly the winner's t: which one the reference reports depends on its leaf order,
+        // so those rays (rare) take the reference-order query
+        if (__ballot_sync(0xFFFFFFFFu, tie)) {
+            const Hit e = trace_warp<CULL, FAST>(sc, tie, o, d, eps);
+            if (tie) h = e;
+        }
+        return h;
+    }
+    return trace_warp<CULL, FAST>(sc, active, o, d, eps, (any_hit && t_far < FLT_MAX) ? t_far : -1.0f);
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11) ---------------------------------------------------------------------------

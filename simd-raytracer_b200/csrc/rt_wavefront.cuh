@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) k_primary(DScene sc, FrameParams fp, Ray*
             primary_sample(sc, fp, x, y, fp.sample_first + s, rx, ry, key);
             camera_ray(sc, fp.tan_half_fov, rx, ry, o, d);
         }
-        Hit h = trace_warp<true, FAST, ORDERED>(sc, valid, o, d, fp.eps);                                // render.hpp:64, culling ON
+        Hit h = trace_any<true, FAST, ORDERED>(sc, valid, o, d, fp.eps);                                // render.hpp:64, culling ON
         if (valid) {
             store_ray(rays + i, o, d, key);
             ++n_rays; n_hits += (h.tri >= 0);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) k_trace_level(DScene sc, FrameParams fp, 
         const bool valid = i < end;
         V3 o = mk(0, 0, 0), d = mk(0, 0, 0); uint2 key;
         if (valid) load_ray(rays + i, o, d, key);
-        const Hit h = trace_warp<false, FAST, ORDERED>(sc, valid, o, d, fp.eps);
+        const Hit h = trace_any<false, FAST, ORDERED>(sc, valid, o, d, fp.eps);
         if (valid) {
             store_hit(hits + i, h);
             ++n_rays; n_hits += (h.tri >= 0);
@@ -214,8 +214,7 @@ __device__ __forceinline__ bool occluded_query(const DScene& sc, bool active, V3
     bool result = false;
     active = active && (0.0f < max_t);                                                                   // :115
     while (__ballot_sync(0xFFFFFFFFu, active)) {
-        const Hit h = trace_warp<false, FAST, ORDERED>(sc, active, o, d, eps,                            // :116
-                                                       (!TRANSMISSIVE && max_t < FLT_MAX) ? max_t : -1.0f);
+        const Hit h = trace_any<false, FAST, ORDERED>(sc, active, o, d, eps, max_t, !TRANSMISSIVE);      // :116
         if (active) {
             ++n_q;
             if (h.tri < 0) active = false;                                                               // :117
@@ -539,7 +538,7 @@ __global__ void __launch_bounds__(256) k_trace_batch(DScene sc, const float* __r
         const bool valid = i < n;
         V3 o = mk(0, 0, 0), d = mk(0, 0, 0);
         if (valid) { const float* q = rays6 + 6 * i; o = mk(q[0], q[1], q[2]); d = mk(q[3], q[4], q[5]); }
-        const Hit h = trace_warp<CULL, FAST, ORDERED>(sc, valid, o, d, eps);
+        const Hit h = trace_any<CULL, FAST, ORDERED>(sc, valid, o, d, eps);
         if (valid) store_hit(hits + i, h);
     }
 }
@@ -571,7 +570,7 @@ __global__ void __launch_bounds__(256) k_primary_hits(DScene sc, FrameParams fp,
         primary_sample(sc, fp, x, y, fp.sample_first, rx, ry, key);
         camera_ray(sc, fp.tan_half_fov, rx, ry, o, d);
     }
-    const Hit h = trace_warp<true, FAST, ORDERED>(sc, valid, o, d, fp.eps);
+    const Hit h = trace_any<true, FAST, ORDERED>(sc, valid, o, d, fp.eps);
     if (valid) store_hit(hits + size_t(y - fp.y0) * fp.tw + (x - fp.x0), h);
 }
 

@@ -159,7 +159,7 @@ KdTree build_kd_tree(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_si
     return t;
 }
 
-DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t) {
+DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t) {
     DeviceLayout d;
     auto bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
     const uint64_t n_nodes = t.nodes.size();
@@ -210,6 +210,11 @@ DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t) {
         f[4] = bits(n.bmax[0]); f[5] = bits(n.bmax[1]); f[6] = bits(n.bmax[2]); f[7] = word;
     }
 
+    return d;
+}
+
+DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t) {
+    DeviceLayout d = flatten_tree_only(g, t);
     const uint64_t nt = g.tris.size();
     d.tri_index.resize(4 * (nt ? nt : 1));
     d.tri_normal.resize(4 * (nt ? nt : 1));

@@ -76,5 +76,6 @@ struct DeviceLayout {
 };
 
 DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t);
+DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t);   // nodes8 / nodes32 / packets only
 
 }  // namespace rtb

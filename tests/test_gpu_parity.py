@@ -263,25 +263,58 @@ def test_fast_mode_within_north_star_tolerance(rt, oracle_mod, name):
 
 
 @pytest.mark.parametrize("name", SCENES)
-def test_ordered_traversal_same_hits(rt, oracle_mod, name):
-    """front-to-back traversal with the reference's arithmetic: same closest t by construction; only exact-t ties between
-    different triangles may resolve differently (none on these scenes' primary rays)"""
+def test_accelerated_mode_same_hits(rt, oracle_mod, name):
+    """RT_FLAG_ORDERED: the backend's own deeper tree, front-to-back (rt_kd8.cuh).  Same arithmetic per triangle, so t/u/v are
+    the reference's bits; exact-t ties between different triangles are re-run in reference order -> identical output"""
     s, data = gpu_scene(rt, name)
     o = oracle_mod.Oracle(data)
+    assert s.info.accel_n_nodes > s.info.n_nodes or name == "hw12_scene4"
     hits = s.trace_primary(rt.default_params(flags=rt.FLAG_ORDERED)).reshape(-1)
-    tuv, tri = o.trace(o.primary_rays(), True)
-    assert np.array_equal(hits["tri"] >= 0, tri >= 0)
-    h = tri >= 0
-    assert np.array_equal(hits["t"][h].view(np.uint32), tuv[h, 0].view(np.uint32))
-    assert (hits["tri"] == tri).mean() >= 0.9999
-    rays = random_rays(100_000, 23)
+    assert_hits_equal(hits, *o.trace(o.primary_rays(), True))
+    rays = random_rays(200_000, 23)
     n5, bx, _ = s.tree()
     rays[:, :3] = rays[:, :3] * (bx[0, 3:] - bx[0, :3]).max() / 2 + (bx[0, :3] + bx[0, 3:]) / 2
-    got = s.trace_closest(rays, False, flags=rt.FLAG_ORDERED)
-    tuv, tri = o.trace(rays, False)
-    assert np.array_equal(got["tri"] >= 0, tri >= 0)
-    h = tri >= 0
-    assert np.array_equal(got["t"][h].view(np.uint32), tuv[h, 0].view(np.uint32))
+    for cull in (False, True):
+        assert_hits_equal(s.trace_closest(rays, cull, flags=rt.FLAG_ORDERED), *o.trace(rays, cull))
+
+
+@pytest.mark.parametrize("name,key,depth", CONFIGS)
+def test_accelerated_mode_frames_bit_exact(rt, golden, name, key, depth):
+    """the accelerated mode renders the same float frame, bit for bit, and issues the same queries; only the shadow-hit
+    STATISTIC differs (it does not look for hits beyond the light)"""
+    g = golden["scenes"][name]["configs"][key]
+    s, _ = gpu_scene(rt, name)
+    img = s.render_frame(rt.default_params(max_ray_depth=depth, flags=rt.FLAG_ORDERED))
+    assert sha(img) == g["sha256_f32"]
+    c = s.counters()
+    assert (c.primary, c.primary_hits) == (g["counts"]["cull"], g["counts"]["cull_hit"])
+    assert c.shadow + c.secondary == g["counts"]["nocull"]
+    assert c.shadow_hits + c.secondary_hits <= g["counts"]["nocull_hit"]
+
+
+def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod):
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=60_000, seed=5, width=320, height=200))
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64)
+    o = oracle_mod.Oracle(data, 24, 64)
+    assert_hits_equal(s.trace_primary(rt.default_params(flags=rt.FLAG_ORDERED)).reshape(-1), *o.trace(o.primary_rays(), True))
+    rays = random_rays(100_000, 3, -1.4, 1.4)
+    assert_hits_equal(s.trace_closest(rays, False, flags=rt.FLAG_ORDERED), *o.trace(rays, False))
+    max_t = np.random.default_rng(4).uniform(0.01, 2.5, len(rays)).astype(np.float32)
+    want, _ = o.occluded(rays, max_t)
+    assert np.array_equal(s.trace_occluded(rays, max_t, flags=rt.FLAG_ORDERED), want)
+    img = s.render_frame(rt.default_params(flags=rt.FLAG_ORDERED))
+    oi, _ = o.render(oracle_mod.default_params())
+    assert np.array_equal(img.view(np.uint32), oi.view(np.uint32))
+    s.close()
+    for name in ("hw15_scene2", "hw11_scene8"):                 # refractive pass-through in the shadow loop
+        s, data = gpu_scene(rt, name)
+        o = oracle_mod.Oracle(data)
+        n5, bx, _ = s.tree()
+        rays = random_rays(100_000, 31)
+        rays[:, :3] = rays[:, :3] * (bx[0, 3:] - bx[0, :3]).max() / 2 + (bx[0, :3] + bx[0, 3:]) / 2
+        max_t = np.random.default_rng(6).uniform(0.01, 6.0, len(rays)).astype(np.float32)
+        want, _ = o.occluded(rays, max_t)
+        assert np.array_equal(s.trace_occluded(rays, max_t, flags=rt.FLAG_ORDERED), want)
 
 
 # ---- device-pointer entry points, threading ----------------------------------------------------------------------------------------

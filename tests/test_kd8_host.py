@@ -1,0 +1,99 @@
+"""The accelerated traversal (simd-raytracer_b200/csrc/rt_kd8.cuh, RT_FLAG_ORDERED) checked on the CPU: the same source the
+CUDA kernels compile is built as plain C++ (tests/helpers/kd8_host.cpp) and run over the product's flattened tree
+(rt_scene_get_accel_layout, host-only scene) against the oracle's reference-order traversal.  No product compute runs here."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from .conftest import REPO, SCENES, resized, scene_bytes
+from .helpers import crtscene
+
+
+@pytest.fixture(scope="module")
+def kd8(tmp_path_factory):
+    out = tmp_path_factory.mktemp("kd8") / "libkd8_host.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                           os.path.join(REPO, "tests", "helpers", "kd8_host.cpp"), "-o", str(out)])
+    lib = C.CDLL(str(out))
+    lib.kd8_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
+                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def trace(scene, rays, cull, fast=False, t_far=None, any_hit=False, eps=np.float32(1e-6)):
+        nodes8, packets, root = scene.accel_layout()
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        tuv = np.zeros((len(rays), 3), np.float32)
+        tri = np.zeros(len(rays), np.int32)
+        tie = np.zeros(len(rays), np.uint8)
+        far = None if t_far is None else np.ascontiguousarray(t_far, np.float32)
+        lib.kd8_trace_batch(nodes8.ctypes.data, packets.ctypes.data, root.ctypes.data, rays.ctypes.data, len(rays), int(cull), int(fast),
+                            C.c_float(eps), None if far is None else far.ctypes.data, int(any_hit), tuv.ctypes.data, tri.ctypes.data, tie.ctypes.data)
+        return tuv, tri, tie.astype(bool)
+    return trace
+
+
+def scene_rays(o, s, n=150_000, seed=3):
+    rng = np.random.default_rng(seed)
+    _, bx, _ = s.tree()
+    c, ext = (bx[0, :3] + bx[0, 3:]) / 2, (bx[0, 3:] - bx[0, :3]).max()
+    org = rng.uniform(-1, 1, (n, 3)) * ext * 0.9 + c
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, d], axis=1).astype(np.float32)
+    rays[0, 3:] = (0, 0, -1); rays[1, 3:] = (1, 0, 0); rays[2, 3:] = (0, -1, 0); rays[3, 3:] = (0, 0, 0); rays[4, :3] = np.nan
+    rays[5, 3:] = (-0.0, 1, 0); rays[6, :3] = c; rays[7, :3] = bx[0, :3]
+    return rays
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_kd8_equals_reference_traversal(rt, oracle_mod, kd8, name):
+    """primary rays (culling) at reduced resolution + incoherent rays (no culling): same hit/miss, t bit-exact, and the same
+    triangle with the same u/v on every ray the traversal does not flag as an exact-t tie between different triangles
+    (flagged rays - a shared edge, or config 1's cube standing on the floor - are re-run in reference order on the device)"""
+    data = resized(scene_bytes(name), 640, 360 if name != "hw15_scene2" else 640)
+    s = rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY)
+    o = oracle_mod.Oracle(data)
+    assert s.info.accel_n_nodes >= s.info.n_nodes
+    for rays, cull in ((o.primary_rays(), True), (scene_rays(o, s), False)):
+        want_tuv, want_tri = o.trace(rays, cull)
+        tuv, tri, tie = kd8(s, rays, cull)
+        assert np.array_equal(tri >= 0, want_tri >= 0)
+        h = want_tri >= 0
+        assert np.array_equal(tuv[h, 0].view(np.uint32), want_tuv[h, 0].view(np.uint32))
+        assert tie.mean() < 2e-3, (name, cull, tie.mean())
+        assert np.array_equal(tri[~tie], want_tri[~tie])
+        assert np.array_equal(tuv[h & ~tie].view(np.uint32), want_tuv[h & ~tie].view(np.uint32))
+
+
+@pytest.mark.parametrize("kd,accel", [((8, 64), (0, 0)), ((24, 64), (0, 0)), ((8, 64), (20, 2)), ((8, 64), (6, 128))])
+def test_kd8_synthetic_mesh(rt, oracle_mod, kd8, kd, accel):
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=20_000, seed=9, width=160, height=120))
+    s = rt.Scene.from_rtsc(data, kd_max_depth=kd[0], kd_max_leaf_size=kd[1], device=rt.DEVICE_HOST_ONLY, accel=accel)
+    o = oracle_mod.Oracle(data, *kd)
+    for rays, cull in ((o.primary_rays(), True), (scene_rays(o, s, 60_000), False)):
+        want_tuv, want_tri = o.trace(rays, cull)
+        tuv, tri, tie = kd8(s, rays, cull)
+        assert np.array_equal(tri[~tie], want_tri[~tie]) and np.array_equal(tri >= 0, want_tri >= 0)
+        h = (want_tri >= 0) & ~tie
+        assert np.array_equal(tuv[h].view(np.uint32), want_tuv[h].view(np.uint32))
+
+
+def test_kd8_any_hit_and_far_limit(rt, oracle_mod, kd8):
+    """t_far: a hit beyond it may be reported as a miss, a hit inside it never; any_hit returns SOME hit inside it"""
+    data = resized(scene_bytes("hw09_scene5"), 320, 180)
+    s = rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY)
+    o = oracle_mod.Oracle(data)
+    rays = scene_rays(o, s, 80_000, seed=8)
+    want_tuv, want_tri = o.trace(rays, False)
+    far = np.random.default_rng(2).uniform(0.05, 3.0, len(rays)).astype(np.float32)
+    inside = (want_tri >= 0) & (want_tuv[:, 0] <= far)
+    tuv, tri, tie = kd8(s, rays, False, t_far=far)
+    inside &= ~tie
+    assert np.array_equal(tri[inside], want_tri[inside]) and np.array_equal(tuv[inside, 0], want_tuv[inside, 0])
+    assert not np.any((tri >= 0) & (tuv[:, 0] <= far) & ~((want_tri >= 0) & (want_tuv[:, 0] <= far)))
+    tuv, tri, _ = kd8(s, rays, False, t_far=far, any_hit=True)
+    assert np.array_equal((tri >= 0) & (tuv[:, 0] <= far), (want_tri >= 0) & (want_tuv[:, 0] <= far))
