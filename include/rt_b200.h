@@ -88,8 +88,8 @@ typedef struct rt_build_opts {
     uint32_t kd_max_depth;           /* default 8  (kd_tree_simd.hpp:65) */
     uint32_t kd_max_leaf_size;       /* default 64 (kd_tree_simd.hpp:66) */
     int32_t device;                  /* CUDA ordinal; RT_DEVICE_HOST_ONLY builds tree + layout without a GPU */
-    /* the backend's own, deeper tree used by RT_FLAG_ORDERED (same builder, more depth, small leaves).
-     * 0 / 0 = automatic: depth min(max(kd_max_depth, ceil(log2(n_triangles)) + 4), 24), leaf size min(kd_max_leaf_size, 8) */
+    /* the backend's own tree used by RT_FLAG_ORDERED (surface-area heuristic, clipped triangles).
+     * 0 = automatic: depth min(30, 8 + 1.3 log2(n_triangles)); the heuristic decides where leaves end (leaf size is a floor) */
     uint32_t accel_max_depth;
     uint32_t accel_max_leaf_size;
 } rt_build_opts;
@@ -130,7 +130,7 @@ typedef struct rt_scene_info {
     double build_seconds, flatten_seconds, upload_seconds;
     int32_t device;
     uint32_t accel_max_depth, accel_max_leaf_size;       /* parameters the accelerated tree was built with */
-    uint64_t accel_n_nodes, accel_n_leaf_refs, accel_n_packets, accel_tree_depth;
+    uint64_t accel_n_nodes, accel_n_leaf_refs, accel_n_leaves, accel_tree_depth;
 } rt_scene_info;
 
 typedef struct rt_counters {         /* of the last rt_render_frame* call */
@@ -171,8 +171,9 @@ RT_API int rt_scene_get_info(const rt_scene* s, rt_scene_info* info);
 RT_API int rt_scene_get_tree(const rt_scene* s, uint64_t* node5, float* boxes, uint32_t* refs);
 /*   nodes8 : the 8-byte device nodes (2 x u32 per node); packets: 40 x u32 per 4-triangle SoA packet          */
 RT_API int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets);
-/* same for the accelerated tree (sizes in rt_scene_info.accel_*); root6 = min xyz, max xyz of the root box                  */
-RT_API int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets, float* root6);
+/* the accelerated tree (sizes in rt_scene_info.accel_*): 8-byte nodes; tris12 = 12 x u32 per leaf reference
+ * { v0.xyz, id } { e1.xyz, 0 } { e2.xyz, 0 }; root6 = min xyz, max xyz of the root box                                          */
+RT_API int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* tris12, float* root6);
 /*   tri9 = v0,e1,e2 per triangle; face normals; vertex normals (mesh-concatenated vertex order)               */
 RT_API int rt_scene_get_geometry(const rt_scene* s, float* tri9, float* face_normals, float* vertex_normals);
 

@@ -92,7 +92,7 @@ class SceneInfo(C.Structure):
                 ("device_bytes", C.c_uint64), ("build_seconds", C.c_double), ("flatten_seconds", C.c_double),
                 ("upload_seconds", C.c_double), ("device", C.c_int32),
                 ("accel_max_depth", C.c_uint32), ("accel_max_leaf_size", C.c_uint32), ("accel_n_nodes", C.c_uint64),
-                ("accel_n_leaf_refs", C.c_uint64), ("accel_n_packets", C.c_uint64), ("accel_tree_depth", C.c_uint64)]
+                ("accel_n_leaf_refs", C.c_uint64), ("accel_n_leaves", C.c_uint64), ("accel_tree_depth", C.c_uint64)]
 
 
 class Counters(C.Structure):
@@ -287,12 +287,12 @@ class Scene:
         return nodes8, packets
 
     def accel_layout(self):
-        """nodes8 / packets / root box of the backend's own deeper tree (RT_FLAG_ORDERED)"""
+        """nodes8 / 48-byte triangle records / root box of the backend's own tree (RT_FLAG_ORDERED)"""
         nodes8 = np.zeros((self.info.accel_n_nodes, 2), np.uint32)
-        packets = np.zeros((self.info.accel_n_packets, 10, 4), np.uint32)
+        tris = np.zeros((max(self.info.accel_n_leaf_refs, 1), 12), np.uint32)
         root = np.zeros(6, np.float32)
-        _check(lib.rt_scene_get_accel_layout(self.h, nodes8.ctypes.data, packets.ctypes.data, root.ctypes.data))
-        return nodes8, packets, root
+        _check(lib.rt_scene_get_accel_layout(self.h, nodes8.ctypes.data, tris.ctypes.data, root.ctypes.data))
+        return nodes8, tris, root
 
     def geometry(self):
         tri9 = np.zeros((self.info.n_triangles, 9), np.float32)

@@ -18,9 +18,10 @@ LIB = os.path.join(HERE, "librt_b200.so")
 BUILD = os.path.join(HERE, "build")
 
 CU = [os.path.join(HERE, "csrc", "rt_api.cu")]
-CPP = [os.path.join(HERE, "host", "kd_build.cpp"), os.path.join(HERE, "host", "scene_io.cpp")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("rt_device.cuh", "rt_wavefront.cuh")] + \
-       [os.path.join(HERE, "host", f) for f in ("kd_build.hpp", "scene.hpp", "json.hpp")] + \
+CPP = [os.path.join(HERE, "host", f) for f in ("kd_build.cpp", "kd_sah.cpp", "scene_io.cpp")]
+import glob  # noqa: E402
+
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "host", "*.hpp"))) + \
        [os.path.join(REPO, "include", "rt_b200.h"), os.path.abspath(__file__)]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -19,7 +19,7 @@
 #include "../../include/rt_b200.h"
 #include "../host/kd_build.hpp"
 #include "../host/scene.hpp"
-#include "rt_wavefront.cuh"
+#include "rt_stream.cuh"
 
 using namespace rtb;
 
@@ -95,7 +95,7 @@ struct rt_scene {
     KdTree tree;
     DeviceLayout layout;
     KdTree accel_tree;               // the backend's own deeper tree (RT_FLAG_ORDERED)
-    DeviceLayout accel_layout;
+    AccelLayout accel_layout;
     rt_scene_info info{};
 
     int device = RT_DEVICE_HOST_ONLY;
@@ -127,6 +127,7 @@ struct rt_scene {
 
     std::mutex mtx;
     int g_primary[4] = {0, 0, 0, 0}, g_trace[4] = {0, 0, 0, 0}, g_shadow[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g_shade[2] = {0, 0}, g_resolve = 0;
+    int gs_primary[2] = {0, 0}, gs_level[2] = {0, 0}, gs_shadow[4] = {0, 0, 0, 0};   // stream kernels (accelerated mode)
 
     ~rt_scene() {
         if (device >= 0) {
@@ -184,7 +185,7 @@ void upload_scene(rt_scene* s) {
     DScene& d = s->d;
     auto keep = [&](auto* p) { s->owned.push_back((void*)p); return p; };
     d.a_nodes8 = keep(upload<uint32_t>(s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size(), bytes));
-    d.a_packets = reinterpret_cast<const float*>(keep(upload<float4>(s->accel_layout.packets.data(), s->accel_layout.packets.size() / 4, bytes)));
+    d.a_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->accel_layout.tris.data(), s->accel_layout.tris.size() / 4, bytes)));
     d.nodes32 = keep(upload<float4>(L.nodes32.data(), L.nodes32.size() / 4, bytes));
     d.packets = keep(upload<float4>(L.packets.data(), L.packets.size() / 4, bytes));
     d.tri_index = keep(upload<uint4>(L.tri_index.data(), L.tri_index.size() / 4, bytes));
@@ -234,14 +235,15 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         const uint64_t n = std::max<uint64_t>(s->geom.tris.size(), 1);
         uint32_t lg = 0;
         while ((1ull << lg) < n) ++lg;
-        const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : std::min<uint32_t>(std::max<uint32_t>(o.kd_max_depth, lg + 4), 24);
-        const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : std::min<uint32_t>(o.kd_max_leaf_size, 8);
+        // the usual kd-tree depth bound 8 + 1.3 log2(N); the surface-area heuristic stops earlier where it does not pay
+        const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : std::min<uint32_t>(30, 8 + (13 * lg + 9) / 10);
+        const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : 2;
         if (ad > 30) throw rt_error(RT_ERR_BAD_ARG, "accel_max_depth > 30");
-        s->accel_tree = build_kd_tree(s->geom, ad, al);
-        s->accel_layout = flatten_tree_only(s->geom, s->accel_tree);
+        s->accel_tree = build_kd_tree_sah(s->geom, ad, al);
+        s->accel_layout = flatten_accel(s->geom, s->accel_tree);
         s->info.accel_max_depth = ad; s->info.accel_max_leaf_size = al;
         s->info.accel_n_nodes = s->accel_tree.nodes.size(); s->info.accel_n_leaf_refs = s->accel_tree.refs.size();
-        s->info.accel_n_packets = s->accel_layout.n_packets; s->info.accel_tree_depth = s->accel_tree.depth;
+        s->info.accel_n_leaves = s->accel_tree.n_leaves; s->info.accel_tree_depth = s->accel_tree.depth;
     }
     s->info.flatten_seconds = now_s() - t0;
     s->info.width = s->host.width; s->info.height = s->host.height;
@@ -408,12 +410,20 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     const bool tr = s->d.has_transmissive != 0;
     if (!g_resolve) g_resolve = grid_for(s, k_resolve);
     if (!g_shade[has_gi]) g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
-#define CALL(F, O)                                                                         \
-    if (!g_primary[mi]) g_primary[mi] = grid_for(s, k_primary<F, O>);                      \
-    if (!g_trace[mi]) g_trace[mi] = grid_for(s, k_trace_level<F, O>);                      \
-    if (!g_shadow[mi * 2 + tr]) g_shadow[mi * 2 + tr] = tr ? grid_for(s, k_shadow<true, F, O>) : grid_for(s, k_shadow<false, F, O>)
-    DISPATCH_MODE(m, CALL);
-#undef CALL
+    const int fi = m.fast ? 1 : 0;
+    if (m.ordered) {
+        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>) : grid_for(s, k_stream_primary<false>);
+        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>) : grid_for(s, k_stream_level<false>);
+        if (!s->gs_shadow[fi * 2 + tr])
+            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>) : grid_for(s, k_stream_shadow<true, false>))
+                                           : (m.fast ? grid_for(s, k_stream_shadow<false, true>) : grid_for(s, k_stream_shadow<false, false>));
+    } else {
+        if (!g_primary[mi]) g_primary[mi] = m.fast ? grid_for(s, k_primary<true, false>) : grid_for(s, k_primary<false, false>);
+        if (!g_trace[mi]) g_trace[mi] = m.fast ? grid_for(s, k_trace_level<true, false>) : grid_for(s, k_trace_level<false, false>);
+        if (!g_shadow[mi * 2 + tr])
+            g_shadow[mi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_shadow<true, true, false>) : grid_for(s, k_shadow<true, false, false>))
+                                       : (m.fast ? grid_for(s, k_shadow<false, true, false>) : grid_for(s, k_shadow<false, false, false>));
+    }
 
     uint32_t done = 0;
     while (done < spp) {
@@ -433,17 +443,21 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
             k_pass_init<<<1, 256, 0, st>>>(s->ps, uint32_t(n0));
             CK(cudaGetLastError());
             timed(TC_PRIMARY, [&] {
-#define CALL(F, O) k_primary<F, O><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot)
-                DISPATCH_MODE(m, CALL);
-#undef CALL
+                if (m.ordered) {
+                    if (m.fast) k_stream_primary<true><<<s->gs_primary[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+                    else k_stream_primary<false><<<s->gs_primary[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+                } else if (m.fast) k_primary<true, false><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+                else k_primary<false, false><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
             });
             ++slot;
             for (uint32_t lvl = 0; lvl < levels; ++lvl) {
                 if (lvl > 0) {
                     timed(TC_SECONDARY, [&] {
-#define CALL(F, O) k_trace_level<F, O><<<g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot)
-                        DISPATCH_MODE(m, CALL);
-#undef CALL
+                        if (m.ordered) {
+                            if (m.fast) k_stream_level<true><<<s->gs_level[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                            else k_stream_level<false><<<s->gs_level[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                        } else if (m.fast) k_trace_level<true, false><<<g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                        else k_trace_level<false, false><<<g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
                     });
                     ++slot;
                 }
@@ -455,11 +469,19 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
             }
             if (!s->host.lights.empty()) {
                 timed(TC_SHADOW, [&] {
-#define CALL(F, O)                                                                                               \
-    if (tr) k_shadow<true, F, O><<<g_shadow[mi * 2 + 1], 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);  \
-    else k_shadow<false, F, O><<<g_shadow[mi * 2], 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot)
-                    DISPATCH_MODE(m, CALL);
-#undef CALL
+                    if (m.ordered) {
+                        const int g = s->gs_shadow[fi * 2 + tr];
+                        if (tr) { if (m.fast) k_stream_shadow<true, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                                  else k_stream_shadow<true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                        else { if (m.fast) k_stream_shadow<false, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                               else k_stream_shadow<false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                    } else {
+                        const int g = g_shadow[mi * 2 + tr];
+                        if (tr) { if (m.fast) k_shadow<true, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                                  else k_shadow<true, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                        else { if (m.fast) k_shadow<false, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                               else k_shadow<false, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                    }
                 });
                 ++slot;
             }
@@ -574,10 +596,10 @@ int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* pa
     return RT_OK;
 }
 
-int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets, float* root6) {
+int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* tris12, float* root6) {
     if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
     if (nodes8) std::memcpy(nodes8, s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size() * 4);
-    if (packets) std::memcpy(packets, s->accel_layout.packets.data(), size_t(s->accel_layout.n_packets) * PACKET_WORDS * 4);
+    if (tris12) std::memcpy(tris12, s->accel_layout.tris.data(), size_t(s->accel_layout.n_refs) * 12 * 4);
     if (root6) { std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12); }
     return RT_OK;
 }

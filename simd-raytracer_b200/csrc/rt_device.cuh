@@ -24,7 +24,7 @@ struct DLight { float pos[3], intensity; };                                     
 
 struct DScene {
     const uint32_t* __restrict__ a_nodes8;  // accelerated mode: 8-byte nodes of the backend's own deeper kd-tree (rt_kd8.cuh)
-    const float* __restrict__ a_packets;    //                   and its leaf packets
+    const float* __restrict__ a_tris;       //                   and its 48-byte leaf triangle records
     const float4* __restrict__ nodes32;     // 2 x float4 per node: box + the same two words (reference-order traversal)
     const float4* __restrict__ packets;     // 10 x float4 per 4-triangle SoA packet
     const uint4* __restrict__ tri_index;    // vi0, vi1, vi2, material
@@ -298,7 +298,7 @@ __device__ __forceinline__ Hit trace_any(const DScene& sc, bool active, V3 o, V3
         Hit h; h.t = FLT_MAX; h.u = 0.0f; h.v = 0.0f; h.tri = -1;
         bool tie = false;
         if (active) {
-            const KdHit k = kd8_trace<CULL, FAST>(sc.a_nodes8, sc.a_packets, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, eps,
+            const KdHit k = kd8_trace<CULL, FAST>(sc.a_nodes8, sc.a_tris, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, eps,
                                                   t_far, any_hit);
             h.t = k.t; h.u = k.u; h.v = k.v; h.tri = k.tri;
             tie = !any_hit && k.tri >= 0 && k.tie_t == k.t;

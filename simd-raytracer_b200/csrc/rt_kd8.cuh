@@ -15,7 +15,7 @@
 // The tree is built by the same host builder (host/kd_build.cpp) with more depth and small leaves, flattened to
 //   nodes8  : 8 B per node.  inner: { f32 split, u32 axis | has0<<2 | has1<<3 | child1<<4 }, child0 = index+1
 //                            leaf : { u32 first_packet, u32 3 | n_packets<<2 }
-//   packets : 160 B, 4 triangles SoA (v0, e1, e2 rows + ids)
+//   tris    : 48 B per leaf reference, array of structures { v0.xyz, id } { e1.xyz, - } { e2.xyz, - }
 // Node boxes are implicit: the ray carries its parametric interval [t0,t1] down the tree.  Interval comparisons are
 // widened by a relative slack so that rounding can only ADD a visit, never drop one; hits are never clipped to the
 // leaf interval, pruning uses only "the node starts beyond the closest hit so far".
@@ -33,6 +33,11 @@
 #define RT_HD __host__ __device__ __forceinline__
 #else
 #define RT_HD inline
+#endif
+
+#ifndef KD8_COUNT_NODE
+#define KD8_COUNT_NODE() ((void)0)      // instrumentation hooks for host-side experiments
+#define KD8_COUNT_TRI() ((void)0)
 #endif
 
 namespace rtb {
@@ -127,18 +132,19 @@ RT_HD int kd_as_int(float f) {
 #endif
 }
 
+// leaf triangles of the accelerated tree: 48 B per reference, three aligned 16-byte rows
+//   { v0.xyz, id }  { e1.xyz, - }  { e2.xyz, - }
+// (one ray per thread walks small leaves, so array-of-structures beats the 4-wide SoA packets of the reference-order path:
+// no padding lanes, three LDG.128 per triangle)
+constexpr uint32_t KD8_TRI_FLOATS = 12;
+
 template <bool CULL, bool FAST>
-RT_HD void kd_test_packets(const float* pk, uint32_t count, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
-                           KdHit& best) {
-    for (uint32_t p = 0; p < count; ++p, pk += 40) {
-        const KdRow v0x = kd_load_row(pk), v0y = kd_load_row(pk + 4), v0z = kd_load_row(pk + 8);
-        const KdRow e1x = kd_load_row(pk + 12), e1y = kd_load_row(pk + 16), e1z = kd_load_row(pk + 20);
-        const KdRow e2x = kd_load_row(pk + 24), e2y = kd_load_row(pk + 28), e2z = kd_load_row(pk + 32);
-        const KdRow id = kd_load_row(pk + 36);
-        kd_test_tri<CULL, FAST>(v0x.x, v0y.x, v0z.x, e1x.x, e1y.x, e1z.x, e2x.x, e2y.x, e2z.x, kd_as_int(id.x), ox, oy, oz, dx, dy, dz, eps, best);
-        kd_test_tri<CULL, FAST>(v0x.y, v0y.y, v0z.y, e1x.y, e1y.y, e1z.y, e2x.y, e2y.y, e2z.y, kd_as_int(id.y), ox, oy, oz, dx, dy, dz, eps, best);
-        kd_test_tri<CULL, FAST>(v0x.z, v0y.z, v0z.z, e1x.z, e1y.z, e1z.z, e2x.z, e2y.z, e2z.z, kd_as_int(id.z), ox, oy, oz, dx, dy, dz, eps, best);
-        kd_test_tri<CULL, FAST>(v0x.w, v0y.w, v0z.w, e1x.w, e1y.w, e1z.w, e2x.w, e2y.w, e2z.w, kd_as_int(id.w), ox, oy, oz, dx, dy, dz, eps, best);
+RT_HD void kd_test_leaf(const float* tr, uint32_t count, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
+                        KdHit& best) {
+    for (uint32_t k = 0; k < count; ++k, tr += KD8_TRI_FLOATS) {
+        KD8_COUNT_TRI();
+        const KdRow a = kd_load_row(tr), b = kd_load_row(tr + 4), c = kd_load_row(tr + 8);
+        kd_test_tri<CULL, FAST>(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, kd_as_int(a.w), ox, oy, oz, dx, dy, dz, eps, best);
     }
 }
 
@@ -146,79 +152,116 @@ constexpr int KD8_STACK = 32;     // tree depth is capped at 30 by the host
 
 struct KdStackEntry { uint32_t node; float t0, t1; };
 
-// Closest hit with t <= t_far (t_far = FLT_MAX for a plain query).  any_hit: return at the first hit inside [.., t_far].
-template <bool CULL, bool FAST>
-RT_HD KdHit kd8_trace(const uint32_t* __restrict__ nodes8, const float* __restrict__ packets, const float* root_min, const float* root_max,
-                      float ox, float oy, float oz, float dx, float dy, float dz, float eps, float t_far, bool any_hit) {
-    KdHit best; best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.tri = -1; best.tie_t = -1.0f;
-    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+// Traversal state of one ray, so that a kernel can advance many rays in lock step and refill finished lanes
+// (rt_stream.cuh).  phase: WALK = standing at `node` with interval [t0,t1]; LEAF = parked at a leaf that still has to be
+// tested (leaf_first / leaf_count); DONE = query finished, `best` is the answer.
+enum : int { KD8_WALK = 0, KD8_LEAF = 1, KD8_DONE = 2 };
+
+struct Kd8State {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+    float t0, t1, t_far;
+    uint32_t node, leaf_first, leaf_count;
+    int sp, phase;
+    bool any_hit;
+    KdHit best;
+};   // scalars only, so that it lives in registers; the stack is a separate (local-memory) array passed alongside
+
+// returns false when the ray misses the root box (the query is then finished: a miss)
+RT_HD bool kd8_init(Kd8State& s, const float* root_min, const float* root_max, float ox, float oy, float oz, float dx, float dy, float dz,
+                    float t_far, bool any_hit) {
+    s.ox = ox; s.oy = oy; s.oz = oz; s.dx = dx; s.dy = dy; s.dz = dz;
+    s.ix = 1.0f / dx; s.iy = 1.0f / dy; s.iz = 1.0f / dz;
+    s.t_far = t_far; s.any_hit = any_hit;
+    s.best.t = FLT_MAX; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = -1; s.best.tie_t = -1.0f;
+    s.node = 0; s.sp = 0; s.phase = KD8_DONE; s.leaf_first = 0; s.leaf_count = 0;
     // parametric interval of the root box (aabb3.hpp:74-90 semantics: NaN from 0*inf leaves a bound unchanged)
     float t0 = 0.0f, t1 = FLT_MAX;
-    {
-        const float ax = (root_min[0] - ox) * ix, bx = (root_max[0] - ox) * ix;
-        const float ay = (root_min[1] - oy) * iy, by = (root_max[1] - oy) * iy;
-        const float az = (root_min[2] - oz) * iz, bz = (root_max[2] - oz) * iz;
-        t0 = kd_max(t0, (bx < ax) ? bx : ax); t1 = kd_min(t1, (bx < ax) ? ax : bx);
-        t0 = kd_max(t0, (by < ay) ? by : ay); t1 = kd_min(t1, (by < ay) ? ay : by);
-        t0 = kd_max(t0, (bz < az) ? bz : az); t1 = kd_min(t1, (bz < az) ? az : bz);
-    }
+    const float ax = (root_min[0] - ox) * s.ix, bx = (root_max[0] - ox) * s.ix;
+    const float ay = (root_min[1] - oy) * s.iy, by = (root_max[1] - oy) * s.iy;
+    const float az = (root_min[2] - oz) * s.iz, bz = (root_max[2] - oz) * s.iz;
+    t0 = kd_max(t0, (bx < ax) ? bx : ax); t1 = kd_min(t1, (bx < ax) ? ax : bx);
+    t0 = kd_max(t0, (by < ay) ? by : ay); t1 = kd_min(t1, (by < ay) ? ay : by);
+    t0 = kd_max(t0, (bz < az) ? bz : az); t1 = kd_min(t1, (bz < az) ? az : bz);
     const float S = 2e-6f;                       // relative widening of every interval comparison
-    if (t1 + S * fabsf(t1) < t0) return best;
-    t0 = kd_max(0.0f, t0 - S * fabsf(t0));
-    t1 = t1 + S * fabsf(t1);
+    if (t1 + S * fabsf(t1) < t0) return false;
+    s.t0 = kd_max(0.0f, t0 - S * fabsf(t0));
+    s.t1 = t1 + S * fabsf(t1);
+    if (!(s.t0 <= t_far)) return false;
+    s.phase = KD8_WALK;
+    return true;
+}
 
-    KdStackEntry stack[KD8_STACK];
-    int sp = 0;
-    uint32_t node = 0;
-    for (;;) {
-        float limit = kd_min(best.t, t_far);
-        bool pop = t0 > limit;
-        if (!pop) {
-            const uint32_t first = nodes8[2 * node], word = nodes8[2 * node + 1];
-            const uint32_t axis = word & 3u;
-            if (axis == 3u) {
-                kd_test_packets<CULL, FAST>(packets + size_t(first) * 40u, word >> 2, ox, oy, oz, dx, dy, dz, eps, best);
-                if (any_hit && best.t <= t_far) return best;
-                pop = true;
-            } else {
-                const float split = kd_bits_to_float(first);
-                const float oa = axis == 0u ? ox : (axis == 1u ? oy : oz);
-                const float da = axis == 0u ? dx : (axis == 1u ? dy : dz);
-                const float ia = axis == 0u ? ix : (axis == 1u ? iy : iz);
-                const uint32_t c0 = (word & 4u) ? node + 1u : 0xFFFFFFFFu;       // lower half  [min, split]
-                const uint32_t c1 = (word & 8u) ? (word >> 4) : 0xFFFFFFFFu;     // upper half  [split, max]
-                const bool below = oa < split;
-                const uint32_t near_c = below ? c0 : c1, far_c = below ? c1 : c0;
-                const float ts = (split - oa) * ia;                               // exact sign; +-inf for da == 0; NaN if also oa == split
-                bool go_near = true, go_far = true;
-                float near_t1 = t1, far_t0 = t0;
-                if (oa == split || ts != ts) {
-                    // origin on the plane: both halves, intervals kept
-                } else if (ts < 0.0f || da == 0.0f) {
-                    go_far = false;                                               // moving away from / parallel to the plane
-                } else {
-                    const float w = S * kd_max(fabsf(ts), kd_max(fabsf(t0), fabsf(t1)));
-                    if (ts > t1 + w) go_far = false;                              // leaves the node before the plane
-                    else if (ts < t0 - w) go_near = false;                        // crossed the plane before entering the node
-                    else { near_t1 = kd_min(t1, ts + w); far_t0 = kd_max(t0, ts - w); }
-                }
-                go_near = go_near && near_c != 0xFFFFFFFFu;
-                go_far = go_far && far_c != 0xFFFFFFFFu;
-                if (go_near) {
-                    if (go_far) { stack[sp].node = far_c; stack[sp].t0 = far_t0; stack[sp].t1 = t1; ++sp; }
-                    node = near_c; t1 = near_t1;
-                } else if (go_far) {
-                    node = far_c; t0 = far_t0;
-                } else pop = true;
-            }
-        }
-        if (pop) {
-            if (!sp) break;
-            --sp;
-            node = stack[sp].node; t0 = stack[sp].t0; t1 = stack[sp].t1;
-        }
+RT_HD void kd8_pop(Kd8State& s, const KdStackEntry* stack) {
+    if (!s.sp) { s.phase = KD8_DONE; return; }
+    --s.sp;
+    s.node = stack[s.sp].node; s.t0 = stack[s.sp].t0; s.t1 = stack[s.sp].t1;
+    s.phase = KD8_WALK;
+}
+
+// One node visit (phase WALK): prune and pop, go down one level, or park at a leaf.
+RT_HD void kd8_node_step(Kd8State& s, KdStackEntry* stack, const uint32_t* __restrict__ nodes8) {
+    const float S = 2e-6f;
+    if (s.t0 > kd_min(s.best.t, s.t_far)) { kd8_pop(s, stack); return; }         // the node starts beyond the closest hit so far
+    KD8_COUNT_NODE();
+#if defined(__CUDA_ARCH__)
+    const uint2 nd = __ldg(reinterpret_cast<const uint2*>(nodes8) + s.node);
+    const uint32_t first = nd.x, word = nd.y;
+#else
+    const uint32_t first = nodes8[2 * s.node], word = nodes8[2 * s.node + 1];
+#endif
+    const uint32_t axis = word & 3u;
+    if (axis == 3u) { s.leaf_first = first; s.leaf_count = word >> 2; s.phase = KD8_LEAF; return; }
+    const float split = kd_bits_to_float(first);
+    const float oa = axis == 0u ? s.ox : (axis == 1u ? s.oy : s.oz);
+    const float da = axis == 0u ? s.dx : (axis == 1u ? s.dy : s.dz);
+    const float ia = axis == 0u ? s.ix : (axis == 1u ? s.iy : s.iz);
+    const uint32_t c0 = (word & 4u) ? s.node + 1u : 0xFFFFFFFFu;           // lower half  [min, split]
+    const uint32_t c1 = (word & 8u) ? (word >> 4) : 0xFFFFFFFFu;           // upper half  [split, max]
+    const bool below = oa < split;
+    const uint32_t near_c = below ? c0 : c1, far_c = below ? c1 : c0;
+    const float ts = (split - oa) * ia;                                     // exact sign; +-inf for da == 0; NaN if also oa == split
+    bool go_near = true, go_far = true;
+    float near_t1 = s.t1, far_t0 = s.t0;
+    if (oa == split || ts != ts) {
+        // origin on the plane: both halves, intervals kept
+    } else if (ts < 0.0f || da == 0.0f) {
+        go_far = false;                                                     // moving away from / parallel to the plane
+    } else {
+        const float w = S * kd_max(fabsf(ts), kd_max(fabsf(s.t0), fabsf(s.t1)));
+        if (ts > s.t1 + w) go_far = false;                                  // leaves the node before the plane
+        else if (ts < s.t0 - w) go_near = false;                            // crossed the plane before entering the node
+        else { near_t1 = kd_min(s.t1, ts + w); far_t0 = kd_max(s.t0, ts - w); }
     }
-    return best;
+    go_near = go_near && near_c != 0xFFFFFFFFu;
+    go_far = go_far && far_c != 0xFFFFFFFFu;
+    if (go_near) {
+        if (go_far) { stack[s.sp].node = far_c; stack[s.sp].t0 = far_t0; stack[s.sp].t1 = s.t1; ++s.sp; }
+        s.node = near_c; s.t1 = near_t1;
+    } else if (go_far) {
+        s.node = far_c; s.t0 = far_t0;
+    } else kd8_pop(s, stack);
+}
+
+// The parked leaf (phase LEAF): test its triangles, then pop the next node or finish.
+template <bool CULL, bool FAST>
+RT_HD void kd8_leaf_step(Kd8State& s, const KdStackEntry* stack, const float* __restrict__ tris, float eps) {
+    kd_test_leaf<CULL, FAST>(tris + size_t(s.leaf_first) * KD8_TRI_FLOATS, s.leaf_count, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
+    if (s.any_hit && s.best.t <= s.t_far) { s.phase = KD8_DONE; return; }
+    kd8_pop(s, stack);
+}
+
+// Closest hit with t <= t_far (t_far = FLT_MAX for a plain query).  any_hit: return at the first hit inside [.., t_far].
+template <bool CULL, bool FAST>
+RT_HD KdHit kd8_trace(const uint32_t* __restrict__ nodes8, const float* __restrict__ tris, const float* root_min, const float* root_max,
+                      float ox, float oy, float oz, float dx, float dy, float dz, float eps, float t_far, bool any_hit) {
+    Kd8State s;
+    KdStackEntry stack[KD8_STACK];
+    if (kd8_init(s, root_min, root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit))
+        while (s.phase != KD8_DONE) {
+            if (s.phase == KD8_WALK) kd8_node_step(s, stack, nodes8);
+            else kd8_leaf_step<CULL, FAST>(s, stack, tris, eps);
+        }
+    return s.best;
 }
 
 }  // namespace rtb

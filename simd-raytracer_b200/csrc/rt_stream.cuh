@@ -1,0 +1,215 @@
+// csrc/rt_stream.cuh - the trace kernels of the accelerated mode (RT_FLAG_ORDERED): persistent warps that keep every lane
+// busy.  A lane owns one query at a time (rt_kd8.cuh state machine); when it finishes - early for an occluded shadow ray,
+// at once for a camera ray that misses the scene box - it takes the next query from the level's device-side counter
+// instead of idling until the slowest ray of a 32-ray chunk is done.  Bursts of traversal steps alternate with a
+// warp-uniform completion phase, which is where exact-t ties are re-run in reference order (trace_warp) and where the
+// is_occluded loop (render/render.hpp:110-131) re-arms a lane that passed through a refractive surface.
+#pragma once
+
+#include "rt_wavefront.cuh"
+
+namespace rtb {
+
+constexpr int STREAM_BURST = 8;          // rounds (node steps + one leaf phase) between completion phases
+constexpr int STREAM_NODE_STEPS = 3;     // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
+constexpr int STREAM_LEAF_MIN = 8;       // run the leaf phase when this many lanes are parked (or nobody can walk on)
+constexpr int STREAM_REFILL_BELOW = 22;  // go and fetch new queries when fewer lanes than this are traversing
+
+// The reference-order re-run of a tied query is rare; keeping it out of line keeps its register needs out of the hot loop.
+template <bool CULL, bool FAST>
+__device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
+                                         Hit* out) {
+    const Hit e = trace_warp<CULL, FAST>(sc, active, mk(ox, oy, oz), mk(dx, dy, dz), eps);
+    if (active) *out = e;
+}
+
+// Policy concept:
+//   bool load(const DScene&, uint32_t idx, V3& o, V3& d, float& t_far, bool& any_hit)   false: entry needs no query
+//   bool finish(const DScene&, uint32_t idx, const Hit& h, Kd8State& st)                  true: lane re-armed (st re-initialised)
+template <bool CULL, bool FAST, class Policy>
+__device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    Kd8State st;
+    KdStackEntry stack[KD8_STACK];
+    st.sp = 0; st.phase = KD8_DONE; st.any_hit = false; st.best.tri = -1; st.best.t = FLT_MAX; st.best.tie_t = -1.0f;
+    st.ox = st.oy = st.oz = st.dx = st.dy = st.dz = 0.0f;
+    bool busy = false, exhausted = false;
+    uint32_t idx = 0;
+    for (;;) {
+        // ---- refill idle lanes ----
+#pragma unroll 1
+        for (int round = 0; round < 8 && !exhausted; ++round) {
+            const uint32_t idle = __ballot_sync(FULL, !busy);
+            if (32 - __popc(idle) >= STREAM_REFILL_BELOW) break;
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == uint32_t(leader)) base = atomicAdd(counter, uint32_t(__popc(idle)));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + uint32_t(__popc(idle)) >= end) exhausted = true;
+            if (!busy) {
+                const uint32_t mine = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
+                if (mine < end) {
+                    idx = mine;
+                    V3 o, d; float t_far; bool any_hit;
+                    if (p.load(sc, idx, o, d, t_far, any_hit)) {
+                        if (kd8_init(st, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, t_far, any_hit)) busy = true;
+                        else {
+                            Hit miss; miss.t = FLT_MAX; miss.u = 0.0f; miss.v = 0.0f; miss.tri = -1;
+                            busy = p.finish(sc, idx, miss, st);
+                        }
+                    }
+                }
+            }
+        }
+        if (!__ballot_sync(FULL, busy)) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- burst: lanes walk inner nodes in lock step (one node per step, the same code for every lane); a lane that
+        // reaches a leaf parks, and parked lanes test their leaves together - neither phase runs with a handful of lanes ----
+#pragma unroll 1
+        for (int it = 0; it < STREAM_BURST; ++it) {
+#pragma unroll 1
+            for (int k = 0; k < STREAM_NODE_STEPS; ++k)
+                if (busy && st.phase == KD8_WALK) kd8_node_step(st, stack, sc.a_nodes8);
+            const uint32_t parked = __ballot_sync(FULL, busy && st.phase == KD8_LEAF);
+            const uint32_t walking = __ballot_sync(FULL, busy && st.phase == KD8_WALK);
+            if (parked && (__popc(parked) >= STREAM_LEAF_MIN || !walking)) {
+                if (busy && st.phase == KD8_LEAF) kd8_leaf_step<CULL, FAST>(st, stack, sc.a_tris, eps);
+            }
+            const int running = __popc(__ballot_sync(FULL, busy && st.phase != KD8_DONE));
+            if (running == 0 || (!exhausted && running < STREAM_REFILL_BELOW)) break;
+        }
+        // ---- completion (warp-uniform) ----
+        const bool fin = busy && st.phase == KD8_DONE;
+        Hit h; h.t = st.best.t; h.u = st.best.u; h.v = st.best.v; h.tri = st.best.tri;
+        const bool tie = fin && !st.any_hit && st.best.tri >= 0 && st.best.tie_t == st.best.t;
+        if (__ballot_sync(FULL, tie)) {
+            // two different triangles at exactly the winner's t: the reference's leaf order decides, so ask it
+            exact_rerun<CULL, FAST>(sc, tie, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, eps, &h);
+        }
+        if (fin) busy = p.finish(sc, idx, h, st);
+    }
+}
+
+template <class T>
+__device__ __forceinline__ void warp_sum_to(unsigned long long* a, unsigned long long* b, T na, T nb) {
+    unsigned long long x = na, y = nb;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { x += __shfl_xor_sync(0xFFFFFFFFu, x, o); y += __shfl_xor_sync(0xFFFFFFFFu, y, o); }
+    if ((threadIdx.x & 31u) == 0 && (x | y)) { atomicAdd(a, x); atomicAdd(b, y); }
+}
+
+// ---- primary rays ---------------------------------------------------------------------------------------------------------
+struct PrimaryPolicy {
+    const FrameParams* fp; Ray* rays; Hit* hits;
+    unsigned long long n_rays = 0, n_hits = 0;
+    __device__ __forceinline__ bool load(const DScene& sc, uint32_t i, V3& o, V3& d, float& t_far, bool& any_hit) {
+        const uint32_t s = i / fp->plane, j = i - s * fp->plane;
+        uint32_t x, y;
+        if (!level0_pixel(*fp, j, x, y)) {
+            Hit h; h.t = 0.0f; h.u = 0.0f; h.v = 0.0f; h.tri = TRI_INACTIVE;
+            store_hit(hits + i, h);
+            return false;
+        }
+        float rx, ry; uint2 key;
+        primary_sample(sc, *fp, x, y, fp->sample_first + s, rx, ry, key);
+        camera_ray(sc, fp->tan_half_fov, rx, ry, o, d);
+        store_ray(rays + i, o, d, key);
+        t_far = FLT_MAX; any_hit = false;
+        ++n_rays;
+        return true;
+    }
+    __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, Kd8State&) {
+        store_hit(hits + i, h);
+        n_hits += (h.tri >= 0);
+        return false;
+    }
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, 2) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+                                                        PassState* __restrict__ ps, int work_slot) {
+    PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
+    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
+    warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
+}
+
+// ---- level d >= 1 ------------------------------------------------------------------------------------------------------------
+struct LevelPolicy {
+    const Ray* rays; Hit* hits; uint32_t begin;
+    unsigned long long n_rays = 0, n_hits = 0;
+    __device__ __forceinline__ bool load(const DScene&, uint32_t i, V3& o, V3& d, float& t_far, bool& any_hit) {
+        uint2 key;
+        load_ray(rays + begin + i, o, d, key);
+        t_far = FLT_MAX; any_hit = false;
+        ++n_rays;
+        return true;
+    }
+    __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, Kd8State&) {
+        store_hit(hits + begin + i, h);
+        n_hits += (h.tri >= 0);
+        return false;
+    }
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, 2) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
+                                                      PassState* __restrict__ ps, int level, int work_slot) {
+    const uint32_t begin = ps->lv[level];
+    const uint32_t end = min(ps->pool_count, fp.pool_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ps->lv[level + 1] = end;
+    LevelPolicy p; p.rays = rays; p.hits = hits; p.begin = begin;
+    stream_loop<false, FAST>(sc, p, &ps->work[work_slot], end - begin, fp.eps);
+    warp_sum_to(&ps->pc.secondary, &ps->pc.secondary_hits, p.n_rays, p.n_hits);
+}
+
+// ---- shadow jobs: is_occluded, render/render.hpp:110-131 ---------------------------------------------------------------------------
+template <bool TRANSMISSIVE>
+struct ShadowPolicy {
+    ShadowJob* jobs; float eps, shadow_bias;
+    V3 o, d; float max_t;
+    unsigned long long n_q = 0, n_h = 0;
+    __device__ __forceinline__ bool load(const DScene&, uint32_t i, V3& ro, V3& rd, float& t_far, bool& any_hit) {
+        const float4* q = reinterpret_cast<const float4*>(jobs + i);
+        const float4 a = q[0], b = q[1];
+        o = mk(a.x, a.y, a.z); d = mk(a.w, b.x, b.y); max_t = b.z;
+        if (!(0.0f < max_t)) return false;                                                               // :115 - not occluded, no query
+        ro = o; rd = d; t_far = max_t; any_hit = !TRANSMISSIVE;
+        return true;
+    }
+    __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, Kd8State& st) {
+        ++n_q;                                                                                           // :116 one closest-hit query
+        if (h.tri < 0) return false;                                                                     // :117
+        ++n_h;
+        if (max_t < h.t) return false;                                                                   // :117-119
+        bool occluded = true;
+        if (TRANSMISSIVE) {
+            const uint32_t mat = __ldg(&sc.tri_index[h.tri]).w;
+            if (sc.materials[mat].kind == 2u) {                                                          // :121-124 refractive: pass through
+                const V3 pos = o + h.t * d;
+                o = pos + shadow_bias * d;                                                               // :126
+                max_t -= h.t;                                                                            // :127
+                if (!(0.0f < max_t)) return false;                                                       // :115
+                if (kd8_init(st, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, max_t, false)) return true;
+                ++n_q;                                                                                   // the next query misses the scene box
+                return false;
+            }
+        }
+        if (occluded) jobs[i].max_t = -1.0f;
+        return false;
+    }
+};
+
+template <bool TRANSMISSIVE, bool FAST>
+__global__ void __launch_bounds__(256, 2) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
+                                                       int work_slot) {
+    const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
+    ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.eps = fp.eps; p.shadow_bias = fp.shadow_bias;
+    p.o = mk(0, 0, 0); p.d = mk(0, 0, 0); p.max_t = 0.0f;
+    stream_loop<false, FAST>(sc, p, &ps->work[work_slot], end, fp.eps);
+    warp_sum_to(&ps->pc.shadow, &ps->pc.shadow_hits, p.n_q, p.n_h);
+}
+
+}  // namespace rtb

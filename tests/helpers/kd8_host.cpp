@@ -3,16 +3,16 @@
 // oracle on a machine without a GPU.  Built with -ffp-contract=off (the device TU is built with -fmad=false).
 #include "../../simd-raytracer_b200/csrc/rt_kd8.cuh"
 
-extern "C" void kd8_trace_batch(const uint32_t* nodes8, const float* packets, const float* root6, const float* rays6, uint64_t n,
+extern "C" void kd8_trace_batch(const uint32_t* nodes8, const float* tris, const float* root6, const float* rays6, uint64_t n,
                                 int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie) {
     for (uint64_t i = 0; i < n; ++i) {
         const float* q = rays6 + 6 * i;
         const float far = t_far ? t_far[i] : FLT_MAX;
         rtb::KdHit h;
-        if (cull) h = fast ? rtb::kd8_trace<true, true>(nodes8, packets, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
-                           : rtb::kd8_trace<true, false>(nodes8, packets, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
-        else h = fast ? rtb::kd8_trace<false, true>(nodes8, packets, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
-                      : rtb::kd8_trace<false, false>(nodes8, packets, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        if (cull) h = fast ? rtb::kd8_trace<true, true>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
+                           : rtb::kd8_trace<true, false>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        else h = fast ? rtb::kd8_trace<false, true>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
+                      : rtb::kd8_trace<false, false>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
         tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
         tri[i] = h.tri;
         if (tie) tie[i] = (h.tri >= 0 && h.tie_t == h.t) ? 1 : 0;     // the device re-runs these through the reference-order query
