@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iterator>
@@ -239,8 +240,12 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : std::min<uint32_t>(30, 8 + (13 * lg + 9) / 10);
         const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : 2;
         if (ad > 30) throw rt_error(RT_ERR_BAD_ARG, "accel_max_depth > 30");
+        const double t1 = now_s();
         s->accel_tree = build_kd_tree_sah(s->geom, ad, al);
+        const double t2 = now_s();
         s->accel_layout = flatten_accel(s->geom, s->accel_tree);
+        if (std::getenv("RT_B200_VERBOSE"))
+            std::fprintf(stderr, "[rt_b200] flatten %.3f s, accel build %.3f s, accel flatten %.3f s\n", t1 - t0, t2 - t1, now_s() - t2);
         s->info.accel_max_depth = ad; s->info.accel_max_leaf_size = al;
         s->info.accel_n_nodes = s->accel_tree.nodes.size(); s->info.accel_n_leaf_refs = s->accel_tree.refs.size();
         s->info.accel_n_leaves = s->accel_tree.n_leaves; s->info.accel_tree_depth = s->accel_tree.depth;

@@ -2,6 +2,7 @@
 // Compiled with -ffp-contract=off: triangle / vertex normals must carry the same bits as the canonical
 // (uncontracted) reference build, they feed the shading of every hit.
 #include "kd_build.hpp"
+#include "kd_parallel.hpp"
 
 #include <cfloat>
 #include <cmath>
@@ -90,73 +91,57 @@ Geometry prepare_geometry(const HostScene& s) {
     return g;
 }
 
-KdTree build_kd_tree(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size) {
-    KdTree t;
+namespace {
+
+// The reference's builder as a policy of the parallel driver (kd_parallel.hpp): build_tree, kd_tree_simd.hpp:146-185.
+struct MedianPolicy {
     struct Work {
-        uint64_t parent;       // KD_NONE for the root
-        int which;             // 0 / 1: which child slot of the parent this node fills
-        uint64_t depth;
+        uint64_t depth = 0;
         float lo[3], hi[3];
         std::vector<uint32_t> tris;
+        size_t size() const { return tris.size(); }
+        bool empty() const { return tris.empty(); }
     };
-    std::vector<Work> todo;
-    {
-        Work root;
-        root.parent = KD_NONE; root.which = 0; root.depth = 0;
-        std::memcpy(root.lo, g.root_min, 12); std::memcpy(root.hi, g.root_max, 12);
-        root.tris.resize(g.tris.size());
-        for (uint32_t i = 0; i < root.tris.size(); ++i) root.tris[i] = i;
-        todo.push_back(std::move(root));
-    }
-    // A node gets its index when it is taken off the stack; child1 is stacked below child0, so the whole child0
-    // subtree is numbered first: the reference's recursion order (kd_tree_simd.hpp:172-184).
-    while (!todo.empty()) {
-        Work w = std::move(todo.back());
-        todo.pop_back();
-        const uint64_t idx = t.nodes.size();
-        KdNode n{};
-        n.parent = w.parent; n.child0 = n.child1 = n.first_ref = KD_NONE; n.ref_count = 0;
-        std::memcpy(n.bmin, w.lo, 12); std::memcpy(n.bmax, w.hi, 12);
-        n.axis = 3; n.split = 0.0f;
-        t.nodes.push_back(n);
-        if (w.parent != KD_NONE) (w.which ? t.nodes[w.parent].child1 : t.nodes[w.parent].child0) = idx;
-        if (w.depth > t.depth) t.depth = w.depth;
+    const Geometry& g;
+    uint32_t max_depth, max_leaf_size;
 
-        if (w.depth == max_depth || w.tris.size() <= max_leaf_size) {     // kd_tree_simd.hpp:147
-            t.nodes[idx].first_ref = t.refs.size();
-            t.nodes[idx].ref_count = w.tris.size();
-            t.refs.insert(t.refs.end(), w.tris.begin(), w.tris.end());
-            ++t.n_leaves;
-            if (w.tris.size() > t.max_leaf_refs) t.max_leaf_refs = w.tris.size();
-            continue;
-        }
+    bool expand(Work& w, uint32_t& axis_out, float& split_out, Work& c0, Work& c1) const {
+        if (w.depth == max_depth || w.tris.size() <= max_leaf_size) return false;         // kd_tree_simd.hpp:147
         // aabb3::split, aabb3.hpp:43-60: median of the box on axis depth%3; a zero-width axis defers to the next.
         // (The reference would recurse forever on a point-sized box; we stop after trying all three.)
         uint32_t axis = uint32_t(w.depth % 3);
         for (int tries = 0; tries < 3 && w.lo[axis] == w.hi[axis]; ++tries) axis = (axis + 1u) % 3u;
         const float mid = w.lo[axis] + ((w.hi[axis] - w.lo[axis]) / 2.0f);
-        t.nodes[idx].axis = axis;
-        t.nodes[idx].split = mid;
-
-        Work c0, c1;
-        c0.parent = c1.parent = idx; c0.which = 0; c1.which = 1; c0.depth = c1.depth = w.depth + 1;
+        axis_out = axis; split_out = mid;
+        c0.depth = c1.depth = w.depth + 1;
         std::memcpy(c0.lo, w.lo, 12); std::memcpy(c0.hi, w.hi, 12);
         std::memcpy(c1.lo, w.lo, 12); std::memcpy(c1.hi, w.hi, 12);
         c0.hi[axis] = mid;
         c1.lo[axis] = mid;
         c0.tris.reserve(w.tris.size());
         c1.tris.reserve(w.tris.size());
-        for (uint32_t id : w.tris) {                                       // no clipping: refs are duplicated
+        for (uint32_t id : w.tris) {                                       // no clipping: refs are duplicated (:160-170)
             const TriGeom& tg = g.tris[id];
             if (overlaps(c0.lo, c0.hi, tg.bmin, tg.bmax)) c0.tris.push_back(id);
             if (overlaps(c1.lo, c1.hi, tg.bmin, tg.bmax)) c1.tris.push_back(id);
         }
-        w.tris.clear();
-        w.tris.shrink_to_fit();
-        if (!c1.tris.empty()) todo.push_back(std::move(c1));               // empty children are never created
-        if (!c0.tris.empty()) todo.push_back(std::move(c0));
+        c0.tris.shrink_to_fit();
+        c1.tris.shrink_to_fit();
+        return true;
     }
-    return t;
+    void emit(const Work& w, std::vector<uint32_t>& refs) const { refs.insert(refs.end(), w.tris.begin(), w.tris.end()); }
+};
+
+}  // namespace
+
+KdTree build_kd_tree(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size) {
+    MedianPolicy pol{g, max_depth, max_leaf_size};
+    MedianPolicy::Work root;
+    root.depth = 0;
+    std::memcpy(root.lo, g.root_min, 12); std::memcpy(root.hi, g.root_max, 12);
+    root.tris.resize(g.tris.size());
+    for (uint32_t i = 0; i < root.tris.size(); ++i) root.tris[i] = i;
+    return kd_build_parallel(pol, std::move(root));
 }
 
 DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t) {
@@ -173,19 +158,33 @@ DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t) {
     d.n_packets = n_packets;
     d.packets.assign(uint64_t(PACKET_WORDS) * (n_packets ? n_packets : 1), 0u);
 
-    uint64_t next_packet = 0;
-    for (uint64_t i = 0; i < n_nodes; ++i) {
+    std::vector<uint64_t> first_packet(n_nodes, 0);
+    {
+        uint64_t next = 0;
+        for (uint64_t i = 0; i < n_nodes; ++i) {
+            const KdNode& n = t.nodes[i];
+            first_packet[i] = next;
+            if (n.first_ref != KD_NONE) next += (n.ref_count + PACKET_LANES - 1) / PACKET_LANES;
+        }
+        if (next >= (1ull << 32)) throw rt_error(RT_ERR_UNSUPPORTED, "too many leaf packets");
+    }
+    for (const KdNode& n : t.nodes) {
+        if (n.first_ref == KD_NONE) {
+            if (n.child0 != KD_NONE && n.child0 != uint64_t(&n - t.nodes.data()) + 1) throw rt_error(RT_ERR_BAD_ARG, "kd-tree is not in DFS pre-order");
+            if (n.child1 != KD_NONE && n.child1 >= (1ull << 28)) throw rt_error(RT_ERR_UNSUPPORTED, "kd-tree has too many nodes");
+        } else if ((n.ref_count + PACKET_LANES - 1) / PACKET_LANES >= (1ull << 30)) throw rt_error(RT_ERR_UNSUPPORTED, "too many leaf packets");
+    }
+    parallel_for(n_nodes, 4096, [&](uint64_t nb, uint64_t ne) {
+    for (uint64_t i = nb; i < ne; ++i) {
         const KdNode& n = t.nodes[i];
         uint32_t first, word;
         if (n.first_ref == KD_NONE) {
-            if (n.child0 != KD_NONE && n.child0 != i + 1) throw rt_error(RT_ERR_BAD_ARG, "kd-tree is not in DFS pre-order");
-            if (n.child1 != KD_NONE && n.child1 >= (1ull << 28)) throw rt_error(RT_ERR_UNSUPPORTED, "kd-tree has too many nodes");
             first = bits(n.split);
             word = (n.axis & 3u) | (n.child0 != KD_NONE ? 4u : 0u) | (n.child1 != KD_NONE ? 8u : 0u) |
                    (n.child1 != KD_NONE ? uint32_t(n.child1) << 4 : 0u);
         } else {
             const uint64_t count = (n.ref_count + PACKET_LANES - 1) / PACKET_LANES;
-            if (next_packet >= (1ull << 32) || count >= (1ull << 30)) throw rt_error(RT_ERR_UNSUPPORTED, "too many leaf packets");
+            const uint64_t next_packet = first_packet[i];
             first = uint32_t(next_packet);
             word = 3u | (uint32_t(count) << 2);
             for (uint64_t k = 0; k < count * PACKET_LANES; ++k) {
@@ -201,7 +200,6 @@ DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t) {
                 }
                 p[9 * 4 + lane] = id;
             }
-            next_packet += count;
         }
         d.nodes8[2 * i] = first;
         d.nodes8[2 * i + 1] = word;
@@ -209,6 +207,7 @@ DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t) {
         f[0] = bits(n.bmin[0]); f[1] = bits(n.bmin[1]); f[2] = bits(n.bmin[2]); f[3] = first;
         f[4] = bits(n.bmax[0]); f[5] = bits(n.bmax[1]); f[6] = bits(n.bmax[2]); f[7] = word;
     }
+    });
 
     return d;
 }
@@ -219,7 +218,8 @@ DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t) {
     d.tri_index.resize(4 * (nt ? nt : 1));
     d.tri_normal.resize(4 * (nt ? nt : 1));
     d.tri_uv.resize(8 * (nt ? nt : 1));
-    for (uint64_t i = 0; i < nt; ++i) {
+    parallel_for(nt, 1 << 16, [&](uint64_t tb, uint64_t te) {
+    for (uint64_t i = tb; i < te; ++i) {
         const TriGeom& tg = g.tris[i];
         d.tri_index[4 * i] = tg.vi[0]; d.tri_index[4 * i + 1] = tg.vi[1]; d.tri_index[4 * i + 2] = tg.vi[2];
         d.tri_index[4 * i + 3] = s.meshes[tg.mesh].material;
@@ -228,12 +228,15 @@ DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t) {
         for (int c = 0; c < 6; ++c) d.tri_uv[8 * i + c] = tg.uv[c];
         d.tri_uv[8 * i + 6] = d.tri_uv[8 * i + 7] = 0.0f;
     }
+    });
     const uint64_t nv = g.vertex_normals.size() / 3;
     d.vnormals.resize(4 * (nv ? nv : 1));
-    for (uint64_t i = 0; i < nv; ++i) {
+    parallel_for(nv, 1 << 16, [&](uint64_t vb, uint64_t ve) {
+    for (uint64_t i = vb; i < ve; ++i) {
         d.vnormals[4 * i] = g.vertex_normals[3 * i]; d.vnormals[4 * i + 1] = g.vertex_normals[3 * i + 1];
         d.vnormals[4 * i + 2] = g.vertex_normals[3 * i + 2]; d.vnormals[4 * i + 3] = 0.0f;
     }
+    });
     for (const auto& m : s.materials) if (m.kind == RT_MAT_REFRACTIVE) d.has_transmissive = true;
     return d;
 }
@@ -251,16 +254,23 @@ AccelLayout flatten_accel(const Geometry& g, const KdTree& t) {
         if (n.first_ref == KD_NONE) {
             if (n.child0 != KD_NONE && n.child0 != i + 1) throw rt_error(RT_ERR_BAD_ARG, "kd-tree is not in DFS pre-order");
             if (n.child1 != KD_NONE && n.child1 >= (1ull << 28)) throw rt_error(RT_ERR_UNSUPPORTED, "kd-tree has too many nodes");
+        } else if (n.ref_count >= (1ull << 30)) throw rt_error(RT_ERR_UNSUPPORTED, "leaf too large");
+    }
+    parallel_for(n_nodes, 1 << 16, [&](uint64_t nb, uint64_t ne) {
+    for (uint64_t i = nb; i < ne; ++i) {
+        const KdNode& n = t.nodes[i];
+        if (n.first_ref == KD_NONE) {
             d.nodes8[2 * i] = bits(n.split);
             d.nodes8[2 * i + 1] = (n.axis & 3u) | (n.child0 != KD_NONE ? 4u : 0u) | (n.child1 != KD_NONE ? 8u : 0u) |
                                   (n.child1 != KD_NONE ? uint32_t(n.child1) << 4 : 0u);
         } else {
-            if (n.ref_count >= (1ull << 30)) throw rt_error(RT_ERR_UNSUPPORTED, "leaf too large");
             d.nodes8[2 * i] = uint32_t(n.first_ref);
             d.nodes8[2 * i + 1] = 3u | (uint32_t(n.ref_count) << 2);
         }
     }
-    for (uint64_t r = 0; r < d.n_refs; ++r) {
+    });
+    parallel_for(d.n_refs, 1 << 16, [&](uint64_t rb, uint64_t re) {
+    for (uint64_t r = rb; r < re; ++r) {
         const uint32_t id = t.refs[r];
         const TriGeom& tg = g.tris[id];
         uint32_t* p = d.tris.data() + 12 * r;
@@ -268,6 +278,7 @@ AccelLayout flatten_accel(const Geometry& g, const KdTree& t) {
         p[4] = bits(tg.e1[0]); p[5] = bits(tg.e1[1]); p[6] = bits(tg.e1[2]);
         p[8] = bits(tg.e2[0]); p[9] = bits(tg.e2[1]); p[10] = bits(tg.e2[2]);
     }
+    });
     return d;
 }
 

@@ -18,6 +18,7 @@
 #include <utility>
 
 #include "kd_build.hpp"
+#include "kd_parallel.hpp"
 
 namespace rtb {
 
@@ -82,44 +83,22 @@ constexpr double COST_STEP = 1.0, COST_TRI = 2.0, EMPTY_BONUS = 0.8;
 
 }  // namespace
 
-KdTree build_kd_tree_sah(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size) {
-    KdTree t;
+namespace {
+
+// the SAH builder as a policy of the parallel driver (kd_parallel.hpp)
+struct SahPolicy {
     struct Work {
-        uint64_t parent;
-        int which;
-        uint64_t depth;
+        uint64_t depth = 0;
         float lo[3], hi[3];
         std::vector<Ref> refs;
+        size_t size() const { return refs.size(); }
+        bool empty() const { return refs.empty(); }
     };
-    double extent = 0;
-    for (int c = 0; c < 3; ++c) extent = std::max(extent, double(g.root_max[c]) - g.root_min[c]);
-    const double grow = 1e-6 * (extent > 0 ? extent : 1.0);
+    const Geometry& g;
+    uint32_t max_depth, max_leaf_size;
+    double grow;
 
-    std::vector<Work> todo;
-    {
-        Work root;
-        root.parent = KD_NONE; root.which = 0; root.depth = 0;
-        std::memcpy(root.lo, g.root_min, 12); std::memcpy(root.hi, g.root_max, 12);
-        root.refs.resize(g.tris.size());
-        for (uint32_t i = 0; i < g.tris.size(); ++i) {
-            Ref& r = root.refs[i];
-            r.tri = i;
-            std::memcpy(r.lo, g.tris[i].bmin, 12); std::memcpy(r.hi, g.tris[i].bmax, 12);
-        }
-        todo.push_back(std::move(root));
-    }
-    while (!todo.empty()) {
-        Work w = std::move(todo.back());
-        todo.pop_back();
-        const uint64_t idx = t.nodes.size();
-        KdNode n{};
-        n.parent = w.parent; n.child0 = n.child1 = n.first_ref = KD_NONE; n.ref_count = 0;
-        std::memcpy(n.bmin, w.lo, 12); std::memcpy(n.bmax, w.hi, 12);
-        n.axis = 3; n.split = 0.0f;
-        t.nodes.push_back(n);
-        if (w.parent != KD_NONE) (w.which ? t.nodes[w.parent].child1 : t.nodes[w.parent].child0) = idx;
-        if (w.depth > t.depth) t.depth = w.depth;
-
+    bool expand(Work& w, uint32_t& axis_out, float& split_out, Work& c0, Work& c1) const {
         const size_t N = w.refs.size();
         int best_axis = -1;
         float best_plane = 0;
@@ -157,19 +136,10 @@ KdTree build_kd_tree_sah(const Geometry& g, uint32_t max_depth, uint32_t max_lea
                 }
             }
         }
-        if (best_axis < 0) {
-            t.nodes[idx].first_ref = t.refs.size();
-            t.nodes[idx].ref_count = N;
-            for (const Ref& r : w.refs) t.refs.push_back(r.tri);
-            ++t.n_leaves;
-            if (N > t.max_leaf_refs) t.max_leaf_refs = N;
-            continue;
-        }
-        t.nodes[idx].axis = uint32_t(best_axis);
-        t.nodes[idx].split = best_plane;
+        if (best_axis < 0) return false;
 
-        Work c0, c1;
-        c0.parent = c1.parent = idx; c0.which = 0; c1.which = 1; c0.depth = c1.depth = w.depth + 1;
+        c0.refs.clear(); c1.refs.clear();
+        c0.depth = c1.depth = w.depth + 1;
         std::memcpy(c0.lo, w.lo, 12); std::memcpy(c0.hi, w.hi, 12);
         std::memcpy(c1.lo, w.lo, 12); std::memcpy(c1.hi, w.hi, 12);
         c0.hi[best_axis] = best_plane;
@@ -190,21 +160,33 @@ KdTree build_kd_tree_sah(const Geometry& g, uint32_t max_depth, uint32_t max_lea
             else c1.refs.push_back(r);
         }
         // a split that separated nothing and cut no empty space would recurse for nothing
-        if (c0.refs.size() == N && c1.refs.size() == N) {
-            t.nodes[idx].axis = 3;
-            t.nodes[idx].first_ref = t.refs.size();
-            t.nodes[idx].ref_count = N;
-            for (const Ref& r : w.refs) t.refs.push_back(r.tri);
-            ++t.n_leaves;
-            if (N > t.max_leaf_refs) t.max_leaf_refs = N;
-            continue;
-        }
-        w.refs.clear();
-        w.refs.shrink_to_fit();
-        if (!c1.refs.empty()) todo.push_back(std::move(c1));
-        if (!c0.refs.empty()) todo.push_back(std::move(c0));
+        if (c0.refs.size() == N && c1.refs.size() == N) { c0.refs.clear(); c1.refs.clear(); return false; }
+        axis_out = uint32_t(best_axis); split_out = best_plane;
+        return true;
     }
-    return t;
+    void emit(const Work& w, std::vector<uint32_t>& refs) const {
+        for (const Ref& r : w.refs) refs.push_back(r.tri);
+    }
+};
+
+}  // namespace
+
+KdTree build_kd_tree_sah(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size) {
+    double extent = 0;
+    for (int c = 0; c < 3; ++c) extent = std::max(extent, double(g.root_max[c]) - g.root_min[c]);
+    SahPolicy pol{g, max_depth, max_leaf_size, 1e-6 * (extent > 0 ? extent : 1.0)};
+    SahPolicy::Work root;
+    root.depth = 0;
+    std::memcpy(root.lo, g.root_min, 12); std::memcpy(root.hi, g.root_max, 12);
+    root.refs.resize(g.tris.size());
+    parallel_for(g.tris.size(), 1 << 16, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            Ref& r = root.refs[i];
+            r.tri = uint32_t(i);
+            std::memcpy(r.lo, g.tris[i].bmin, 12); std::memcpy(r.hi, g.tris[i].bmax, 12);
+        }
+    });
+    return kd_build_parallel(pol, std::move(root));
 }
 
 }  // namespace rtb

@@ -220,3 +220,23 @@ def test_partitions_cover_exactly(rt):
         for world in (1, 2, 8):
             rows = sorted(y for r in range(world) for y0, y1 in rt.row_bands(h, b, r, world) for y in range(y0, y1))
             assert rows == list(range(h))
+
+
+@pytest.mark.parametrize("kd", [(24, 64), (8, 64)])
+def test_parallel_builder_is_thread_invariant(rt, oracle_mod, kd, monkeypatch):
+    """the task-parallel host builder (host/kd_parallel.hpp) must emit the reference's tree - same
+    median splits, same overlap test, same DFS order - whatever the thread count; the backend's own SAH tree likewise."""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=40_000, seed=11, width=64, height=48))
+    o = oracle_mod.Oracle(data, kd[0], kd[1])
+    on5, obx, orf = o.tree()
+    layouts = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RT_B200_BUILD_THREADS", threads)
+        s = rt.Scene.from_rtsc(data, kd_max_depth=kd[0], kd_max_leaf_size=kd[1], device=rt.DEVICE_HOST_ONLY)
+        n5, bx, rf = s.tree()
+        assert np.array_equal(n5, on5) and np.array_equal(bx.view(np.uint32), obx.view(np.uint32)) and np.array_equal(rf, orf)
+        assert (s.info.n_leaves, s.info.max_leaf_refs, s.info.tree_depth) == (o.n_leaves, o.max_leaf_refs, o.tree_depth)
+        layouts.append([np.ascontiguousarray(a).tobytes() for a in s.device_layout() + s.accel_layout()] +
+                       [(s.info.accel_n_nodes, s.info.accel_n_leaves, s.info.accel_n_leaf_refs, s.info.accel_tree_depth)])
+        s.close()
+    assert layouts[0] == layouts[1] == layouts[2]
