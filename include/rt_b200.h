@@ -209,6 +209,36 @@ RT_API int rt_get_counters(rt_scene* s, rt_counters* c);        /* blocks until 
 RT_API int rt_resolve_sum_device(rt_scene* s, const float* d_sum, uint32_t spp_total, float* d_rgb_out, uint8_t* d_rgb8_out,
                           void* stream);
 
+/* ---- multi-GPU combine over NVLink peer memory ------------------------------------------------
+ * The reference renders one image on one host; its decomposition into independent tiles / samples
+ * (render/tile/bucket.hpp:7-21, render/render.hpp:31-35,66-74) is what shards.  One process per GPU: every rank renders its
+ * sample slice with RT_FLAG_RAW_SUM into rt_peer_framebuffer(), then rt_peer_combine() runs ONE kernel per rank that waits
+ * for all peers on device flags, adds its 1/world slice of every rank's framebuffer through NVLink (rank order = the
+ * reference's sample order), divides by spp_total, quantises (io/image/ppm.hpp:17-19) and stores into rank 0's result
+ * buffers.  Handles are cudaIpcMemHandle_t bytes; exchange them with any host-side all-gather.                        */
+#define RT_PEER_HANDLE_BYTES 64
+#define RT_PEER_MAX_RANKS 16
+#define RT_PEER_OUT_RGB 1u          /* float result in rank 0's rt_peer_result_rgb()  */
+#define RT_PEER_OUT_RGB8 2u         /* 8-bit result in rank 0's rt_peer_result_rgb8() */
+typedef struct rt_peer_group rt_peer_group;
+RT_API int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t width, uint32_t height, rt_peer_group** out,
+                                uint8_t* handle /* RT_PEER_HANDLE_BYTES, may be null */);
+RT_API int rt_peer_group_connect(rt_peer_group* g, const uint8_t* handles /* world x RT_PEER_HANDLE_BYTES, rank order */);
+/* all ranks inside one process (one GPU emulating several ranks, or several peer GPUs driven by one host thread) */
+RT_API int rt_peer_group_connect_local(rt_peer_group* const* groups, uint32_t world);
+RT_API float* rt_peer_framebuffer(rt_peer_group* g);      /* device pointers into this rank's block */
+RT_API float* rt_peer_result_rgb(rt_peer_group* g);
+RT_API uint8_t* rt_peer_result_rgb8(rt_peer_group* g);
+/* signal + reduce/resolve + wait, asynchronous on `stream` (the stream the frame was rendered on)             */
+RT_API int rt_peer_combine(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void* stream);
+/* the three steps separately (single-process emulation must signal every rank before any rank reduces)        */
+RT_API int rt_peer_signal_ready(rt_peer_group* g, void* stream);
+RT_API int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void* stream);
+RT_API int rt_peer_wait_done(rt_peer_group* g, void* stream);
+/* rank 0: copy the combined frame to host buffers (either may be null); synchronises `stream`                   */
+RT_API int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream);
+RT_API void rt_peer_group_destroy(rt_peer_group* g);
+
 #ifdef __cplusplus
 }
 #endif

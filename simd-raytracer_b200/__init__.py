@@ -34,6 +34,9 @@ ABI_SYMBOLS = (
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
     "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_device", "rt_trace_primary", "rt_get_counters",
     "rt_resolve_sum_device",
+    "rt_peer_group_create", "rt_peer_group_connect", "rt_peer_group_connect_local", "rt_peer_framebuffer", "rt_peer_result_rgb",
+    "rt_peer_result_rgb8", "rt_peer_combine", "rt_peer_signal_ready", "rt_peer_reduce_resolve", "rt_peer_wait_done",
+    "rt_peer_read_result", "rt_peer_group_destroy",
 )
 
 
@@ -137,6 +140,19 @@ def _load():
     L.rt_trace_primary.argtypes = [vp, C.POINTER(Params), vp]
     L.rt_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.rt_resolve_sum_device.argtypes = [vp, vp, u32, vp, vp, vp]
+    L.rt_peer_group_create.argtypes = [u32, u32, i32, u32, u32, C.POINTER(vp), vp]
+    L.rt_peer_group_connect.argtypes = [vp, vp]
+    L.rt_peer_group_connect_local.argtypes = [C.POINTER(vp), u32]
+    for fn in ("rt_peer_framebuffer", "rt_peer_result_rgb", "rt_peer_result_rgb8"):
+        getattr(L, fn).argtypes = [vp]
+        getattr(L, fn).restype = vp
+    L.rt_peer_combine.argtypes = [vp, u32, u32, vp]
+    L.rt_peer_signal_ready.argtypes = [vp, vp]
+    L.rt_peer_reduce_resolve.argtypes = [vp, u32, u32, vp]
+    L.rt_peer_wait_done.argtypes = [vp, vp]
+    L.rt_peer_read_result.argtypes = [vp, vp, vp, vp]
+    L.rt_peer_group_destroy.argtypes = [vp]
+    L.rt_peer_group_destroy.restype = None
     return L
 
 
@@ -359,6 +375,79 @@ class Scene:
         c = Counters()
         _check(lib.rt_get_counters(self.h, C.byref(c)))
         return c
+
+
+PEER_HANDLE_BYTES = 64
+PEER_OUT_RGB, PEER_OUT_RGB8 = 1, 2
+
+
+class PeerGroup:
+    """One rank's end of the NVLink peer-memory combine (include/rt_b200.h "multi-GPU combine"): owns the rank's raw-sum
+    framebuffer, result buffers and flag block; `handle` is the cudaIpc handle to all-gather across ranks."""
+
+    def __init__(self, world: int, rank: int, device: int, width: int, height: int):
+        self.world, self.rank, self.width, self.height = world, rank, width, height
+        h = C.c_void_p()
+        buf = (C.c_uint8 * PEER_HANDLE_BYTES)()
+        _check(lib.rt_peer_group_create(world, rank, device, width, height, C.byref(h), C.cast(buf, C.c_void_p)))
+        self.h = h
+        self.handle = bytes(buf)
+
+    def connect(self, handles) -> None:
+        """handles: the `handle` of every rank, in rank order (multi-process: one rank per process)."""
+        blob = b"".join(handles)
+        assert len(blob) == self.world * PEER_HANDLE_BYTES
+        _check(lib.rt_peer_group_connect(self.h, C.cast(C.create_string_buffer(blob, len(blob)), C.c_void_p)))
+
+    @staticmethod
+    def connect_local(groups) -> None:
+        """all ranks live in this process (single-GPU emulation of N ranks, or N peer GPUs driven by one thread)"""
+        arr = (C.c_void_p * len(groups))(*[g.h for g in groups])
+        _check(lib.rt_peer_group_connect_local(arr, len(groups)))
+
+    @property
+    def framebuffer(self) -> int:
+        return int(lib.rt_peer_framebuffer(self.h))
+
+    @property
+    def result_rgb(self) -> int:
+        return int(lib.rt_peer_result_rgb(self.h))
+
+    @property
+    def result_rgb8(self) -> int:
+        return int(lib.rt_peer_result_rgb8(self.h))
+
+    def combine(self, spp_total: int, outputs: int = PEER_OUT_RGB | PEER_OUT_RGB8, stream: int | None = None) -> None:
+        _check(lib.rt_peer_combine(self.h, spp_total, outputs, _stream(stream)))
+
+    def signal_ready(self, stream: int | None = None) -> None:
+        _check(lib.rt_peer_signal_ready(self.h, _stream(stream)))
+
+    def reduce_resolve(self, spp_total: int, outputs: int = PEER_OUT_RGB | PEER_OUT_RGB8, stream: int | None = None) -> None:
+        _check(lib.rt_peer_reduce_resolve(self.h, spp_total, outputs, _stream(stream)))
+
+    def wait_done(self, stream: int | None = None) -> None:
+        _check(lib.rt_peer_wait_done(self.h, _stream(stream)))
+
+    def read_result(self, stream: int | None = None, rgb: np.ndarray | None = None, want_rgb8: bool = True):
+        """rank 0: (float frame, 8-bit frame) on the host; `rgb` may be a caller-provided (pinned) float32 buffer"""
+        if rgb is None:
+            rgb = np.zeros((self.height, self.width, 3), np.float32)
+        assert rgb.dtype == np.float32 and rgb.size == self.height * self.width * 3 and rgb.flags["C_CONTIGUOUS"]
+        rgb8 = np.zeros((self.height, self.width, 3), np.uint8) if want_rgb8 else None
+        _check(lib.rt_peer_read_result(self.h, rgb.ctypes.data, rgb8.ctypes.data if want_rgb8 else None, _stream(stream)))
+        return rgb, rgb8
+
+    def close(self) -> None:
+        if self.h:
+            lib.rt_peer_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 # ---- multi-GPU partitioning (SURVEY section 8e): pure functions, shared by bench.py and the CLI ------------------------------

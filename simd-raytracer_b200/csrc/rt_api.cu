@@ -21,6 +21,7 @@
 #include "../host/kd_build.hpp"
 #include "../host/scene.hpp"
 #include "rt_stream.cuh"
+#include "rt_peer.cuh"
 
 using namespace rtb;
 
@@ -798,6 +799,192 @@ int rt_resolve_sum_device(rt_scene* s, const float* d_sum, uint32_t spp_total, f
         CK(cudaGetLastError());
         return int(RT_OK);
     });
+}
+
+}  // extern "C"
+
+// ---- multi-GPU combine over NVLink peer memory (rt_peer.cuh) ---------------------------------------------------------------
+struct rt_peer_group {
+    uint32_t world = 1, rank = 0;
+    int device = 0;
+    uint64_t n = 0;                         // floats per framebuffer
+    uint8_t* block = nullptr;               // local allocation: [raw sums][result rgb][result rgb8][flags]
+    size_t off_rgb = 0, off_rgb8 = 0, off_flags = 0, bytes = 0;
+    uint8_t* peer[PEER_MAX] = {};           // every rank's block as mapped here (own entry = block)
+    bool opened[PEER_MAX] = {};
+    bool connected = false;
+    uint32_t epoch = 0;
+    PeerTable table{};
+};
+
+namespace {
+constexpr size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+void peer_fill_table(rt_peer_group* g) {
+    for (uint32_t r = 0; r < g->world; ++r) {
+        g->table.fb[r] = reinterpret_cast<const float*>(g->peer[r]);
+        g->table.flags[r] = reinterpret_cast<uint32_t*>(g->peer[r] + g->off_flags);
+    }
+    g->connected = true;
+}
+}  // namespace
+
+extern "C" {
+
+int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t width, uint32_t height, rt_peer_group** out, uint8_t* handle) {
+    if (!out) return fail(RT_ERR_BAD_ARG, "null output handle");
+    *out = nullptr;
+    rt_peer_group* g = nullptr;
+    const int st = guarded([&] {
+        if (world == 0 || world > uint32_t(PEER_MAX) || rank >= world || !width || !height) throw rt_error(RT_ERR_BAD_ARG, "bad peer group shape");
+        static_assert(sizeof(cudaIpcMemHandle_t) == RT_PEER_HANDLE_BYTES, "handle size");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+            cudaGetLastError();
+            throw rt_error(RT_ERR_NO_DEVICE, "no such CUDA device");
+        }
+        CK(cudaSetDevice(device));
+        g = new rt_peer_group();
+        g->world = world; g->rank = rank; g->device = device;
+        g->n = uint64_t(width) * height * 3;
+        g->off_rgb = align256(g->n * 4);
+        g->off_rgb8 = g->off_rgb + align256(g->n * 4);
+        g->off_flags = g->off_rgb8 + align256(g->n);
+        g->bytes = g->off_flags + align256(PEER_FLAG_COUNT * 4);
+        CK(cudaMalloc(&g->block, g->bytes));
+        CK(cudaMemset(g->block, 0, g->bytes));
+        CK(cudaDeviceSynchronize());
+        g->peer[rank] = g->block;
+        if (handle) {
+            cudaIpcMemHandle_t h;
+            CK(cudaIpcGetMemHandle(&h, g->block));
+            std::memcpy(handle, &h, sizeof h);
+        }
+        if (world == 1) peer_fill_table(g);
+        *out = g;
+        return int(RT_OK);
+    });
+    if (st != RT_OK) { if (g) { if (g->block) cudaFree(g->block); delete g; } *out = nullptr; }
+    return st;
+}
+
+int rt_peer_group_connect(rt_peer_group* g, const uint8_t* handles) {
+    return guarded([&] {
+        if (!g || !handles) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        CK(cudaSetDevice(g->device));
+        for (uint32_t r = 0; r < g->world; ++r) {
+            if (r == g->rank || g->peer[r]) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + size_t(r) * RT_PEER_HANDLE_BYTES, sizeof h);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            g->peer[r] = static_cast<uint8_t*>(p);
+            g->opened[r] = true;
+        }
+        peer_fill_table(g);
+        return int(RT_OK);
+    });
+}
+
+int rt_peer_group_connect_local(rt_peer_group* const* groups, uint32_t world) {
+    return guarded([&] {
+        if (!groups || world == 0 || world > uint32_t(PEER_MAX)) throw rt_error(RT_ERR_BAD_ARG, "bad argument");
+        for (uint32_t r = 0; r < world; ++r)
+            if (!groups[r] || groups[r]->world != world || groups[r]->rank != r || groups[r]->n != groups[0]->n)
+                throw rt_error(RT_ERR_BAD_ARG, "groups must be the ranks 0..world-1 of one shape");
+        for (uint32_t a = 0; a < world; ++a) {
+            rt_peer_group* g = groups[a];
+            CK(cudaSetDevice(g->device));
+            for (uint32_t r = 0; r < world; ++r) {
+                if (r == a) continue;
+                if (groups[r]->device != g->device) {
+                    int can = 0;
+                    CK(cudaDeviceCanAccessPeer(&can, g->device, groups[r]->device));
+                    if (!can) throw rt_error(RT_ERR_UNSUPPORTED, "devices are not peers");
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(groups[r]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw cuda_error{e, "cudaDeviceEnablePeerAccess"};
+                    cudaGetLastError();
+                }
+                g->peer[r] = groups[r]->block;
+            }
+            peer_fill_table(g);
+        }
+        return int(RT_OK);
+    });
+}
+
+float* rt_peer_framebuffer(rt_peer_group* g) { return g ? reinterpret_cast<float*>(g->block) : nullptr; }
+float* rt_peer_result_rgb(rt_peer_group* g) { return g ? reinterpret_cast<float*>(g->block + g->off_rgb) : nullptr; }
+uint8_t* rt_peer_result_rgb8(rt_peer_group* g) { return g ? g->block + g->off_rgb8 : nullptr; }
+
+int rt_peer_signal_ready(rt_peer_group* g, void* stream) {
+    return guarded([&] {
+        if (!g || !g->connected) throw rt_error(RT_ERR_BAD_ARG, "peer group is not connected");
+        CK(cudaSetDevice(g->device));
+        ++g->epoch;
+        k_peer_signal_ready<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table, int(g->world), int(g->rank), g->epoch);
+        CK(cudaGetLastError());
+        return int(RT_OK);
+    });
+}
+
+int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void* stream) {
+    return guarded([&] {
+        if (!g || !g->connected || spp_total == 0) throw rt_error(RT_ERR_BAD_ARG, "bad argument");
+        if (g->epoch == 0) throw rt_error(RT_ERR_BAD_ARG, "rt_peer_signal_ready has not been called for this frame");
+        CK(cudaSetDevice(g->device));
+        const uint64_t n4 = g->n / 4;
+        const uint64_t g0 = n4 * g->rank / g->world, g1 = n4 * (g->rank + 1) / g->world;
+        int n_sm = 0;
+        CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g->device));
+        const uint64_t want = (g1 - g0 + 255) / 256;
+        const int blocks = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(n_sm) * 8)));
+        uint8_t* root = g->peer[0];
+        k_peer_reduce_resolve<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            g->table, int(g->world), int(g->rank), g0, g1, float(spp_total),
+            (outputs & 1u) ? reinterpret_cast<float*>(root + g->off_rgb) : nullptr, (outputs & 2u) ? root + g->off_rgb8 : nullptr,
+            g->epoch, n4 * 4, g->n);
+        CK(cudaGetLastError());
+        return int(RT_OK);
+    });
+}
+
+int rt_peer_wait_done(rt_peer_group* g, void* stream) {
+    return guarded([&] {
+        if (!g || !g->connected) throw rt_error(RT_ERR_BAD_ARG, "peer group is not connected");
+        CK(cudaSetDevice(g->device));
+        k_peer_wait_done<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch);
+        CK(cudaGetLastError());
+        return int(RT_OK);
+    });
+}
+
+int rt_peer_combine(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void* stream) {
+    int st = rt_peer_signal_ready(g, stream);
+    if (st == RT_OK) st = rt_peer_reduce_resolve(g, spp_total, outputs, stream);
+    if (st == RT_OK) st = rt_peer_wait_done(g, stream);
+    return st;
+}
+
+int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream) {
+    return guarded([&] {
+        if (!g) throw rt_error(RT_ERR_BAD_ARG, "null peer group");
+        CK(cudaSetDevice(g->device));
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (rgb) CK(cudaMemcpyAsync(rgb, g->block + g->off_rgb, g->n * 4, cudaMemcpyDeviceToHost, st));
+        if (rgb8) CK(cudaMemcpyAsync(rgb8, g->block + g->off_rgb8, g->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return int(RT_OK);
+    });
+}
+
+void rt_peer_group_destroy(rt_peer_group* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (uint32_t r = 0; r < g->world; ++r)
+        if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
+    if (g->block) cudaFree(g->block);
+    delete g;
 }
 
 }  // extern "C"

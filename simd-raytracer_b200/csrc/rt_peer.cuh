@@ -1,0 +1,102 @@
+// csrc/rt_peer.cuh - the multi-GPU combine of an spp-sliced frame as ONE kernel over NVLink peer memory.
+//
+// the scene is replicated, every GPU renders its own samples of every pixel into its own
+// framebuffer (RT_FLAG_RAW_SUM), and the frame is sum_over_ranks / spp followed by the PPM quantisation
+// (render/render.hpp:66-74, io/image/ppm.hpp:17-19).  Instead of ncclReduce + a resolve kernel on the root, every rank runs
+// k_peer_reduce_resolve: it waits (device side) until all peers have published "frame e rendered", reads ITS 1/world slice
+// of every peer's framebuffer straight through NVLink (P2P loads on cudaIpc-mapped pointers), adds them in rank order - rank
+// r holds sample slice r, so this is the reference's sample order and the result is bit-identical to the single-GPU frame
+// when every rank renders one sample - divides, quantises, and stores the float and 8-bit slices into the root's result
+// buffers (P2P stores).  The last block publishes "rank r done with frame e" to every peer; k_peer_wait_done then orders the
+// next frame behind everybody's reads.  No host round trip, no staging copy, one NVLink crossing per byte.
+//
+// Flags live in each rank's own block and are written remotely by peers with system-scope release stores.  Epochs only
+// grow, so no flag is ever reset.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rtb {
+
+constexpr int PEER_MAX = 16;
+constexpr int PEER_FLAG_READY = 0;            // flags[PEER_FLAG_READY + r] = last frame rank r has rendered
+constexpr int PEER_FLAG_DONE = PEER_MAX;      // flags[PEER_FLAG_DONE + r]  = last frame rank r has finished reducing
+constexpr int PEER_FLAG_COUNT = 2 * PEER_MAX + 2;   // [2*PEER_MAX] = block counter of the local reduce kernel
+
+struct PeerTable {
+    const float* fb[PEER_MAX];                // every rank's raw sample sums (height*width*3 floats)
+    uint32_t* flags[PEER_MAX];                // every rank's flag block
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// "my framebuffer holds frame `epoch`": one remote store per peer
+__global__ void k_peer_signal_ready(PeerTable t, int world, int rank, uint32_t epoch) {
+    const int i = threadIdx.x;
+    if (i < world) st_release_sys(t.flags[i] + PEER_FLAG_READY + rank, epoch);
+}
+
+__global__ void k_peer_wait_done(const uint32_t* my_flags, int world, uint32_t epoch) {
+    const int i = threadIdx.x;
+    if (i < world)
+        while (ld_acquire_sys(my_flags + PEER_FLAG_DONE + i) < epoch) __nanosleep(64);
+}
+
+__device__ __forceinline__ uint8_t peer_quantise(float c) {          // io/image/ppm.hpp:17-19, product in double
+    const float cl = fminf(fmaxf(c, 0.0f), 1.0f);
+    return uint8_t(__dmul_rn(255.999, double(cl)));
+}
+
+// n4 = number of float4 groups of the whole frame; this rank owns groups [g0, g1)
+__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, int world, int rank, uint64_t g0, uint64_t g1, float div,
+                                                             float* __restrict__ root_rgb, uint8_t* __restrict__ root_rgb8,
+                                                             uint32_t epoch, uint64_t n_tail_begin, uint64_t n_total) {
+    // ---- wait until every peer has rendered frame `epoch` (flags are in MY memory, peers store into them) ----
+    if (threadIdx.x < world)
+        while (ld_acquire_sys(t.flags[rank] + PEER_FLAG_READY + threadIdx.x) < epoch) __nanosleep(32);
+    __syncthreads();
+
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t g = g0 + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < g1; g += stride) {
+        float4 s = __ldcg(reinterpret_cast<const float4*>(t.fb[0]) + g);
+        for (int r = 1; r < world; ++r) {                                // rank order = sample order (render.hpp:66-72)
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(t.fb[r]) + g);
+            s.x = s.x + v.x; s.y = s.y + v.y; s.z = s.z + v.z; s.w = s.w + v.w;
+        }
+        s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);   // :74
+        if (root_rgb) reinterpret_cast<float4*>(root_rgb)[g] = s;
+        if (root_rgb8)
+            reinterpret_cast<uchar4*>(root_rgb8)[g] = make_uchar4(peer_quantise(s.x), peer_quantise(s.y), peer_quantise(s.z), peer_quantise(s.w));
+    }
+    // the last rank also owns the (< 4 element) tail of a frame whose size is not a multiple of four floats
+    if (rank == world - 1 && blockIdx.x == 0) {
+        for (uint64_t i = n_tail_begin + threadIdx.x; i < n_total; i += blockDim.x) {
+            float s = __ldcg(t.fb[0] + i);
+            for (int r = 1; r < world; ++r) s = s + __ldcg(t.fb[r] + i);
+            s = __fdiv_rn(s, div);
+            if (root_rgb) root_rgb[i] = s;
+            if (root_rgb8) root_rgb8[i] = peer_quantise(s);
+        }
+    }
+    // ---- publish "rank done": last block to finish, after its stores are visible system-wide ----
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicAdd(t.flags[rank] + 2 * PEER_MAX, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) t.flags[rank][2 * PEER_MAX] = 0u;
+        __threadfence_system();
+        if (threadIdx.x < world) st_release_sys(t.flags[threadIdx.x] + PEER_FLAG_DONE + rank, epoch);
+    }
+}
+
+}  // namespace rtb

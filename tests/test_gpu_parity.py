@@ -317,6 +317,67 @@ def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod):
         assert np.array_equal(s.trace_occluded(rays, max_t, flags=rt.FLAG_ORDERED), want)
 
 
+def test_config5_shape_synthetic_gi_frame(rt, oracle_mod):
+    """BASELINE.json configs[4] in miniature: a 300 K-triangle random mesh in the diffuse box, kd<24,64>, GI 1, depth 5.
+    Size-independent properties at a size the full-resolution job shares: the two query modes render the SAME float frame
+    (bit for bit - the GI rays are Philox-keyed, so both modes trace identical rays) with the same query counts; a crop is
+    checked against the oracle's Philox render (cos/sin last-bit differences only); 1-spp deterministic part is bit-exact."""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=300_000, seed=1234, width=480, height=270))
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64)
+    o = oracle_mod.Oracle(data, 24, 64)
+    kw = dict(samples_per_pixel=1, diffuse_reflection_ray_count=1, max_ray_depth=5)
+    a = s.render_frame(rt.default_params(**kw))
+    ca = s.counters()
+    b = s.render_frame(rt.default_params(flags=rt.FLAG_ORDERED, **kw))
+    cb = s.counters()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert (ca.primary, ca.primary_hits, ca.shadow, ca.secondary, ca.secondary_hits) == (cb.primary, cb.primary_hits, cb.shadow, cb.secondary, cb.secondary_hits)
+    rect = (120, 60, 360, 200)
+    oi, oc = o.render(oracle_mod.default_params(spp=1, gi_rays=1, max_ray_depth=5), rect=rect)
+    crop = (slice(rect[1], rect[3]), slice(rect[0], rect[2]))
+    same = (quantise(a[crop]) == quantise(oi[crop])).all(axis=2).mean()
+    assert same >= 0.99, same
+    assert psnr8(a[crop], oi[crop]) >= 45.0
+    # no GI: the frame is deterministic and must equal the oracle bit for bit in both modes
+    oi0, oc0 = o.render(oracle_mod.default_params(), rect=rect)
+    for flags in (0, rt.FLAG_ORDERED):
+        img = s.render_frame(rt.default_params(flags=flags))
+        assert np.array_equal(img[crop].view(np.uint32), oi0[crop].view(np.uint32))
+    s.close()
+
+
+@pytest.mark.parametrize("size", [(320, 180), (322, 181)])
+def test_peer_combine_equals_single_gpu_frame(rt, size):
+    """N ranks, one sample slice each, combined by the fused peer-memory kernel (rt_peer_combine's three
+    steps) = the single-GPU frame at spp = N, bit for bit, float and 8-bit.  The ranks are emulated on this one GPU inside one
+    process (rt_peer_group_connect_local; every rank is signalled before any rank reduces); two frames exercise the epochs;
+    322x181 has a tail that is not a multiple of four floats."""
+    import torch
+    s, _ = gpu_scene(rt, "hw11_scene8", size=size)
+    world = 4
+    st = torch.cuda.current_stream().cuda_stream
+    groups = [rt.PeerGroup(world, r, 0, size[0], size[1]) for r in range(world)]
+    rt.PeerGroup.connect_local(groups)
+    kw = dict(max_ray_depth=3, diffuse_reflection_ray_count=1)
+    want = s.render_frame(rt.default_params(samples_per_pixel=world, **kw))
+    for _frame in range(2):
+        for r, g in enumerate(groups):
+            first, count = rt.spp_slice(world, r, world)
+            s.render_frame_device(rt.default_params(samples_per_pixel=count, sample_offset=first, spp_total=world,
+                                                    flags=rt.FLAG_RAW_SUM, **kw), g.framebuffer, stream=st)
+        for g in groups:
+            g.signal_ready(st)
+        for g in groups:
+            g.reduce_resolve(world, stream=st)
+        for g in groups:
+            g.wait_done(st)
+        rgb, rgb8 = groups[0].read_result(st)
+        assert np.array_equal(rgb.view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(rgb8, quantise(want))
+    for g in groups:
+        g.close()
+
+
 # ---- device-pointer entry points, threading ----------------------------------------------------------------------------------------
 def test_device_pointer_api_with_torch(rt, oracle_mod):
     torch = pytest.importorskip("torch")
