@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librt_b200.so")
+# RT_B200_LIB: developer override for parameter sweeps (a variant built by build.py --define=... --out=...)
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")
 
 RT_OK, RT_ERR_BAD_ARG, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_OOM, RT_ERR_UNSUPPORTED = range(8)
 FLAG_RAW_SUM, FLAG_FAST_MATH, FLAG_ORDERED = 1, 2, 4

@@ -37,15 +37,19 @@ def _stale(out: str, srcs) -> bool:
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines / out: developer sweeps only - a variant library with -D overrides of the tuning knobs (csrc/rt_stream.cuh),
+    loaded through the RT_B200_LIB environment variable; the product is always the default build."""
     os.makedirs(BUILD, exist_ok=True)
     objs = []
+    lib = out or LIB
+    tag = "" if not out else "." + os.path.splitext(os.path.basename(out))[0]
     for src in CU:
-        obj = os.path.join(BUILD, os.path.basename(src) + ".o")
+        obj = os.path.join(BUILD, os.path.basename(src) + tag + ".o")
         if force or _stale(obj, [src] + DEPS):
-            cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [NVCC] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", src, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
-            with open(os.path.join(BUILD, os.path.basename(src) + ".ptxas.log"), "w") as fh:
+            with open(os.path.join(BUILD, os.path.basename(src) + tag + ".ptxas.log"), "w") as fh:
                 fh.write(r.stderr)
             if r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
@@ -58,11 +62,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or _stale(obj, [src] + DEPS):
             subprocess.check_call(["g++"] + CXX_FLAGS + ["-c", src, "-o", obj])
         objs.append(obj)
-    if force or _stale(LIB, objs):
-        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
+    if force or _stale(lib, objs):
+        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs +
                               ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"])
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--define=")]
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -126,6 +126,9 @@ struct rt_scene {
     bool counters_pending = false;
     uint64_t pool_hwm = 0, shadow_hwm = 0;
     uint32_t launches = 0, passes = 0;
+    // levels that held rays in the last pass rendered with `hint_params` (0 = unknown): deeper, empty levels are not launched
+    uint32_t levels_hint = 0;
+    rt_params hint_params{};
 
     std::mutex mtx;
     int g_primary[4] = {0, 0, 0, 0}, g_trace[4] = {0, 0, 0, 0}, g_shadow[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g_shade[2] = {0, 0}, g_resolve = 0;
@@ -238,8 +241,10 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         uint32_t lg = 0;
         while ((1ull << lg) < n) ++lg;
         // the usual kd-tree depth bound 8 + 1.3 log2(N); the surface-area heuristic stops earlier where it does not pay
-        const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : std::min<uint32_t>(30, 8 + (13 * lg + 9) / 10);
-        const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : 2;
+        uint32_t env_d = 0, env_l = 0;                                 // RT_B200_ACCEL="depth,leaf": tuning sweeps only
+        if (const char* e = std::getenv("RT_B200_ACCEL")) std::sscanf(e, "%u,%u", &env_d, &env_l);
+        const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : env_d ? env_d : std::min<uint32_t>(30, 8 + (13 * lg + 9) / 10);
+        const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : env_l ? env_l : 2;
         if (ad > 30) throw rt_error(RT_ERR_BAD_ARG, "accel_max_depth > 30");
         const double t1 = now_s();
         s->accel_tree = build_kd_tree_sah(s->geom, ad, al);
@@ -332,8 +337,15 @@ __global__ void k_pass_init(PassState* ps, uint32_t n0) {
     if (threadIdx.x == 0) { ps->pool_count = n0; ps->lv[0] = 0u; ps->lv[1] = n0; }
 }
 // end of a pass: publish the pool usage to pinned host memory and, if the pass is kept, fold its ray counts
-__global__ void k_pass_commit(const PassState* ps, FrameCounters* fc, uint32_t* out) {
-    out[0] = ps->pool_count; out[1] = ps->shadow_count; out[2] = ps->overflow; out[3] = 0u;
+// `launched` of the `total` levels the frame can reach were traced and shaded (the host skips levels the previous pass of the
+// same frame parameters left empty); if the last launched level spawned children after all, the pass is marked truncated
+// (overflow bit 4) and the host renders it again with every level.  out[3] = levels that held entries.
+__global__ void k_pass_commit(PassState* ps, FrameCounters* fc, uint32_t* out, uint32_t launched, uint32_t total) {
+    uint32_t used = 0;
+    for (uint32_t d = 0; d < launched; ++d)
+        if (ps->lv[d + 1] > ps->lv[d]) used = d + 1;
+    if (launched < total && ps->pool_count > ps->lv[launched]) ps->overflow |= 4u;
+    out[0] = ps->pool_count; out[1] = ps->shadow_count; out[2] = ps->overflow; out[3] = used;
     if (ps->overflow) return;
     fc->primary += ps->pc.primary; fc->primary_hits += ps->pc.primary_hits;
     fc->shadow += ps->pc.shadow; fc->shadow_hits += ps->pc.shadow_hits;
@@ -431,6 +443,12 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
                                        : (m.fast ? grid_for(s, k_shadow<false, true, false>) : grid_for(s, k_shadow<false, false, false>));
     }
 
+    // same frame parameters as the last frame: launch only the levels that held rays then (checked on device, see k_pass_commit)
+    rt_params key = p;
+    key.sample_offset = 0; key.samples_per_pixel = 0;
+    if (std::memcmp(&key, &s->hint_params, sizeof key) != 0) { s->levels_hint = 0; s->hint_params = key; }
+    uint32_t levels_seen = 0;
+
     uint32_t done = 0;
     while (done < spp) {
         const uint32_t ns = std::min(per_pass, spp - done);
@@ -445,6 +463,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
             fp.pool_cap = uint32_t(std::min<uint64_t>(s->rays.cap, 0xFFFFFFFFull));
             fp.shadow_cap = uint32_t(std::min<uint64_t>(s->jobs.cap, 0xFFFFFFFFull));
 
+            const uint32_t launched = s->levels_hint ? std::min(levels, s->levels_hint) : levels;
             int slot = 0;
             k_pass_init<<<1, 256, 0, st>>>(s->ps, uint32_t(n0));
             CK(cudaGetLastError());
@@ -456,7 +475,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
                 else k_primary<false, false><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
             });
             ++slot;
-            for (uint32_t lvl = 0; lvl < levels; ++lvl) {
+            for (uint32_t lvl = 0; lvl < launched; ++lvl) {
                 if (lvl > 0) {
                     timed(TC_SECONDARY, [&] {
                         if (m.ordered) {
@@ -491,11 +510,11 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
                 });
                 ++slot;
             }
-            for (int lvl = int(levels) - 1; lvl >= 0; --lvl) {
+            for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
                 timed(TC_RESOLVE, [&] { k_resolve<<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot); });
                 ++slot;
             }
-            k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, s->h_flags);
+            k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, s->h_flags, launched, levels);
             CK(cudaGetLastError());
             // the accumulate kernel skips itself on the device when the pass overflowed its pools
             timed(TC_RESOLVE, [&] {
@@ -507,8 +526,10 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
             if (s->h_flags[2] == 0) {
                 s->pool_hwm = std::max(s->pool_hwm, used_pool);
                 s->shadow_hwm = std::max(s->shadow_hwm, used_shadow);
+                levels_seen = std::max(levels_seen, s->h_flags[3]);
                 break;
             }
+            if (s->h_flags[2] & 4u) s->levels_hint = 0;              // a skipped level was needed: all levels from now on
             if (attempt >= 24) throw rt_error(RT_ERR_OOM, "wavefront pools keep overflowing");
             // the counts of a truncated pass are lower bounds: grow past them and render the pass again (it is deterministic)
             if (s->h_flags[2] & 1u) s->pool_factor = std::max(s->pool_factor * 1.5, double(used_pool) / double(n0) * 1.25);
@@ -518,6 +539,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
         done += ns;
         ++s->passes;
     }
+    if (s->levels_hint == 0 || levels_seen > s->levels_hint) s->levels_hint = std::max<uint32_t>(levels_seen, 1);
     CK(cudaEventRecord(s->frame_b, st));
     CK(cudaMemcpyAsync(s->h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     s->counters_pending = true;

@@ -217,14 +217,17 @@ RT_HD void kd8_node_step(Kd8State& s, KdStackEntry* stack, const uint32_t* __res
     const float ia = axis == 0u ? s.ix : (axis == 1u ? s.iy : s.iz);
     const uint32_t c0 = (word & 4u) ? s.node + 1u : 0xFFFFFFFFu;           // lower half  [min, split]
     const uint32_t c1 = (word & 8u) ? (word >> 4) : 0xFFFFFFFFu;           // upper half  [split, max]
-    const bool below = oa < split;
+    // the half the ray is in for small t > 0; an origin exactly ON the plane (a camera at x = 0 and a binned plane at 0.0)
+    // moves into the half its direction points to and never meets the other one again
+    const bool on_plane = oa == split;
+    const bool below = oa < split || (on_plane && da < 0.0f);
     const uint32_t near_c = below ? c0 : c1, far_c = below ? c1 : c0;
     const float ts = (split - oa) * ia;                                     // exact sign; +-inf for da == 0; NaN if also oa == split
     bool go_near = true, go_far = true;
     float near_t1 = s.t1, far_t0 = s.t0;
-    if (oa == split || ts != ts) {
-        // origin on the plane: both halves, intervals kept
-    } else if (ts < 0.0f || da == 0.0f) {
+    if (ts != ts || (on_plane && da == 0.0f)) {
+        // the ray runs inside the plane (or carries a NaN): both halves, intervals kept
+    } else if (on_plane || ts < 0.0f || da == 0.0f) {
         go_far = false;                                                     // moving away from / parallel to the plane
     } else {
         const float w = S * kd_max(fabsf(ts), kd_max(fabsf(s.t0), fabsf(s.t1)));

@@ -10,10 +10,26 @@
 
 namespace rtb {
 
-constexpr int STREAM_BURST = 8;          // rounds (node steps + one leaf phase) between completion phases
-constexpr int STREAM_NODE_STEPS = 3;     // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
-constexpr int STREAM_LEAF_MIN = 8;       // run the leaf phase when this many lanes are parked (or nobody can walk on)
-constexpr int STREAM_REFILL_BELOW = 22;  // go and fetch new queries when fewer lanes than this are traversing
+// tuning knobs (overridable at compile time for parameter sweeps: simd-raytracer_b200/build.py --define ... --out ...)
+#ifndef RT_STREAM_BURST
+#define RT_STREAM_BURST 8
+#endif
+#ifndef RT_STREAM_NODE_STEPS
+#define RT_STREAM_NODE_STEPS 3
+#endif
+#ifndef RT_STREAM_LEAF_MIN
+#define RT_STREAM_LEAF_MIN 8
+#endif
+#ifndef RT_STREAM_REFILL_BELOW
+#define RT_STREAM_REFILL_BELOW 22
+#endif
+#ifndef RT_STREAM_MIN_BLOCKS
+#define RT_STREAM_MIN_BLOCKS 2
+#endif
+constexpr int STREAM_BURST = RT_STREAM_BURST;                // rounds (node steps + one leaf phase) between completion phases
+constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
+constexpr int STREAM_LEAF_MIN = RT_STREAM_LEAF_MIN;          // run the leaf phase when this many lanes are parked (or nobody can walk on)
+constexpr int STREAM_REFILL_BELOW = RT_STREAM_REFILL_BELOW;  // go and fetch new queries when fewer lanes than this are traversing
 
 // The reference-order re-run of a tied query is rare; keeping it out of line keeps its register needs out of the hot loop.
 template <bool CULL, bool FAST>
@@ -24,7 +40,7 @@ __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox
 }
 
 // Policy concept:
-//   bool load(const DScene&, uint32_t idx, V3& o, V3& d, float& t_far, bool& any_hit)   false: entry needs no query
+//   bool load(const DScene&, uint32_t& idx, V3& o, V3& d, float& t_far, bool& any_hit)  false: entry needs no query; may remap idx
 //   bool finish(const DScene&, uint32_t idx, const Hit& h, Kd8State& st)                  true: lane re-armed (st re-initialised)
 template <bool CULL, bool FAST, class Policy>
 __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps) {
@@ -105,7 +121,7 @@ __device__ __forceinline__ void warp_sum_to(unsigned long long* a, unsigned long
 struct PrimaryPolicy {
     const FrameParams* fp; Ray* rays; Hit* hits;
     unsigned long long n_rays = 0, n_hits = 0;
-    __device__ __forceinline__ bool load(const DScene& sc, uint32_t i, V3& o, V3& d, float& t_far, bool& any_hit) {
+    __device__ __forceinline__ bool load(const DScene& sc, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
         const uint32_t s = i / fp->plane, j = i - s * fp->plane;
         uint32_t x, y;
         if (!level0_pixel(*fp, j, x, y)) {
@@ -129,7 +145,7 @@ struct PrimaryPolicy {
 };
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, 2) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                         PassState* __restrict__ ps, int work_slot) {
     PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
     stream_loop<true, FAST>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
@@ -140,7 +156,7 @@ __global__ void __launch_bounds__(256, 2) k_stream_primary(DScene sc, FrameParam
 struct LevelPolicy {
     const Ray* rays; Hit* hits; uint32_t begin;
     unsigned long long n_rays = 0, n_hits = 0;
-    __device__ __forceinline__ bool load(const DScene&, uint32_t i, V3& o, V3& d, float& t_far, bool& any_hit) {
+    __device__ __forceinline__ bool load(const DScene&, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
         uint2 key;
         load_ray(rays + begin + i, o, d, key);
         t_far = FLT_MAX; any_hit = false;
@@ -155,7 +171,7 @@ struct LevelPolicy {
 };
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, 2) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                       PassState* __restrict__ ps, int level, int work_slot) {
     const uint32_t begin = ps->lv[level];
     const uint32_t end = min(ps->pool_count, fp.pool_cap);
@@ -171,7 +187,18 @@ struct ShadowPolicy {
     ShadowJob* jobs; float eps, shadow_bias;
     V3 o, d; float max_t;
     unsigned long long n_q = 0, n_h = 0;
-    __device__ __forceinline__ bool load(const DScene&, uint32_t i, V3& ro, V3& rd, float& t_far, bool& any_hit) {
+    // Jobs are stored hit-major: the n_lights jobs of one shading point sit next to each other (k_shade), so 32 consecutive
+    // jobs would send a warp towards n_lights different lights.  Work index -> job index transposes every full block of
+    // 32 * n_lights jobs, so that consecutive work items are 32 neighbouring shading points and ONE light: coherent rays.
+    uint32_t n_lights, n_jobs;
+    __device__ __forceinline__ uint32_t job_of(uint32_t i) const {
+        const uint32_t span = 32u * n_lights, block = i / span;
+        if (n_lights <= 1u || (block + 1u) * span > n_jobs) return i;
+        const uint32_t within = i - block * span;
+        return block * span + (within & 31u) * n_lights + (within >> 5);
+    }
+    __device__ __forceinline__ bool load(const DScene&, uint32_t& i, V3& ro, V3& rd, float& t_far, bool& any_hit) {
+        i = job_of(i);
         const float4* q = reinterpret_cast<const float4*>(jobs + i);
         const float4 a = q[0], b = q[1];
         o = mk(a.x, a.y, a.z); d = mk(a.w, b.x, b.y); max_t = b.z;
@@ -203,10 +230,11 @@ struct ShadowPolicy {
 };
 
 template <bool TRANSMISSIVE, bool FAST>
-__global__ void __launch_bounds__(256, 2) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
+__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                        int work_slot) {
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
     ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.eps = fp.eps; p.shadow_bias = fp.shadow_bias;
+    p.n_lights = sc.n_lights; p.n_jobs = end;
     p.o = mk(0, 0, 0); p.d = mk(0, 0, 0); p.max_t = 0.0f;
     stream_loop<false, FAST>(sc, p, &ps->work[work_slot], end, fp.eps);
     warp_sum_to(&ps->pc.shadow, &ps->pc.shadow_hits, p.n_q, p.n_h);

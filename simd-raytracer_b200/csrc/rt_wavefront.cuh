@@ -60,6 +60,11 @@ __device__ __forceinline__ uint32_t claim32(uint32_t* counter) {
     if ((threadIdx.x & 31u) == 0) base = atomicAdd(counter, 32u);
     return __shfl_sync(0xFFFFFFFFu, base, 0);
 }
+// Streaming kernels (shade, resolve) cost about the same per entry, so their warps take 32-entry chunks in a fixed
+// grid-stride order: no atomic round trip in front of every chunk's loads (the dependent atomic + load chain made these
+// kernels latency-bound at a third of the HBM rate).  The trace kernels keep the dynamic counter: their cost per ray varies.
+__device__ __forceinline__ uint32_t first_chunk() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; }
+__device__ __forceinline__ uint32_t chunk_stride() { return gridDim.x * (blockDim.x >> 5) * 32u; }
 // warp-aggregated append: every lane asks for n slots, returns its first slot
 __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, uint32_t n) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -299,9 +304,8 @@ __global__ void __launch_bounds__(256) k_shade(DScene sc, FrameParams fp, Ray* _
                                                int level, int work_slot) {
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const float PI = 3.14159265358979323846f;
-    for (;;) {
-        const uint32_t base = claim32(&ps->work[work_slot]);
-        if (base >= end - begin) break;
+    (void)work_slot;
+    for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
         const bool live = i < end;
 
@@ -449,9 +453,8 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
                                                  PassState* __restrict__ ps, int level, int work_slot) {
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const V3 bg = mk(sc.bg[0], sc.bg[1], sc.bg[2]), black = mk(0.0f, 0.0f, 0.0f);
-    for (;;) {
-        const uint32_t base = claim32(&ps->work[work_slot]);
-        if (base >= end - begin) break;
+    (void)work_slot;
+    for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
         if (i >= end) continue;
         float4* p = reinterpret_cast<float4*>(recs + i);

@@ -14,6 +14,8 @@
 #include <array>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 
@@ -79,7 +81,18 @@ inline double half_area(const float* lo, const float* hi) {
 }
 
 constexpr int BINS = 32;
-constexpr double COST_STEP = 1.0, COST_TRI = 2.0, EMPTY_BONUS = 0.8;
+constexpr double COST_STEP = 1.0;
+// cost of one triangle test relative to one node step, and the discount of a split that cuts off empty space; the
+// RT_B200_SAH="tri_cost,empty_bonus" environment variable overrides them for tuning sweeps
+struct SahCosts { double tri = 2.0, empty_bonus = 0.8; };
+SahCosts sah_costs() {
+    SahCosts c;
+    if (const char* e = std::getenv("RT_B200_SAH")) {
+        double a = 0, b = 0;
+        if (std::sscanf(e, "%lf,%lf", &a, &b) == 2 && a > 0 && b > 0) { c.tri = a; c.empty_bonus = b; }
+    }
+    return c;
+}
 
 }  // namespace
 
@@ -97,6 +110,7 @@ struct SahPolicy {
     const Geometry& g;
     uint32_t max_depth, max_leaf_size;
     double grow;
+    double COST_TRI, EMPTY_BONUS;
 
     bool expand(Work& w, uint32_t& axis_out, float& split_out, Work& c0, Work& c1) const {
         const size_t N = w.refs.size();
@@ -174,7 +188,8 @@ struct SahPolicy {
 KdTree build_kd_tree_sah(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size) {
     double extent = 0;
     for (int c = 0; c < 3; ++c) extent = std::max(extent, double(g.root_max[c]) - g.root_min[c]);
-    SahPolicy pol{g, max_depth, max_leaf_size, 1e-6 * (extent > 0 ? extent : 1.0)};
+    const SahCosts costs = sah_costs();
+    SahPolicy pol{g, max_depth, max_leaf_size, 1e-6 * (extent > 0 ? extent : 1.0), costs.tri, costs.empty_bonus};
     SahPolicy::Work root;
     root.depth = 0;
     std::memcpy(root.lo, g.root_min, 12); std::memcpy(root.hi, g.root_max, 12);

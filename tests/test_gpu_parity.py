@@ -378,6 +378,28 @@ def test_peer_combine_equals_single_gpu_frame(rt, size):
         g.close()
 
 
+def test_empty_level_skipping_never_changes_a_frame(rt):
+    """The host launches only the recursion levels that held rays in the previous pass with the same frame parameters; if a
+    skipped level turns out to be needed (GI paths of another sample slice reach deeper) the device flags the pass and it is
+    rendered again with every level.  Frames from a scene with a warm hint must equal frames from a fresh scene."""
+    data = resized(scene_bytes("hw15_scene2"), 48, 48)
+    warm = rt.Scene.from_rtsc(data)
+    for mode in (0, rt.FLAG_ORDERED):
+        for depth in (2, 6):
+            for off in (0, 5, 11, 3, 0):
+                p = rt.default_params(samples_per_pixel=1, sample_offset=off, spp_total=16, max_ray_depth=depth,
+                                      diffuse_reflection_ray_count=1, flags=mode | rt.FLAG_RAW_SUM)
+                got = warm.render_frame(p)
+                cw = warm.counters()
+                fresh = rt.Scene.from_rtsc(data)
+                want = fresh.render_frame(p)
+                cf = fresh.counters()
+                fresh.close()
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, depth, off)
+                assert (cw.primary, cw.shadow, cw.secondary, cw.secondary_hits) == (cf.primary, cf.shadow, cf.secondary, cf.secondary_hits)
+    warm.close()
+
+
 # ---- device-pointer entry points, threading ----------------------------------------------------------------------------------------
 def test_device_pointer_api_with_torch(rt, oracle_mod):
     torch = pytest.importorskip("torch")

@@ -33,6 +33,12 @@ def kd8(tmp_path_factory):
         lib.kd8_trace_batch(nodes8.ctypes.data, packets.ctypes.data, root.ctypes.data, rays.ctypes.data, len(rays), int(cull), int(fast),
                             C.c_float(eps), None if far is None else far.ctypes.data, int(any_hit), tuv.ctypes.data, tri.ctypes.data, tie.ctypes.data)
         return tuv, tri, tie.astype(bool)
+
+    def counters(reset=True):
+        n, t = C.c_uint64(0), C.c_uint64(0)
+        lib.kd8_counters(C.byref(n), C.byref(t), int(reset))
+        return n.value, t.value
+    trace.counters = counters
     return trace
 
 
@@ -97,3 +103,19 @@ def test_kd8_any_hit_and_far_limit(rt, oracle_mod, kd8):
     assert not np.any((tri >= 0) & (tuv[:, 0] <= far) & ~((want_tri >= 0) & (want_tuv[:, 0] <= far)))
     tuv, tri, _ = kd8(s, rays, False, t_far=far, any_hit=True)
     assert np.array_equal((tri >= 0) & (tuv[:, 0] <= far), (want_tri >= 0) & (want_tuv[:, 0] <= far))
+
+
+def test_origin_on_split_planes_stays_cheap(rt, oracle_mod, kd8):
+    """The synthetic scene's camera sits at x = y = 0, exactly on the binned SAH planes of the top of the tree.  A query from
+    such an origin must stay on ONE side of every such plane (the side its direction points to); visiting both halves
+    multiplied the work per ray by 12 on config 5 without changing a single hit, so only a work bound can catch it."""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=100_000, seed=1234, width=160, height=90))
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64, device=rt.DEVICE_HOST_ONLY)
+    o = oracle_mod.Oracle(data, 24, 64)
+    rays = o.primary_rays()
+    kd8.counters()
+    tuv, tri, tie = kd8(s, rays, True)
+    nodes, tris = kd8.counters()
+    want_tuv, want_tri = o.trace(rays, True)
+    assert np.array_equal(tri[~tie], want_tri[~tie]) and np.array_equal(tri >= 0, want_tri >= 0)
+    assert nodes / len(rays) < 40 and tris / len(rays) < 12, (nodes / len(rays), tris / len(rays))
