@@ -13,10 +13,7 @@ run() {  # name, env assignments...
 }
 run base X=1
 for v in simd-raytracer_b200/variants/librt_*.so; do n=$(basename $v .so); run ${n#librt_} RT_B200_LIB=$PWD/$v; done
-run sah1 RT_B200_SAH=1,0.8
-run sah2b RT_B200_SAH=2,1.0
-run acc18 RT_B200_ACCEL=18,2
-run acc16 RT_B200_ACCEL=16,4
+for e in $SWEEP_ENVS; do run $(echo $e | tr -c 'A-Za-z0-9\n' '_') $e; done
 python - <<PY
 import json,glob,collections
 t=collections.defaultdict(dict)

@@ -65,6 +65,13 @@ RT_HD float kd_fma(float a, float b, float c) {
     return std::fmaf(a, b, c);
 #endif
 }
+RT_HD bool kd_sign_bit(float f) {
+#if defined(__CUDA_ARCH__)
+    return (__float_as_uint(f) >> 31) != 0u;
+#else
+    uint32_t u; std::memcpy(&u, &f, 4); return (u >> 31) != 0u;
+#endif
+}
 RT_HD float kd_min(float a, float b) { return (b < a) ? b : a; }      // NaN in b is ignored
 RT_HD float kd_max(float a, float b) { return (a < b) ? b : a; }
 
@@ -158,7 +165,7 @@ struct KdStackEntry { uint32_t node; float t0, t1; };
 enum : int { KD8_WALK = 0, KD8_LEAF = 1, KD8_DONE = 2 };
 
 struct Kd8State {
-    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+    float ox, oy, oz, dx, dy, dz;                // 1/d is re-derived per node visit (one MUFU) instead of living in three registers
     float t0, t1, t_far;
     uint32_t node, leaf_first, leaf_count;
     int sp, phase;
@@ -170,15 +177,15 @@ struct Kd8State {
 RT_HD bool kd8_init(Kd8State& s, const float* root_min, const float* root_max, float ox, float oy, float oz, float dx, float dy, float dz,
                     float t_far, bool any_hit) {
     s.ox = ox; s.oy = oy; s.oz = oz; s.dx = dx; s.dy = dy; s.dz = dz;
-    s.ix = 1.0f / dx; s.iy = 1.0f / dy; s.iz = 1.0f / dz;
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
     s.t_far = t_far; s.any_hit = any_hit;
     s.best.t = FLT_MAX; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = -1; s.best.tie_t = -1.0f;
     s.node = 0; s.sp = 0; s.phase = KD8_DONE; s.leaf_first = 0; s.leaf_count = 0;
     // parametric interval of the root box (aabb3.hpp:74-90 semantics: NaN from 0*inf leaves a bound unchanged)
     float t0 = 0.0f, t1 = FLT_MAX;
-    const float ax = (root_min[0] - ox) * s.ix, bx = (root_max[0] - ox) * s.ix;
-    const float ay = (root_min[1] - oy) * s.iy, by = (root_max[1] - oy) * s.iy;
-    const float az = (root_min[2] - oz) * s.iz, bz = (root_max[2] - oz) * s.iz;
+    const float ax = (root_min[0] - ox) * ix, bx = (root_max[0] - ox) * ix;
+    const float ay = (root_min[1] - oy) * iy, by = (root_max[1] - oy) * iy;
+    const float az = (root_min[2] - oz) * iz, bz = (root_max[2] - oz) * iz;
     t0 = kd_max(t0, (bx < ax) ? bx : ax); t1 = kd_min(t1, (bx < ax) ? ax : bx);
     t0 = kd_max(t0, (by < ay) ? by : ay); t1 = kd_min(t1, (by < ay) ? ay : by);
     t0 = kd_max(t0, (bz < az) ? bz : az); t1 = kd_min(t1, (bz < az) ? az : bz);
@@ -199,6 +206,13 @@ RT_HD void kd8_pop(Kd8State& s, const KdStackEntry* stack) {
 }
 
 // One node visit (phase WALK): prune and pop, go down one level, or park at a leaf.
+//
+// Children are ordered along the ray: `near` is the half the ray is in BEFORE it crosses the plane (the lower half when the
+// direction component is positive), `far` the half after it.  With ts the plane's parameter the ray is in near on
+// [t0, ts] and in far on [ts, t1]; a crossing behind the node (ts < t0) leaves only far, one beyond it (ts > t1) only
+// near.  A zero direction component gives ts = +-inf with the right sign for this rule (and NaN - both halves - when the
+// origin also lies on the plane).  An origin exactly ON the plane with a non-zero component is in far for every t > 0
+// (a camera at x = 0 and a binned plane at 0.0): near is skipped outright instead of being walked with a zero-length interval.
 RT_HD void kd8_node_step(Kd8State& s, KdStackEntry* stack, const uint32_t* __restrict__ nodes8) {
     const float S = 2e-6f;
     if (s.t0 > kd_min(s.best.t, s.t_far)) { kd8_pop(s, stack); return; }         // the node starts beyond the closest hit so far
@@ -214,34 +228,23 @@ RT_HD void kd8_node_step(Kd8State& s, KdStackEntry* stack, const uint32_t* __res
     const float split = kd_bits_to_float(first);
     const float oa = axis == 0u ? s.ox : (axis == 1u ? s.oy : s.oz);
     const float da = axis == 0u ? s.dx : (axis == 1u ? s.dy : s.dz);
-    const float ia = axis == 0u ? s.ix : (axis == 1u ? s.iy : s.iz);
-    const uint32_t c0 = (word & 4u) ? s.node + 1u : 0xFFFFFFFFu;           // lower half  [min, split]
-    const uint32_t c1 = (word & 8u) ? (word >> 4) : 0xFFFFFFFFu;           // upper half  [split, max]
-    // the half the ray is in for small t > 0; an origin exactly ON the plane (a camera at x = 0 and a binned plane at 0.0)
-    // moves into the half its direction points to and never meets the other one again
-    const bool on_plane = oa == split;
-    const bool below = oa < split || (on_plane && da < 0.0f);
-    const uint32_t near_c = below ? c0 : c1, far_c = below ? c1 : c0;
-    const float ts = (split - oa) * ia;                                     // exact sign; +-inf for da == 0; NaN if also oa == split
-    bool go_near = true, go_far = true;
-    float near_t1 = s.t1, far_t0 = s.t0;
-    if (ts != ts || (on_plane && da == 0.0f)) {
-        // the ray runs inside the plane (or carries a NaN): both halves, intervals kept
-    } else if (on_plane || ts < 0.0f || da == 0.0f) {
-        go_far = false;                                                     // moving away from / parallel to the plane
-    } else {
-        const float w = S * kd_max(fabsf(ts), kd_max(fabsf(s.t0), fabsf(s.t1)));
-        if (ts > s.t1 + w) go_far = false;                                  // leaves the node before the plane
-        else if (ts < s.t0 - w) go_near = false;                            // crossed the plane before entering the node
-        else { near_t1 = kd_min(s.t1, ts + w); far_t0 = kd_max(s.t0, ts - w); }
-    }
-    go_near = go_near && near_c != 0xFFFFFFFFu;
-    go_far = go_far && far_c != 0xFFFFFFFFu;
+    // the 1-ulp reciprocal is good enough here: the interval comparisons below carry a relative slack of 2e-6, and a
+    // flushed subnormal component behaves like zero (its displacement over any finite t is below float resolution)
+    const float ia = kd_rcp_estimate(da);
+    const float ts = (split - oa) * ia;                                     // +-inf for a zero component; NaN if also oa == split
+    const bool neg = kd_sign_bit(ia);                                       // direction component < 0 (or -0.0)
+    const bool has_lo = (word & 4u) != 0u, has_hi = (word & 8u) != 0u;      // lower half [min, split] at index + 1, upper at word >> 4
+    const uint32_t lo_c = s.node + 1u, hi_c = word >> 4;
+    const uint32_t near_c = neg ? hi_c : lo_c, far_c = neg ? lo_c : hi_c;
+    const float w = S * kd_max(kd_min(fabsf(ts), FLT_MAX), s.t1);           // finite for ts = +-inf; 0 <= t0 <= t1 here
+    const bool on_plane = (oa == split) & (ts == ts);
+    const bool go_near = (neg ? has_hi : has_lo) & !(ts < s.t0 - w) & !on_plane;     // a NaN ts fails both compares: both halves
+    const bool go_far = (neg ? has_lo : has_hi) & !(ts > s.t1 + w);
     if (go_near) {
-        if (go_far) { stack[s.sp].node = far_c; stack[s.sp].t0 = far_t0; stack[s.sp].t1 = s.t1; ++s.sp; }
-        s.node = near_c; s.t1 = near_t1;
+        if (go_far) { stack[s.sp].node = far_c; stack[s.sp].t0 = kd_max(s.t0, ts - w); stack[s.sp].t1 = s.t1; ++s.sp; }
+        s.node = near_c; s.t1 = kd_min(s.t1, ts + w);
     } else if (go_far) {
-        s.node = far_c; s.t0 = far_t0;
+        s.node = far_c; s.t0 = kd_max(s.t0, ts - w);
     } else kd8_pop(s, stack);
 }
 

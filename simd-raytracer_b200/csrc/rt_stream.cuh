@@ -24,7 +24,7 @@ namespace rtb {
 #define RT_STREAM_REFILL_BELOW 22
 #endif
 #ifndef RT_STREAM_MIN_BLOCKS
-#define RT_STREAM_MIN_BLOCKS 2
+#define RT_STREAM_MIN_BLOCKS 3
 #endif
 constexpr int STREAM_BURST = RT_STREAM_BURST;                // rounds (node steps + one leaf phase) between completion phases
 constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
@@ -120,7 +120,7 @@ __device__ __forceinline__ void warp_sum_to(unsigned long long* a, unsigned long
 // ---- primary rays ---------------------------------------------------------------------------------------------------------
 struct PrimaryPolicy {
     const FrameParams* fp; Ray* rays; Hit* hits;
-    unsigned long long n_rays = 0, n_hits = 0;
+    uint32_t n_rays = 0, n_hits = 0;
     __device__ __forceinline__ bool load(const DScene& sc, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
         const uint32_t s = i / fp->plane, j = i - s * fp->plane;
         uint32_t x, y;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DS
 // ---- level d >= 1 ------------------------------------------------------------------------------------------------------------
 struct LevelPolicy {
     const Ray* rays; Hit* hits; uint32_t begin;
-    unsigned long long n_rays = 0, n_hits = 0;
+    uint32_t n_rays = 0, n_hits = 0;
     __device__ __forceinline__ bool load(const DScene&, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
         uint2 key;
         load_ray(rays + begin + i, o, d, key);
@@ -184,9 +184,8 @@ __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_level(DSce
 // ---- shadow jobs: is_occluded, render/render.hpp:110-131 ---------------------------------------------------------------------------
 template <bool TRANSMISSIVE>
 struct ShadowPolicy {
-    ShadowJob* jobs; float eps, shadow_bias;
-    V3 o, d; float max_t;
-    unsigned long long n_q = 0, n_h = 0;
+    ShadowJob* jobs; float shadow_bias;
+    uint32_t n_q = 0, n_h = 0;
     // Jobs are stored hit-major: the n_lights jobs of one shading point sit next to each other (k_shade), so 32 consecutive
     // jobs would send a warp towards n_lights different lights.  Work index -> job index transposes every full block of
     // 32 * n_lights jobs, so that consecutive work items are 32 neighbouring shading points and ONE light: coherent rays.
@@ -201,30 +200,30 @@ struct ShadowPolicy {
         i = job_of(i);
         const float4* q = reinterpret_cast<const float4*>(jobs + i);
         const float4 a = q[0], b = q[1];
-        o = mk(a.x, a.y, a.z); d = mk(a.w, b.x, b.y); max_t = b.z;
-        if (!(0.0f < max_t)) return false;                                                               // :115 - not occluded, no query
-        ro = o; rd = d; t_far = max_t; any_hit = !TRANSMISSIVE;
+        if (!(0.0f < b.z)) return false;                                                                 // :115 - not occluded, no query
+        ro = mk(a.x, a.y, a.z); rd = mk(a.w, b.x, b.y); t_far = b.z; any_hit = !TRANSMISSIVE;
         return true;
     }
+    // the query's origin, direction and remaining max_t are the traversal state's own (st.o*, st.d*, st.t_far)
     __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, Kd8State& st) {
         ++n_q;                                                                                           // :116 one closest-hit query
         if (h.tri < 0) return false;                                                                     // :117
         ++n_h;
-        if (max_t < h.t) return false;                                                                   // :117-119
-        bool occluded = true;
+        if (st.t_far < h.t) return false;                                                                // :117-119
         if (TRANSMISSIVE) {
             const uint32_t mat = __ldg(&sc.tri_index[h.tri]).w;
             if (sc.materials[mat].kind == 2u) {                                                          // :121-124 refractive: pass through
-                const V3 pos = o + h.t * d;
-                o = pos + shadow_bias * d;                                                               // :126
-                max_t -= h.t;                                                                            // :127
+                const V3 d = mk(st.dx, st.dy, st.dz);
+                const V3 pos = mk(st.ox, st.oy, st.oz) + h.t * d;
+                const V3 o = pos + shadow_bias * d;                                                      // :126
+                const float max_t = st.t_far - h.t;                                                      // :127
                 if (!(0.0f < max_t)) return false;                                                       // :115
                 if (kd8_init(st, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, max_t, false)) return true;
                 ++n_q;                                                                                   // the next query misses the scene box
                 return false;
             }
         }
-        if (occluded) jobs[i].max_t = -1.0f;
+        jobs[i].max_t = -1.0f;
         return false;
     }
 };
@@ -233,9 +232,8 @@ template <bool TRANSMISSIVE, bool FAST>
 __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                        int work_slot) {
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
-    ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.eps = fp.eps; p.shadow_bias = fp.shadow_bias;
+    ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.shadow_bias = fp.shadow_bias;
     p.n_lights = sc.n_lights; p.n_jobs = end;
-    p.o = mk(0, 0, 0); p.d = mk(0, 0, 0); p.max_t = 0.0f;
     stream_loop<false, FAST>(sc, p, &ps->work[work_slot], end, fp.eps);
     warp_sum_to(&ps->pc.shadow, &ps->pc.shadow_hits, p.n_q, p.n_h);
 }
