@@ -157,17 +157,45 @@ RT_HD void kd_test_leaf(const float* tr, uint32_t count, float ox, float oy, flo
 
 constexpr int KD8_STACK = 32;     // tree depth is capped at 30 by the host
 
-struct KdStackEntry { uint32_t node; float t0, t1; };
+// one 16-byte vector store / load per push / pop (thread-local memory)
+struct alignas(16) KdStackEntry { uint32_t node; float t0, t1; uint32_t pad; };
+RT_HD void kd_stack_put(KdStackEntry* e, uint32_t node, float t0, float t1) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float4*>(e) = make_float4(__uint_as_float(node), t0, t1, 0.0f);
+#else
+    e->node = node; e->t0 = t0; e->t1 = t1; e->pad = 0;
+#endif
+}
+RT_HD void kd_stack_get(const KdStackEntry* e, uint32_t& node, float& t0, float& t1) {
+#if defined(__CUDA_ARCH__)
+    const float4 q = *reinterpret_cast<const float4*>(e);
+    node = __float_as_uint(q.x); t0 = q.y; t1 = q.z;
+#else
+    node = e->node; t0 = e->t0; t1 = e->t1;
+#endif
+}
+// x, y or z by a run-time axis without a branch (two predicates, two selects)
+RT_HD float kd_sel3(uint32_t axis, float x, float y, float z) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.u32 p0, %1, 0;\n\tsetp.eq.u32 p1, %1, 1;\n\t"
+        "selp.f32 %0, %3, %4, p1;\n\tselp.f32 %0, %2, %0, p0;\n\t}"
+        : "=f"(r) : "r"(axis), "f"(x), "f"(y), "f"(z));
+    return r;
+#else
+    return axis == 0u ? x : (axis == 1u ? y : z);
+#endif
+}
 
 // Traversal state of one ray, so that a kernel can advance many rays in lock step and refill finished lanes
-// (rt_stream.cuh).  phase: WALK = standing at `node` with interval [t0,t1]; LEAF = parked at a leaf that still has to be
-// tested (leaf_first / leaf_count); DONE = query finished, `best` is the answer.
+// (rt_stream.cuh).  phase: WALK = standing at `node` with interval [t0,t1]; LEAF = parked at the leaf `node`, which still
+// has to be tested; DONE = query finished, `best` is the answer.
 enum : int { KD8_WALK = 0, KD8_LEAF = 1, KD8_DONE = 2 };
 
 struct Kd8State {
     float ox, oy, oz, dx, dy, dz;                // 1/d is re-derived per node visit (one MUFU) instead of living in three registers
     float t0, t1, t_far;
-    uint32_t node, leaf_first, leaf_count;
+    uint32_t node;
     int sp, phase;
     bool any_hit;
     KdHit best;
@@ -180,7 +208,7 @@ RT_HD bool kd8_init(Kd8State& s, const float* root_min, const float* root_max, f
     const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
     s.t_far = t_far; s.any_hit = any_hit;
     s.best.t = FLT_MAX; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = -1; s.best.tie_t = -1.0f;
-    s.node = 0; s.sp = 0; s.phase = KD8_DONE; s.leaf_first = 0; s.leaf_count = 0;
+    s.node = 0; s.sp = 0; s.phase = KD8_DONE;
     // parametric interval of the root box (aabb3.hpp:74-90 semantics: NaN from 0*inf leaves a bound unchanged)
     float t0 = 0.0f, t1 = FLT_MAX;
     const float ax = (root_min[0] - ox) * ix, bx = (root_max[0] - ox) * ix;
@@ -201,7 +229,7 @@ RT_HD bool kd8_init(Kd8State& s, const float* root_min, const float* root_max, f
 RT_HD void kd8_pop(Kd8State& s, const KdStackEntry* stack) {
     if (!s.sp) { s.phase = KD8_DONE; return; }
     --s.sp;
-    s.node = stack[s.sp].node; s.t0 = stack[s.sp].t0; s.t1 = stack[s.sp].t1;
+    kd_stack_get(stack + s.sp, s.node, s.t0, s.t1);
     s.phase = KD8_WALK;
 }
 
@@ -213,45 +241,55 @@ RT_HD void kd8_pop(Kd8State& s, const KdStackEntry* stack) {
 // near.  A zero direction component gives ts = +-inf with the right sign for this rule (and NaN - both halves - when the
 // origin also lies on the plane).  An origin exactly ON the plane with a non-zero component is in far for every t > 0
 // (a camera at x = 0 and a binned plane at 0.0): near is skipped outright instead of being walked with a zero-length interval.
+// Written without branches between the node fetch and the push: every lane of a warp runs the same instructions.
 RT_HD void kd8_node_step(Kd8State& s, KdStackEntry* stack, const uint32_t* __restrict__ nodes8) {
     const float S = 2e-6f;
-    if (s.t0 > kd_min(s.best.t, s.t_far)) { kd8_pop(s, stack); return; }         // the node starts beyond the closest hit so far
-    KD8_COUNT_NODE();
+    bool pop = s.t0 > kd_min(s.best.t, s.t_far);                            // the node starts beyond the closest hit so far
+    if (!pop) {
+        KD8_COUNT_NODE();
 #if defined(__CUDA_ARCH__)
-    const uint2 nd = __ldg(reinterpret_cast<const uint2*>(nodes8) + s.node);
-    const uint32_t first = nd.x, word = nd.y;
+        const uint2 nd = __ldg(reinterpret_cast<const uint2*>(nodes8) + s.node);
+        const uint32_t first = nd.x, word = nd.y;
 #else
-    const uint32_t first = nodes8[2 * s.node], word = nodes8[2 * s.node + 1];
+        const uint32_t first = nodes8[2 * s.node], word = nodes8[2 * s.node + 1];
 #endif
-    const uint32_t axis = word & 3u;
-    if (axis == 3u) { s.leaf_first = first; s.leaf_count = word >> 2; s.phase = KD8_LEAF; return; }
-    const float split = kd_bits_to_float(first);
-    const float oa = axis == 0u ? s.ox : (axis == 1u ? s.oy : s.oz);
-    const float da = axis == 0u ? s.dx : (axis == 1u ? s.dy : s.dz);
-    // the 1-ulp reciprocal is good enough here: the interval comparisons below carry a relative slack of 2e-6, and a
-    // flushed subnormal component behaves like zero (its displacement over any finite t is below float resolution)
-    const float ia = kd_rcp_estimate(da);
-    const float ts = (split - oa) * ia;                                     // +-inf for a zero component; NaN if also oa == split
-    const bool neg = kd_sign_bit(ia);                                       // direction component < 0 (or -0.0)
-    const bool has_lo = (word & 4u) != 0u, has_hi = (word & 8u) != 0u;      // lower half [min, split] at index + 1, upper at word >> 4
-    const uint32_t lo_c = s.node + 1u, hi_c = word >> 4;
-    const uint32_t near_c = neg ? hi_c : lo_c, far_c = neg ? lo_c : hi_c;
-    const float w = S * kd_max(kd_min(fabsf(ts), FLT_MAX), s.t1);           // finite for ts = +-inf; 0 <= t0 <= t1 here
-    const bool on_plane = (oa == split) & (ts == ts);
-    const bool go_near = (neg ? has_hi : has_lo) & !(ts < s.t0 - w) & !on_plane;     // a NaN ts fails both compares: both halves
-    const bool go_far = (neg ? has_lo : has_hi) & !(ts > s.t1 + w);
-    if (go_near) {
-        if (go_far) { stack[s.sp].node = far_c; stack[s.sp].t0 = kd_max(s.t0, ts - w); stack[s.sp].t1 = s.t1; ++s.sp; }
-        s.node = near_c; s.t1 = kd_min(s.t1, ts + w);
-    } else if (go_far) {
-        s.node = far_c; s.t0 = kd_max(s.t0, ts - w);
-    } else kd8_pop(s, stack);
+        const uint32_t axis = word & 3u;
+        if (axis == 3u) { s.phase = KD8_LEAF; return; }                     // the leaf phase reads the node again
+        const float split = kd_bits_to_float(first);
+        const float oa = kd_sel3(axis, s.ox, s.oy, s.oz);
+        const float da = kd_sel3(axis, s.dx, s.dy, s.dz);
+        // the 1-ulp reciprocal is good enough here: the interval comparisons below carry a relative slack of 2e-6, and a
+        // flushed subnormal component behaves like zero (its displacement over any finite t is below float resolution)
+        const float ia = kd_rcp_estimate(da);
+        const float ts = (split - oa) * ia;                                 // +-inf for a zero component; NaN if also oa == split
+        const bool neg = kd_sign_bit(ia);                                   // direction component < 0 (or -0.0)
+        const uint32_t lo_c = s.node + 1u, hi_c = word >> 4;                // lower half [min, split] at index + 1, upper at word >> 4
+        const uint32_t near_c = neg ? hi_c : lo_c, far_c = neg ? lo_c : hi_c;
+        const uint32_t has_near = neg ? (word & 8u) : (word & 4u), has_far = neg ? (word & 4u) : (word & 8u);
+        const float w = S * kd_max(kd_min(fabsf(ts), FLT_MAX), s.t1);       // finite for ts = +-inf; 0 <= t0 <= t1 here
+        const bool on_plane = (oa == split) & (ts == ts);
+        const bool go_near = (has_near != 0u) & !(ts < s.t0 - w) & !on_plane;   // a NaN ts fails both compares: both halves
+        const bool go_far = (has_far != 0u) & !(ts > s.t1 + w);
+        const float far_t0 = kd_max(s.t0, ts - w), near_t1 = kd_min(s.t1, ts + w);
+        if (go_near & go_far) { kd_stack_put(stack + s.sp, far_c, far_t0, s.t1); ++s.sp; }
+        pop = !(go_near | go_far);
+        s.node = go_near ? near_c : far_c;
+        s.t1 = go_near ? near_t1 : s.t1;
+        s.t0 = go_near ? s.t0 : far_t0;
+    }
+    if (pop) kd8_pop(s, stack);
 }
 
 // The parked leaf (phase LEAF): test its triangles, then pop the next node or finish.
 template <bool CULL, bool FAST>
-RT_HD void kd8_leaf_step(Kd8State& s, const KdStackEntry* stack, const float* __restrict__ tris, float eps) {
-    kd_test_leaf<CULL, FAST>(tris + size_t(s.leaf_first) * KD8_TRI_FLOATS, s.leaf_count, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
+RT_HD void kd8_leaf_step(Kd8State& s, const KdStackEntry* stack, const uint32_t* __restrict__ nodes8, const float* __restrict__ tris, float eps) {
+#if defined(__CUDA_ARCH__)
+    const uint2 nd = __ldg(reinterpret_cast<const uint2*>(nodes8) + s.node);
+    const uint32_t first = nd.x, count = nd.y >> 2;
+#else
+    const uint32_t first = nodes8[2 * s.node], count = nodes8[2 * s.node + 1] >> 2;
+#endif
+    kd_test_leaf<CULL, FAST>(tris + size_t(first) * KD8_TRI_FLOATS, count, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
     if (s.any_hit && s.best.t <= s.t_far) { s.phase = KD8_DONE; return; }
     kd8_pop(s, stack);
 }
@@ -265,7 +303,7 @@ RT_HD KdHit kd8_trace(const uint32_t* __restrict__ nodes8, const float* __restri
     if (kd8_init(s, root_min, root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit))
         while (s.phase != KD8_DONE) {
             if (s.phase == KD8_WALK) kd8_node_step(s, stack, nodes8);
-            else kd8_leaf_step<CULL, FAST>(s, stack, tris, eps);
+            else kd8_leaf_step<CULL, FAST>(s, stack, nodes8, tris, eps);
         }
     return s.best;
 }

@@ -92,7 +92,7 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
             const uint32_t parked = __ballot_sync(FULL, busy && st.phase == KD8_LEAF);
             const uint32_t walking = __ballot_sync(FULL, busy && st.phase == KD8_WALK);
             if (parked && (__popc(parked) >= STREAM_LEAF_MIN || !walking)) {
-                if (busy && st.phase == KD8_LEAF) kd8_leaf_step<CULL, FAST>(st, stack, sc.a_tris, eps);
+                if (busy && st.phase == KD8_LEAF) kd8_leaf_step<CULL, FAST>(st, stack, sc.a_nodes8, sc.a_tris, eps);
             }
             const int running = __popc(__ballot_sync(FULL, busy && st.phase != KD8_DONE));
             if (running == 0 || (!exhausted && running < STREAM_REFILL_BELOW)) break;
