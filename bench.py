@@ -419,7 +419,7 @@ def main() -> None:
                                                  "ncclReduce(sum) to rank 0 + rt_resolve_sum_device")),
             "verify": verify,
             "scene": {"triangles": int(scene.info.n_triangles), "kd_nodes": int(scene.info.n_nodes), "packets": int(scene.info.n_packets),
-                      "accel_nodes": int(scene.info.accel_n_nodes), "accel_leaf_refs": int(scene.info.accel_n_leaf_refs),
+                      "bvh_nodes": int(scene.info.bvh_n_nodes), "bvh_depth": int(scene.info.bvh_depth),
                       "device_bytes": int(scene.info.device_bytes), "host_build_s": round(t_build, 3)},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -131,6 +131,7 @@ typedef struct rt_scene_info {
     int32_t device;
     uint32_t accel_max_depth, accel_max_leaf_size;       /* parameters the accelerated tree was built with */
     uint64_t accel_n_nodes, accel_n_leaf_refs, accel_n_leaves, accel_tree_depth;
+    uint64_t bvh_n_nodes, bvh_n_refs, bvh_n_leaves, bvh_depth;   /* the bounding-volume hierarchy (64-byte two-child nodes) */
 } rt_scene_info;
 
 typedef struct rt_counters {         /* of the last rt_render_frame* call */
@@ -174,6 +175,11 @@ RT_API int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint3
 /* the accelerated tree (sizes in rt_scene_info.accel_*): 8-byte nodes; tris12 = 12 x u32 per leaf reference
  * { v0.xyz, id } { e1.xyz, 0 } { e2.xyz, 0 }; root6 = min xyz, max xyz of the root box                                          */
 RT_API int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* tris12, float* root6);
+/* builds that kd-tree if it has not been built yet (it is not needed by the shipped BVH query) and fills rt_scene_info.accel_* */
+RT_API int rt_scene_build_kd_accel(rt_scene* s);
+/* the bounding-volume hierarchy (rt_scene_info.bvh_*): nodes16 = 16 x u32 per inner node
+ * { c0.min.xyz, c0.max.xyz, c1.min.xyz, c1.max.xyz, ref0, ref1, cnt0, cnt1 }; tris12 as above, one record per triangle   */
+RT_API int rt_scene_get_bvh_layout(const rt_scene* s, uint32_t* nodes16, uint32_t* tris12, float* root6);
 /*   tri9 = v0,e1,e2 per triangle; face normals; vertex normals (mesh-concatenated vertex order)               */
 RT_API int rt_scene_get_geometry(const rt_scene* s, float* tri9, float* face_normals, float* vertex_normals);
 

@@ -31,7 +31,8 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 ABI_SYMBOLS = (
     "rt_abi_version", "rt_status_string", "rt_last_error", "rt_default_build_opts", "rt_default_params",
     "rt_scene_create", "rt_scene_create_from_crtscene", "rt_scene_create_from_rtsc", "rt_scene_destroy",
-    "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_get_geometry",
+    "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_build_kd_accel", "rt_scene_get_bvh_layout",
+    "rt_scene_get_geometry",
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
     "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_device", "rt_trace_primary", "rt_get_counters",
     "rt_resolve_sum_device",
@@ -96,7 +97,8 @@ class SceneInfo(C.Structure):
                 ("device_bytes", C.c_uint64), ("build_seconds", C.c_double), ("flatten_seconds", C.c_double),
                 ("upload_seconds", C.c_double), ("device", C.c_int32),
                 ("accel_max_depth", C.c_uint32), ("accel_max_leaf_size", C.c_uint32), ("accel_n_nodes", C.c_uint64),
-                ("accel_n_leaf_refs", C.c_uint64), ("accel_n_leaves", C.c_uint64), ("accel_tree_depth", C.c_uint64)]
+                ("accel_n_leaf_refs", C.c_uint64), ("accel_n_leaves", C.c_uint64), ("accel_tree_depth", C.c_uint64),
+                ("bvh_n_nodes", C.c_uint64), ("bvh_n_refs", C.c_uint64), ("bvh_n_leaves", C.c_uint64), ("bvh_depth", C.c_uint64)]
 
 
 class Counters(C.Structure):
@@ -131,6 +133,8 @@ def _load():
     L.rt_scene_get_device_layout.argtypes = [vp, vp, vp]
     L.rt_scene_get_geometry.argtypes = [vp, vp, vp, vp]
     L.rt_scene_get_accel_layout.argtypes = [vp, vp, vp, vp]
+    L.rt_scene_get_bvh_layout.argtypes = [vp, vp, vp, vp]
+    L.rt_scene_build_kd_accel.argtypes = [vp]
     L.rt_trace_closest.argtypes = [vp, vp, u64, i32, f32, u32, vp]
     L.rt_trace_occluded.argtypes = [vp, vp, vp, u64, f32, f32, u32, vp]
     L.rt_trace_closest_device.argtypes = [vp, vp, u64, i32, f32, u32, vp, vp]
@@ -305,11 +309,21 @@ class Scene:
 
     def accel_layout(self):
         """nodes8 / 48-byte triangle records / root box of the backend's own tree (RT_FLAG_ORDERED)"""
+        _check(lib.rt_scene_build_kd_accel(self.h))            # built on demand; refresh the sizes
+        _check(lib.rt_scene_get_info(self.h, C.byref(self.info)))
         nodes8 = np.zeros((self.info.accel_n_nodes, 2), np.uint32)
         tris = np.zeros((max(self.info.accel_n_leaf_refs, 1), 12), np.uint32)
         root = np.zeros(6, np.float32)
         _check(lib.rt_scene_get_accel_layout(self.h, nodes8.ctypes.data, tris.ctypes.data, root.ctypes.data))
         return nodes8, tris, root
+
+    def bvh_layout(self):
+        """64-byte two-child nodes / 48-byte triangle records / root box of the bounding-volume hierarchy (RT_FLAG_ORDERED)"""
+        nodes = np.zeros((max(self.info.bvh_n_nodes, 1), 16), np.uint32)
+        tris = np.zeros((max(self.info.bvh_n_refs, 1), 12), np.uint32)
+        root = np.zeros(6, np.float32)
+        _check(lib.rt_scene_get_bvh_layout(self.h, nodes.ctypes.data, tris.ctypes.data, root.ctypes.data))
+        return nodes, tris, root
 
     def geometry(self):
         tri9 = np.zeros((self.info.n_triangles, 9), np.float32)

@@ -1,0 +1,157 @@
+// csrc/rt_bvh.cuh - the accelerated closest-hit query over the backend's bounding-volume hierarchy (host/bvh_build.cpp),
+// one ray per thread, near child first.  SURVEY.md section 8 row f4.
+//
+// Same contract as the kd-tree traversal in rt_kd8.cuh, whose triangle test (kd_test_tri - the reference's own
+// arithmetic, kd_tree_simd.hpp:25-60) it shares: t/u/v of the winner are the reference's bits; the minimum is taken over
+// every triangle whose box the ray touches; an exact-t tie between two different triangles is only recorded
+// (KdHit::tie_t == t) and the caller re-runs those rays in reference order.  Box tests are conservative: both ends of a
+// slab interval are widened by a relative slack far above the rounding of the slab arithmetic, a NaN (0 * inf) never
+// rejects, and pruning only uses "the box starts beyond the closest hit so far".
+//
+// Node (64 B, four aligned 16-byte rows), one per inner node, holding its two children:
+//   { c0.min.xyz, c0.max.x } { c0.max.yz, c1.min.xy } { c1.min.z, c1.max.xyz } { ref0, ref1, cnt0, cnt1 }
+//   cnt == 0: ref = inner node index; cnt > 0: leaf of cnt triangle records starting at ref; cnt == ~0u: no child
+//
+// Compiles as CUDA device code and as plain C++ (tests/helpers/kd8_host.cpp runs this very source on the CPU).
+#pragma once
+
+#include "rt_kd8.cuh"
+
+#ifndef BVH_COUNT_NODE
+#define BVH_COUNT_NODE() ((void)0)
+#endif
+
+namespace rtb {
+
+constexpr int BVH_STACK = 48;                 // the builder caps the depth at 44
+constexpr uint32_t BVH_NO_CHILD = 0xFFFFFFFFu;
+
+struct alignas(16) BvhStackEntry { uint32_t ref, cnt; float t0; uint32_t pad; };
+RT_HD void bvh_stack_put(BvhStackEntry* e, uint32_t ref, uint32_t cnt, float t0) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float4*>(e) = make_float4(__uint_as_float(ref), __uint_as_float(cnt), t0, 0.0f);
+#else
+    e->ref = ref; e->cnt = cnt; e->t0 = t0; e->pad = 0;
+#endif
+}
+RT_HD void bvh_stack_get(const BvhStackEntry* e, uint32_t& ref, uint32_t& cnt, float& t0) {
+#if defined(__CUDA_ARCH__)
+    const float4 q = *reinterpret_cast<const float4*>(e);
+    ref = __float_as_uint(q.x); cnt = __float_as_uint(q.y); t0 = q.z;
+#else
+    ref = e->ref; cnt = e->cnt; t0 = e->t0;
+#endif
+}
+
+// min / max that ignore a NaN operand (fminf / fmaxf semantics on the device)
+RT_HD float bvh_min(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return fminf(a, b);
+#else
+    return (a != a) ? b : ((b != b) ? a : (b < a ? b : a));
+#endif
+}
+RT_HD float bvh_max(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return fmaxf(a, b);
+#else
+    return (a != a) ? b : ((b != b) ? a : (a < b ? b : a));
+#endif
+}
+
+// phase: WALK = standing at inner node `ref`; LEAF = standing at a leaf (cnt triangles from record `ref`); DONE
+struct BvhState {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+    float t0, t_far;
+    uint32_t ref, cnt;
+    int sp, phase;
+    bool any_hit;
+    KdHit best;
+};
+
+constexpr float BVH_SLACK = 1e-5f;
+
+// entry and exit parameter of the ray in a box; entry clamped to 0, NaNs (0 * inf) ignored
+RT_HD void bvh_slab(const BvhState& s, float lx, float ly, float lz, float hx, float hy, float hz, float& t_in, float& t_out) {
+    const float ax = (lx - s.ox) * s.ix, bx = (hx - s.ox) * s.ix;
+    const float ay = (ly - s.oy) * s.iy, by = (hy - s.oy) * s.iy;
+    const float az = (lz - s.oz) * s.iz, bz = (hz - s.oz) * s.iz;
+    t_in = bvh_max(bvh_max(bvh_min(ax, bx), bvh_min(ay, by)), bvh_max(bvh_min(az, bz), 0.0f));
+    t_out = bvh_min(bvh_min(bvh_max(ax, bx), bvh_max(ay, by)), bvh_max(az, bz));
+}
+
+// returns false when the ray misses the root box (the query is then finished: a miss)
+RT_HD bool bvh_init(BvhState& s, const float* root_min, const float* root_max, float ox, float oy, float oz, float dx, float dy, float dz,
+                    float t_far, bool any_hit) {
+    s.ox = ox; s.oy = oy; s.oz = oz; s.dx = dx; s.dy = dy; s.dz = dz;
+    s.ix = 1.0f / dx; s.iy = 1.0f / dy; s.iz = 1.0f / dz;
+    s.t_far = t_far; s.any_hit = any_hit;
+    s.best.t = FLT_MAX; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = -1; s.best.tie_t = -1.0f;
+    s.ref = 0; s.cnt = 0; s.sp = 0; s.phase = KD8_DONE; s.t0 = 0.0f;
+    float t_in, t_out;
+    bvh_slab(s, root_min[0], root_min[1], root_min[2], root_max[0], root_max[1], root_max[2], t_in, t_out);
+    const float in_s = t_in * (1.0f - BVH_SLACK);
+    if (!(in_s <= t_out * (1.0f + BVH_SLACK)) || !(in_s <= t_far)) return false;
+    s.phase = KD8_WALK;
+    return true;
+}
+
+RT_HD void bvh_pop(BvhState& s, const BvhStackEntry* stack) {
+    if (!s.sp) { s.phase = KD8_DONE; return; }
+    --s.sp;
+    bvh_stack_get(stack + s.sp, s.ref, s.cnt, s.t0);
+    s.phase = s.cnt ? KD8_LEAF : KD8_WALK;
+}
+
+// One inner-node visit (phase WALK): test both children's boxes, go to the nearer one, push the other.
+RT_HD void bvh_node_step(BvhState& s, BvhStackEntry* stack, const float* __restrict__ nodes) {
+    const float lim = kd_min(s.best.t, s.t_far);
+    bool pop = s.t0 > lim;                                                   // the box starts beyond the closest hit so far
+    if (!pop) {
+        BVH_COUNT_NODE();
+        const float* p = nodes + size_t(s.ref) * 16u;
+        const KdRow q0 = kd_load_row(p), q1 = kd_load_row(p + 4), q2 = kd_load_row(p + 8), q3 = kd_load_row(p + 12);
+        float in0, out0, in1, out1;
+        bvh_slab(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, in0, out0);
+        bvh_slab(s, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, in1, out1);
+        const uint32_t ref0 = uint32_t(kd_as_int(q3.x)), ref1 = uint32_t(kd_as_int(q3.y));
+        const uint32_t cnt0 = uint32_t(kd_as_int(q3.z)), cnt1 = uint32_t(kd_as_int(q3.w));
+        const float e0 = in0 * (1.0f - BVH_SLACK), e1 = in1 * (1.0f - BVH_SLACK);         // widened entry points (>= 0)
+        const bool hit0 = (cnt0 != BVH_NO_CHILD) & (e0 <= out0 * (1.0f + BVH_SLACK)) & (e0 <= lim);
+        const bool hit1 = (cnt1 != BVH_NO_CHILD) & (e1 <= out1 * (1.0f + BVH_SLACK)) & (e1 <= lim);
+        const bool first1 = hit1 & (!hit0 | (e1 < e0));                     // child 1 is visited first
+        if (hit0 & hit1) { bvh_stack_put(stack + s.sp, first1 ? ref0 : ref1, first1 ? cnt0 : cnt1, first1 ? e0 : e1); ++s.sp; }
+        pop = !(hit0 | hit1);
+        s.ref = first1 ? ref1 : ref0;
+        s.cnt = first1 ? cnt1 : cnt0;
+        s.t0 = first1 ? e1 : e0;
+        s.phase = s.cnt ? KD8_LEAF : KD8_WALK;
+    }
+    if (pop) bvh_pop(s, stack);
+}
+
+// A leaf (phase LEAF): test its triangles, then pop the next subtree or finish.
+template <bool CULL, bool FAST>
+RT_HD void bvh_leaf_step(BvhState& s, const BvhStackEntry* stack, const float* __restrict__ tris, float eps) {
+    if (!(s.t0 > kd_min(s.best.t, s.t_far))) {
+        kd_test_leaf<CULL, FAST>(tris + size_t(s.ref) * KD8_TRI_FLOATS, s.cnt, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
+        if (s.any_hit && s.best.t <= s.t_far) { s.phase = KD8_DONE; return; }
+    }
+    bvh_pop(s, stack);
+}
+
+// Closest hit with t <= t_far (t_far = FLT_MAX for a plain query).  any_hit: return at the first hit inside [.., t_far].
+template <bool CULL, bool FAST>
+RT_HD KdHit bvh_trace(const float* __restrict__ nodes, const float* __restrict__ tris, const float* root_min, const float* root_max,
+                      float ox, float oy, float oz, float dx, float dy, float dz, float eps, float t_far, bool any_hit) {
+    BvhState s;
+    BvhStackEntry stack[BVH_STACK];
+    if (bvh_init(s, root_min, root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit))
+        while (s.phase != KD8_DONE) {
+            if (s.phase == KD8_WALK) bvh_node_step(s, stack, nodes);
+            else bvh_leaf_step<CULL, FAST>(s, stack, tris, eps);
+        }
+    return s.best;
+}
+
+}  // namespace rtb

@@ -13,7 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "rt_kd8.cuh"
+#include "rt_bvh.cuh"
 
 namespace rtb {
 
@@ -23,8 +23,10 @@ struct DTexture { uint32_t kind; float c0[3], c1[3], scalar; uint32_t w, h, off;
 struct DLight { float pos[3], intensity; };                                                              // 16 B
 
 struct DScene {
-    const uint32_t* __restrict__ a_nodes8;  // accelerated mode: 8-byte nodes of the backend's own deeper kd-tree (rt_kd8.cuh)
+    const uint32_t* __restrict__ a_nodes8;  // accelerated mode, kd variant: 8-byte nodes of the backend's own SAH kd-tree (rt_kd8.cuh)
     const float* __restrict__ a_tris;       //                   and its 48-byte leaf triangle records
+    const float* __restrict__ b_nodes;      // accelerated mode, BVH variant (default): 64-byte two-child nodes (rt_bvh.cuh)
+    const float* __restrict__ b_tris;       //                   and its 48-byte triangle records (one per triangle)
     const float4* __restrict__ nodes32;     // 2 x float4 per node: box + the same two words (reference-order traversal)
     const float4* __restrict__ packets;     // 10 x float4 per 4-triangle SoA packet
     const uint4* __restrict__ tri_index;    // vi0, vi1, vi2, material
@@ -41,6 +43,7 @@ struct DScene {
     float cam_pos[3];
     float cam_m[9];
     float root_min[3], root_max[3];
+    float b_root_min[3], b_root_max[3];     // root box of the BVH (tight bounds of the triangles)
     int has_transmissive;
 };
 
@@ -63,6 +66,50 @@ __device__ __forceinline__ V3 normalized(V3 a) {                                
 __device__ __forceinline__ float max_std(float a, float b) { return (a < b) ? b : a; }                   // std::max(a, b)
 
 struct Hit { float t, u, v; int tri; };
+
+// ---- the structure behind the accelerated query mode -----------------------------------------------------------------------
+// RT_ACCEL_BVH = 1 (default): the bounding-volume hierarchy (rt_bvh.cuh); 0: the SAH kd-tree (rt_kd8.cuh), kept as a
+// compile-time alternative for A/B measurements.  Both give the same hits (same triangle arithmetic, same tie rule).
+#ifndef RT_ACCEL_BVH
+#define RT_ACCEL_BVH 1
+#endif
+#if RT_ACCEL_BVH
+using AccelState = BvhState;
+using AccelStackEntry = BvhStackEntry;
+constexpr int ACCEL_STACK = BVH_STACK;
+__device__ __forceinline__ bool accel_init(AccelState& st, const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
+                                           float t_far, bool any_hit) {
+    return bvh_init(st, sc.b_root_min, sc.b_root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit);
+}
+__device__ __forceinline__ void accel_node_step(AccelState& st, AccelStackEntry* stack, const DScene& sc) { bvh_node_step(st, stack, sc.b_nodes); }
+template <bool CULL, bool FAST>
+__device__ __forceinline__ void accel_leaf_step(AccelState& st, const AccelStackEntry* stack, const DScene& sc, float eps) {
+    bvh_leaf_step<CULL, FAST>(st, stack, sc.b_tris, eps);
+}
+template <bool CULL, bool FAST>
+__device__ __forceinline__ KdHit accel_trace(const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
+                                             float t_far, bool any_hit) {
+    return bvh_trace<CULL, FAST>(sc.b_nodes, sc.b_tris, sc.b_root_min, sc.b_root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
+}
+#else
+using AccelState = Kd8State;
+using AccelStackEntry = KdStackEntry;
+constexpr int ACCEL_STACK = KD8_STACK;
+__device__ __forceinline__ bool accel_init(AccelState& st, const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
+                                           float t_far, bool any_hit) {
+    return kd8_init(st, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit);
+}
+__device__ __forceinline__ void accel_node_step(AccelState& st, AccelStackEntry* stack, const DScene& sc) { kd8_node_step(st, stack, sc.a_nodes8); }
+template <bool CULL, bool FAST>
+__device__ __forceinline__ void accel_leaf_step(AccelState& st, const AccelStackEntry* stack, const DScene& sc, float eps) {
+    kd8_leaf_step<CULL, FAST>(st, stack, sc.a_nodes8, sc.a_tris, eps);
+}
+template <bool CULL, bool FAST>
+__device__ __forceinline__ KdHit accel_trace(const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
+                                             float t_far, bool any_hit) {
+    return kd8_trace<CULL, FAST>(sc.a_nodes8, sc.a_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
+}
+#endif
 
 // ---- ray vs. 4-triangle SoA packet --------------------------------------------------------------------------------
 // triangle_packet<F,W>::intersect (kd_tree_simd.hpp:25-60), one lane, in the reference's operation order, folded
@@ -298,8 +345,7 @@ __device__ __forceinline__ Hit trace_any(const DScene& sc, bool active, V3 o, V3
         Hit h; h.t = FLT_MAX; h.u = 0.0f; h.v = 0.0f; h.tri = -1;
         bool tie = false;
         if (active) {
-            const KdHit k = kd8_trace<CULL, FAST>(sc.a_nodes8, sc.a_tris, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, eps,
-                                                  t_far, any_hit);
+            const KdHit k = accel_trace<CULL, FAST>(sc, o.x, o.y, o.z, d.x, d.y, d.z, eps, t_far, any_hit);
             h.t = k.t; h.u = k.u; h.v = k.v; h.tri = k.tri;
             tie = !any_hit && k.tri >= 0 && k.tie_t == k.t;
         }

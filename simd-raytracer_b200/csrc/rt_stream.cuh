@@ -41,14 +41,14 @@ __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox
 
 // Policy concept:
 //   bool load(const DScene&, uint32_t& idx, V3& o, V3& d, float& t_far, bool& any_hit)  false: entry needs no query; may remap idx
-//   bool finish(const DScene&, uint32_t idx, const Hit& h, Kd8State& st)                  true: lane re-armed (st re-initialised)
+//   bool finish(const DScene&, uint32_t idx, const Hit& h, AccelState& st)                  true: lane re-armed (st re-initialised)
 template <bool CULL, bool FAST, class Policy>
 __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
-    Kd8State st;
-    KdStackEntry stack[KD8_STACK];
-    st.sp = 0; st.phase = KD8_DONE; st.any_hit = false; st.best.tri = -1; st.best.t = FLT_MAX; st.best.tie_t = -1.0f;
+    AccelState st;
+    AccelStackEntry stack[ACCEL_STACK];
+    st.sp = 0; st.phase = KD8_DONE; st.any_hit = false; st.best.tri = -1; st.best.t = FLT_MAX; st.best.tie_t = -1.0f; st.t_far = FLT_MAX;
     st.ox = st.oy = st.oz = st.dx = st.dy = st.dz = 0.0f;
     bool busy = false, exhausted = false;
     uint32_t idx = 0;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
                     idx = mine;
                     V3 o, d; float t_far; bool any_hit;
                     if (p.load(sc, idx, o, d, t_far, any_hit)) {
-                        if (kd8_init(st, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, t_far, any_hit)) busy = true;
+                        if (accel_init(st, sc, o.x, o.y, o.z, d.x, d.y, d.z, t_far, any_hit)) busy = true;
                         else {
                             Hit miss; miss.t = FLT_MAX; miss.u = 0.0f; miss.v = 0.0f; miss.tri = -1;
                             busy = p.finish(sc, idx, miss, st);
@@ -88,11 +88,11 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
         for (int it = 0; it < STREAM_BURST; ++it) {
 #pragma unroll 1
             for (int k = 0; k < STREAM_NODE_STEPS; ++k)
-                if (busy && st.phase == KD8_WALK) kd8_node_step(st, stack, sc.a_nodes8);
+                if (busy && st.phase == KD8_WALK) accel_node_step(st, stack, sc);
             const uint32_t parked = __ballot_sync(FULL, busy && st.phase == KD8_LEAF);
             const uint32_t walking = __ballot_sync(FULL, busy && st.phase == KD8_WALK);
             if (parked && (__popc(parked) >= STREAM_LEAF_MIN || !walking)) {
-                if (busy && st.phase == KD8_LEAF) kd8_leaf_step<CULL, FAST>(st, stack, sc.a_nodes8, sc.a_tris, eps);
+                if (busy && st.phase == KD8_LEAF) accel_leaf_step<CULL, FAST>(st, stack, sc, eps);
             }
             const int running = __popc(__ballot_sync(FULL, busy && st.phase != KD8_DONE));
             if (running == 0 || (!exhausted && running < STREAM_REFILL_BELOW)) break;
@@ -137,7 +137,7 @@ struct PrimaryPolicy {
         ++n_rays;
         return true;
     }
-    __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, Kd8State&) {
+    __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, AccelState&) {
         store_hit(hits + i, h);
         n_hits += (h.tri >= 0);
         return false;
@@ -163,7 +163,7 @@ struct LevelPolicy {
         ++n_rays;
         return true;
     }
-    __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, Kd8State&) {
+    __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, AccelState&) {
         store_hit(hits + begin + i, h);
         n_hits += (h.tri >= 0);
         return false;
@@ -205,7 +205,7 @@ struct ShadowPolicy {
         return true;
     }
     // the query's origin, direction and remaining max_t are the traversal state's own (st.o*, st.d*, st.t_far)
-    __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, Kd8State& st) {
+    __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, AccelState& st) {
         ++n_q;                                                                                           // :116 one closest-hit query
         if (h.tri < 0) return false;                                                                     // :117
         ++n_h;
@@ -218,7 +218,7 @@ struct ShadowPolicy {
                 const V3 o = pos + shadow_bias * d;                                                      // :126
                 const float max_t = st.t_far - h.t;                                                      // :127
                 if (!(0.0f < max_t)) return false;                                                       // :115
-                if (kd8_init(st, sc.root_min, sc.root_max, o.x, o.y, o.z, d.x, d.y, d.z, max_t, false)) return true;
+                if (accel_init(st, sc, o.x, o.y, o.z, d.x, d.y, d.z, max_t, false)) return true;
                 ++n_q;                                                                                   // the next query misses the scene box
                 return false;
             }

@@ -89,4 +89,15 @@ struct AccelLayout {
 };
 AccelLayout flatten_accel(const Geometry& g, const KdTree& t);
 
+// the bounding-volume hierarchy of the accelerated mode (bvh_build.cpp, csrc/rt_bvh.cuh): same KdTree container (node boxes
+// are the tight bounds, `axis`/`split` record the SAH decision), flattened to 64-byte two-child nodes
+KdTree build_bvh(const Geometry& g, uint32_t max_leaf);
+struct BvhLayout {
+    std::vector<uint32_t> nodes;       // 16 words per inner node
+    std::vector<uint32_t> tris;        // 12 words per triangle record, leaf order
+    uint64_t n_nodes = 0, n_refs = 0;
+    float root_min[3] = {3.0e38f, 3.0e38f, 3.0e38f}, root_max[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+};
+BvhLayout flatten_bvh(const Geometry& g, const KdTree& t);
+
 }  // namespace rtb

@@ -1,11 +1,12 @@
-// tests/helpers/kd8_host.cpp - TEST INFRASTRUCTURE: compiles simd-raytracer_b200/csrc/rt_kd8.cuh (the accelerated traversal the
+// tests/helpers/kd8_host.cpp - TEST INFRASTRUCTURE: compiles simd-raytracer_b200/csrc/rt_bvh.cuh and rt_kd8.cuh (the accelerated traversals the
 // CUDA kernels run) as plain C++ so that tests/test_kd8_host.py can check the algorithm and the flattened tree against the
 // oracle on a machine without a GPU.  Built with -ffp-contract=off (the device TU is built with -fmad=false).
 #include <cstdint>
 static uint64_t g_kd8_nodes, g_kd8_tris;                 // visit counters (rt_kd8.cuh instrumentation hooks)
 #define KD8_COUNT_NODE() (++g_kd8_nodes)
 #define KD8_COUNT_TRI() (++g_kd8_tris)
-#include "../../simd-raytracer_b200/csrc/rt_kd8.cuh"
+#define BVH_COUNT_NODE() (++g_kd8_nodes)
+#include "../../simd-raytracer_b200/csrc/rt_bvh.cuh"          // includes rt_kd8.cuh
 
 extern "C" void kd8_counters(uint64_t* nodes, uint64_t* tris, int reset) {
     if (nodes) *nodes = g_kd8_nodes;
@@ -26,5 +27,22 @@ extern "C" void kd8_trace_batch(const uint32_t* nodes8, const float* tris, const
         tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
         tri[i] = h.tri;
         if (tie) tie[i] = (h.tri >= 0 && h.tie_t == h.t) ? 1 : 0;     // the device re-runs these through the reference-order query
+    }
+}
+
+// the same batch through the bounding-volume hierarchy (rt_scene_get_bvh_layout)
+extern "C" void bvh_trace_batch(const float* nodes16, const float* tris, const float* root6, const float* rays6, uint64_t n,
+                                int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* q = rays6 + 6 * i;
+        const float far = t_far ? t_far[i] : FLT_MAX;
+        rtb::KdHit h;
+        if (cull) h = fast ? rtb::bvh_trace<true, true>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
+                           : rtb::bvh_trace<true, false>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        else h = fast ? rtb::bvh_trace<false, true>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
+                      : rtb::bvh_trace<false, false>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
+        tri[i] = h.tri;
+        if (tie) tie[i] = (h.tri >= 0 && h.tie_t == h.t) ? 1 : 0;
     }
 }

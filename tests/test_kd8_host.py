@@ -1,6 +1,7 @@
-"""The accelerated traversal (simd-raytracer_b200/csrc/rt_kd8.cuh, RT_FLAG_ORDERED) checked on the CPU: the same source the
-CUDA kernels compile is built as plain C++ (tests/helpers/kd8_host.cpp) and run over the product's flattened tree
-(rt_scene_get_accel_layout, host-only scene) against the oracle's reference-order traversal.  No product compute runs here."""
+"""The accelerated traversals (RT_FLAG_ORDERED) checked on the CPU: the bounding-volume hierarchy the kernels ship with
+(simd-raytracer_b200/csrc/rt_bvh.cuh) and its kd-tree alternative (rt_kd8.cuh).  The same source the CUDA kernels compile is
+built as plain C++ (tests/helpers/kd8_host.cpp) and run over the product's flattened structures (rt_scene_get_bvh_layout /
+rt_scene_get_accel_layout, host-only scene) against the oracle's reference-order traversal.  No product compute runs here."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,23 +15,26 @@ from .conftest import REPO, SCENES, resized, scene_bytes
 from .helpers import crtscene
 
 
-@pytest.fixture(scope="module")
-def kd8(tmp_path_factory):
+@pytest.fixture(scope="module", params=["bvh", "kd"])
+def kd8(tmp_path_factory, request):
+    structure = request.param
     out = tmp_path_factory.mktemp("kd8") / "libkd8_host.so"
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
                            os.path.join(REPO, "tests", "helpers", "kd8_host.cpp"), "-o", str(out)])
     lib = C.CDLL(str(out))
-    lib.kd8_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
-                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    for fn in (lib.kd8_trace_batch, lib.bvh_trace_batch):
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
+                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    batch = lib.bvh_trace_batch if structure == "bvh" else lib.kd8_trace_batch
 
     def trace(scene, rays, cull, fast=False, t_far=None, any_hit=False, eps=np.float32(1e-6)):
-        nodes8, packets, root = scene.accel_layout()
+        nodes8, packets, root = scene.bvh_layout() if structure == "bvh" else scene.accel_layout()
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         tuv = np.zeros((len(rays), 3), np.float32)
         tri = np.zeros(len(rays), np.int32)
         tie = np.zeros(len(rays), np.uint8)
         far = None if t_far is None else np.ascontiguousarray(t_far, np.float32)
-        lib.kd8_trace_batch(nodes8.ctypes.data, packets.ctypes.data, root.ctypes.data, rays.ctypes.data, len(rays), int(cull), int(fast),
+        batch(nodes8.ctypes.data, packets.ctypes.data, root.ctypes.data, rays.ctypes.data, len(rays), int(cull), int(fast),
                             C.c_float(eps), None if far is None else far.ctypes.data, int(any_hit), tuv.ctypes.data, tri.ctypes.data, tie.ctypes.data)
         return tuv, tri, tie.astype(bool)
 
@@ -63,7 +67,7 @@ def test_kd8_equals_reference_traversal(rt, oracle_mod, kd8, name):
     data = resized(scene_bytes(name), 640, 360 if name != "hw15_scene2" else 640)
     s = rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY)
     o = oracle_mod.Oracle(data)
-    assert s.info.accel_n_nodes >= 1
+    assert s.info.bvh_n_nodes >= 1 and s.info.bvh_n_refs == s.info.n_triangles
     for rays, cull in ((o.primary_rays(), True), (scene_rays(o, s), False)):
         want_tuv, want_tri = o.trace(rays, cull)
         tuv, tri, tie = kd8(s, rays, cull)
