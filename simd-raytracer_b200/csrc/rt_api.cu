@@ -279,7 +279,7 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
 #endif
     {
         const double t3 = now_s();
-        uint32_t leaf = 2;                                             // RT_B200_BVH_LEAF: tuning sweeps only
+        uint32_t leaf = 4;                                             // RT_B200_BVH_LEAF: tuning sweeps only
         if (const char* e = std::getenv("RT_B200_BVH_LEAF")) std::sscanf(e, "%u", &leaf);
         KdTree bvh = build_bvh(s->geom, leaf);
         s->bvh_layout = flatten_bvh(s->geom, bvh);
@@ -678,7 +678,7 @@ int rt_scene_get_bvh_layout(const rt_scene* s, uint32_t* nodes16, uint32_t* tris
     if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
     if (nodes16) std::memcpy(nodes16, s->bvh_layout.nodes.data(), size_t(s->bvh_layout.n_nodes) * 16 * 4);
     if (tris12) std::memcpy(tris12, s->bvh_layout.tris.data(), size_t(s->bvh_layout.n_refs) * 12 * 4);
-    if (root6) { std::memcpy(root6, s->bvh_layout.root_min, 12); std::memcpy(root6 + 3, s->bvh_layout.root_max, 12); }
+    if (root6) { std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12); }   // the reference's root box (bvh_init)
     return RT_OK;
 }
 

@@ -80,18 +80,29 @@ RT_HD void bvh_slab(const BvhState& s, float lx, float ly, float lz, float hx, f
     t_out = bvh_min(bvh_min(bvh_max(ax, bx), bvh_max(ay, by)), bvh_max(az, bz));
 }
 
-// returns false when the ray misses the root box (the query is then finished: a miss)
-RT_HD bool bvh_init(BvhState& s, const float* root_min, const float* root_max, float ox, float oy, float oz, float dx, float dy, float dz,
+// returns false when the ray misses the scene (the query is then finished: a miss).  ref_min / ref_max is the REFERENCE's
+// root box (union of the mesh boxes, kd_tree_simd.hpp:101-104) and the test is the reference's own slab arithmetic with its
+// strict t_max < t_min (aabb3.hpp:74-90): whether a ray that starts on the scene boundary and leaves it "misses the scene" is
+// decided exactly as the reference decides it.  Below the root the BVH's own padded boxes take over.
+RT_HD bool bvh_init(BvhState& s, const float* ref_min, const float* ref_max, float ox, float oy, float oz, float dx, float dy, float dz,
                     float t_far, bool any_hit) {
     s.ox = ox; s.oy = oy; s.oz = oz; s.dx = dx; s.dy = dy; s.dz = dz;
     s.ix = 1.0f / dx; s.iy = 1.0f / dy; s.iz = 1.0f / dz;
     s.t_far = t_far; s.any_hit = any_hit;
     s.best.t = FLT_MAX; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = -1; s.best.tie_t = -1.0f;
     s.ref = 0; s.cnt = 0; s.sp = 0; s.phase = KD8_DONE; s.t0 = 0.0f;
-    float t_in, t_out;
-    bvh_slab(s, root_min[0], root_min[1], root_min[2], root_max[0], root_max[1], root_max[2], t_in, t_out);
-    const float in_s = t_in * (1.0f - BVH_SLACK);
-    if (!(in_s <= t_out * (1.0f + BVH_SLACK)) || !(in_s <= t_far)) return false;
+    float t0 = 0.0f, t1 = FLT_MAX;
+    const float ax = (ref_min[0] - ox) * s.ix, bx = (ref_max[0] - ox) * s.ix;
+    const float ay = (ref_min[1] - oy) * s.iy, by = (ref_max[1] - oy) * s.iy;
+    const float az = (ref_min[2] - oz) * s.iz, bz = (ref_max[2] - oz) * s.iz;
+    t0 = kd_max(t0, (bx < ax) ? bx : ax); t1 = kd_min(t1, (bx < ax) ? ax : bx);
+    t0 = kd_max(t0, (by < ay) ? by : ay); t1 = kd_min(t1, (by < ay) ? ay : by);
+    t0 = kd_max(t0, (bz < az) ? bz : az); t1 = kd_min(t1, (bz < az) ? az : bz);
+    if (t1 < t0 || !(t0 * (1.0f - BVH_SLACK) <= t_far)) return false;
+    // t1 == 0: the ray starts ON the scene boundary and leaves the scene at once.  Which wall triangles the reference still
+    // tests then depends on its own leaf boxes, so such rays (rare) are answered by the reference-order traversal: the lane
+    // finishes at once with the KD_RERUN mark
+    if (!(0.0f < t1)) { s.best.tri = KD_RERUN; return true; }
     s.phase = KD8_WALK;
     return true;
 }

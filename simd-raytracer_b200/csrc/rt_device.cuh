@@ -79,7 +79,7 @@ using AccelStackEntry = BvhStackEntry;
 constexpr int ACCEL_STACK = BVH_STACK;
 __device__ __forceinline__ bool accel_init(AccelState& st, const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
                                            float t_far, bool any_hit) {
-    return bvh_init(st, sc.b_root_min, sc.b_root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit);
+    return bvh_init(st, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit);
 }
 __device__ __forceinline__ void accel_node_step(AccelState& st, AccelStackEntry* stack, const DScene& sc) { bvh_node_step(st, stack, sc.b_nodes); }
 template <bool CULL, bool FAST>
@@ -89,7 +89,7 @@ __device__ __forceinline__ void accel_leaf_step(AccelState& st, const AccelStack
 template <bool CULL, bool FAST>
 __device__ __forceinline__ KdHit accel_trace(const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
                                              float t_far, bool any_hit) {
-    return bvh_trace<CULL, FAST>(sc.b_nodes, sc.b_tris, sc.b_root_min, sc.b_root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
+    return bvh_trace<CULL, FAST>(sc.b_nodes, sc.b_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
 }
 #else
 using AccelState = Kd8State;
@@ -347,7 +347,7 @@ __device__ __forceinline__ Hit trace_any(const DScene& sc, bool active, V3 o, V3
         if (active) {
             const KdHit k = accel_trace<CULL, FAST>(sc, o.x, o.y, o.z, d.x, d.y, d.z, eps, t_far, any_hit);
             h.t = k.t; h.u = k.u; h.v = k.v; h.tri = k.tri;
-            tie = !any_hit && k.tri >= 0 && k.tie_t == k.t;
+            tie = (k.tri == KD_RERUN) || (!any_hit && k.tri >= 0 && k.tie_t == k.t);
         }
         // two different triangles at exactly the winner's t: which one the reference reports depends on its leaf order,
         // so those rays (rare) take the reference-order query

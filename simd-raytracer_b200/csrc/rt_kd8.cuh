@@ -43,6 +43,8 @@
 namespace rtb {
 
 struct KdHit { float t, u, v; int tri; float tie_t; };   // tie_t == t: another triangle has exactly the winner's t
+// tri == KD_RERUN: the query has to be answered by the reference-order traversal (see kd8_init / bvh_init)
+constexpr int KD_RERUN = -3;
 
 RT_HD float kd_bits_to_float(uint32_t u) {
 #if defined(__CUDA_ARCH__)
@@ -217,8 +219,15 @@ RT_HD bool kd8_init(Kd8State& s, const float* root_min, const float* root_max, f
     t0 = kd_max(t0, (bx < ax) ? bx : ax); t1 = kd_min(t1, (bx < ax) ? ax : bx);
     t0 = kd_max(t0, (by < ay) ? by : ay); t1 = kd_min(t1, (by < ay) ? ay : by);
     t0 = kd_max(t0, (bz < az) ? bz : az); t1 = kd_min(t1, (bz < az) ? az : bz);
-    const float S = 2e-6f;                       // relative widening of every interval comparison
-    if (t1 + S * fabsf(t1) < t0) return false;
+    // the root box is the reference's own root box and this is the reference's own arithmetic, so the decision "the ray
+    // misses the scene" is taken exactly as the reference takes it (strict t_max < t_min, aabb3.hpp:81-88): a ray that starts
+    // ON the scene boundary and leaves it is a miss there even where a triangle test alone would still accept a wall
+    const float S = 2e-6f;                       // relative widening of every interval comparison below the root
+    if (t1 < t0) return false;
+    // t1 == 0: the ray starts ON the scene boundary and leaves the scene at once.  Which wall triangles the reference still
+    // tests then depends on its own leaf boxes, so such rays (rare) are answered by the reference-order traversal: the lane
+    // finishes at once with the KD_RERUN mark
+    if (!(0.0f < t1)) { s.best.tri = KD_RERUN; return true; }
     s.t0 = kd_max(0.0f, t0 - S * fabsf(t0));
     s.t1 = t1 + S * fabsf(t1);
     if (!(s.t0 <= t_far)) return false;

@@ -100,7 +100,7 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
         // ---- completion (warp-uniform) ----
         const bool fin = busy && st.phase == KD8_DONE;
         Hit h; h.t = st.best.t; h.u = st.best.u; h.v = st.best.v; h.tri = st.best.tri;
-        const bool tie = fin && !st.any_hit && st.best.tri >= 0 && st.best.tie_t == st.best.t;
+        const bool tie = fin && (st.best.tri == KD_RERUN || (!st.any_hit && st.best.tri >= 0 && st.best.tie_t == st.best.t));
         if (__ballot_sync(FULL, tie)) {
             // two different triangles at exactly the winner's t: the reference's leaf order decides, so ask it
             exact_rerun<CULL, FAST>(sc, tie, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, eps, &h);

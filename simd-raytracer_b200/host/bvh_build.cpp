@@ -154,11 +154,19 @@ BvhLayout flatten_bvh(const Geometry& g, const KdTree& t) {
     const bool leaf_root = n_nodes > 0 && t.nodes[0].first_ref != KD_NONE;
     d.n_nodes = std::max<uint64_t>(n_inner, 1);
     d.nodes.assign(16 * d.n_nodes, 0u);
+    // Every stored box is grown by an absolute pad (2e-5 of the largest coordinate magnitude of the scene).  The reference accepts
+    // a hit when its ROUNDED u, v, t pass (kd_tree_simd.hpp:47,54,57), so an accepted hit point may lie a few ulps of the scene
+    // scale outside the triangle's own box - e.g. a ray that starts on the ceiling plane and hits a wall 3e-7 above the wall's
+    // top edge; the relative slack of the slab test (rt_bvh.cuh) vanishes at t ~ 0 and cannot cover that.
+    float scale = 0.0f;
+    if (n_nodes)
+        for (int c = 0; c < 3; ++c) scale = std::max(scale, std::max(std::fabs(t.nodes[0].bmin[c]), std::fabs(t.nodes[0].bmax[c])));
+    const float pad = 2e-5f * scale;
     auto put_child = [&](uint32_t* node, int slot, const KdNode* c, uint64_t ci) {
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};   // inverted: never hit
         uint32_t ref = 0, cnt = 0xFFFFFFFFu;
         if (c) {
-            std::memcpy(lo, c->bmin, 12); std::memcpy(hi, c->bmax, 12);
+            for (int a = 0; a < 3; ++a) { lo[a] = c->bmin[a] - pad; hi[a] = c->bmax[a] + pad; }
             if (c->first_ref != KD_NONE) { if (c->ref_count) { ref = uint32_t(c->first_ref); cnt = uint32_t(c->ref_count); } }   // an empty leaf is no child
             else { ref = inner_index[ci]; cnt = 0; }
         }
@@ -192,7 +200,8 @@ BvhLayout flatten_bvh(const Geometry& g, const KdTree& t) {
             p[8] = bits(tg.e2[0]); p[9] = bits(tg.e2[1]); p[10] = bits(tg.e2[2]);
         }
     });
-    if (n_nodes) { std::memcpy(d.root_min, t.nodes[0].bmin, 12); std::memcpy(d.root_max, t.nodes[0].bmax, 12); }
+    if (n_nodes)
+        for (int a = 0; a < 3; ++a) { d.root_min[a] = t.nodes[0].bmin[a] - pad; d.root_max[a] = t.nodes[0].bmax[a] + pad; }
     return d;
 }
 

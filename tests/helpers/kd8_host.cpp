@@ -26,7 +26,7 @@ extern "C" void kd8_trace_batch(const uint32_t* nodes8, const float* tris, const
                       : rtb::kd8_trace<false, false>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
         tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
         tri[i] = h.tri;
-        if (tie) tie[i] = (h.tri >= 0 && h.tie_t == h.t) ? 1 : 0;     // the device re-runs these through the reference-order query
+        if (tie) tie[i] = (h.tri == rtb::KD_RERUN || (h.tri >= 0 && h.tie_t == h.t)) ? 1 : 0;     // the device re-runs these through the reference-order query
     }
 }
 
@@ -43,6 +43,6 @@ extern "C" void bvh_trace_batch(const float* nodes16, const float* tris, const f
                       : rtb::bvh_trace<false, false>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
         tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
         tri[i] = h.tri;
-        if (tie) tie[i] = (h.tri >= 0 && h.tie_t == h.t) ? 1 : 0;
+        if (tie) tie[i] = (h.tri == rtb::KD_RERUN || (h.tri >= 0 && h.tie_t == h.t)) ? 1 : 0;
     }
 }

@@ -123,3 +123,55 @@ def test_origin_on_split_planes_stays_cheap(rt, oracle_mod, kd8):
     want_tuv, want_tri = o.trace(rays, True)
     assert np.array_equal(tri[~tie], want_tri[~tie]) and np.array_equal(tri >= 0, want_tri >= 0)
     assert nodes / len(rays) < 40 and tris / len(rays) < 12, (nodes / len(rays), tris / len(rays))
+
+
+def test_rays_from_walls_edges_and_triangles(rt, oracle_mod, kd8):
+    """Adversarial origins: exactly on the scene's boundary walls, their edges and corners, and on triangles (edges and
+    vertices included), with generic and nearly axis-parallel directions.  The reference accepts a hit when its ROUNDED u, v, t
+    pass, so accepted hit points may sit a few ulps outside a triangle's own box (-> the BVH boxes are padded), and whether a
+    ray that touches the scene box at a single parameter value still meets a wall depends on the reference's own leaf boxes
+    (-> such rays carry the re-run mark and are answered in reference order on the device).  Everything else must agree bit
+    for bit."""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=20_000, seed=77, width=64, height=48))
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64, device=rt.DEVICE_HOST_ONLY)
+    o = oracle_mod.Oracle(data, 24, 64)
+    rng = np.random.default_rng(5)
+    n = 60_000
+    t9, _, _ = s.geometry()
+
+    def on_walls():
+        p = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+        ax = rng.integers(0, 3, n)
+        p[np.arange(n), ax] = rng.choice([-1.5, 1.5], n).astype(np.float32)
+        k = n // 4
+        p[np.arange(k), (ax[:k] + 1) % 3] = rng.choice([-1.5, 1.5], k).astype(np.float32)      # edges
+        return p
+
+    def on_tris():
+        k = rng.integers(0, len(t9), n)
+        u, v = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+        f = u + v > 1
+        u[f], v[f] = 1 - u[f], 1 - v[f]
+        v[rng.uniform(size=n) < 0.3] = 0                                                        # edges
+        w = rng.uniform(size=n) < 0.1
+        u[w], v[w] = 0, 0                                                                       # vertices
+        return (t9[k, :3] + u[:, None] * t9[k, 3:6] + v[:, None] * t9[k, 6:9]).astype(np.float32)
+
+    def dirs(flat):
+        d = rng.normal(size=(n, 3))
+        if flat:
+            d[np.arange(n), rng.integers(0, 3, n)] *= 1e-4
+        return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+    for org in (on_walls, on_tris):
+        for flat in (False, True):
+            rays = np.concatenate([org(), dirs(flat)], axis=1)
+            for cull in (False, True):
+                want_tuv, want_tri = o.trace(rays, cull)
+                tuv, tri, rerun = kd8(s, rays, cull)
+                ok = ~rerun
+                assert np.array_equal(tri[ok], want_tri[ok])
+                h = ok & (want_tri >= 0)
+                assert np.array_equal(tuv[h].view(np.uint32), want_tuv[h].view(np.uint32))
+                if org is on_tris:
+                    assert rerun.mean() < 2e-2
