@@ -12,6 +12,7 @@ run() {  # name, env assignments...
   done
 }
 run base X=1
+shopt -s nullglob
 for v in simd-raytracer_b200/variants/librt_*.so; do n=$(basename $v .so); run ${n#librt_} RT_B200_LIB=$PWD/$v; done
 for e in $SWEEP_ENVS; do run $(echo $e | tr -c 'A-Za-z0-9\n' '_') $e; done
 python - <<PY

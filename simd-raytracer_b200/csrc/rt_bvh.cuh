@@ -61,7 +61,7 @@ RT_HD float bvh_max(float a, float b) {
 
 // phase: WALK = standing at inner node `ref`; LEAF = standing at a leaf (cnt triangles from record `ref`); DONE
 struct BvhState {
-    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+    float ox, oy, oz, dx, dy, dz;                 // 1/d is re-derived per node visit (three MUFU) instead of living in three registers
     float t0, t_far;
     uint32_t ref, cnt;
     int sp, phase;
@@ -72,10 +72,11 @@ struct BvhState {
 constexpr float BVH_SLACK = 1e-5f;
 
 // entry and exit parameter of the ray in a box; entry clamped to 0, NaNs (0 * inf) ignored
-RT_HD void bvh_slab(const BvhState& s, float lx, float ly, float lz, float hx, float hy, float hz, float& t_in, float& t_out) {
-    const float ax = (lx - s.ox) * s.ix, bx = (hx - s.ox) * s.ix;
-    const float ay = (ly - s.oy) * s.iy, by = (hy - s.oy) * s.iy;
-    const float az = (lz - s.oz) * s.iz, bz = (hz - s.oz) * s.iz;
+RT_HD void bvh_slab(const BvhState& s, float ix, float iy, float iz, float lx, float ly, float lz, float hx, float hy, float hz,
+                    float& t_in, float& t_out) {
+    const float ax = (lx - s.ox) * ix, bx = (hx - s.ox) * ix;
+    const float ay = (ly - s.oy) * iy, by = (hy - s.oy) * iy;
+    const float az = (lz - s.oz) * iz, bz = (hz - s.oz) * iz;
     t_in = bvh_max(bvh_max(bvh_min(ax, bx), bvh_min(ay, by)), bvh_max(bvh_min(az, bz), 0.0f));
     t_out = bvh_min(bvh_min(bvh_max(ax, bx), bvh_max(ay, by)), bvh_max(az, bz));
 }
@@ -87,14 +88,14 @@ RT_HD void bvh_slab(const BvhState& s, float lx, float ly, float lz, float hx, f
 RT_HD bool bvh_init(BvhState& s, const float* ref_min, const float* ref_max, float ox, float oy, float oz, float dx, float dy, float dz,
                     float t_far, bool any_hit) {
     s.ox = ox; s.oy = oy; s.oz = oz; s.dx = dx; s.dy = dy; s.dz = dz;
-    s.ix = 1.0f / dx; s.iy = 1.0f / dy; s.iz = 1.0f / dz;
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;          // the reference's inv_direction (ray3.hpp:11-14)
     s.t_far = t_far; s.any_hit = any_hit;
     s.best.t = FLT_MAX; s.best.u = 0.0f; s.best.v = 0.0f; s.best.tri = -1; s.best.tie_t = -1.0f;
     s.ref = 0; s.cnt = 0; s.sp = 0; s.phase = KD8_DONE; s.t0 = 0.0f;
     float t0 = 0.0f, t1 = FLT_MAX;
-    const float ax = (ref_min[0] - ox) * s.ix, bx = (ref_max[0] - ox) * s.ix;
-    const float ay = (ref_min[1] - oy) * s.iy, by = (ref_max[1] - oy) * s.iy;
-    const float az = (ref_min[2] - oz) * s.iz, bz = (ref_max[2] - oz) * s.iz;
+    const float ax = (ref_min[0] - ox) * ix, bx = (ref_max[0] - ox) * ix;
+    const float ay = (ref_min[1] - oy) * iy, by = (ref_max[1] - oy) * iy;
+    const float az = (ref_min[2] - oz) * iz, bz = (ref_max[2] - oz) * iz;
     t0 = kd_max(t0, (bx < ax) ? bx : ax); t1 = kd_min(t1, (bx < ax) ? ax : bx);
     t0 = kd_max(t0, (by < ay) ? by : ay); t1 = kd_min(t1, (by < ay) ? ay : by);
     t0 = kd_max(t0, (bz < az) ? bz : az); t1 = kd_min(t1, (bz < az) ? az : bz);
@@ -122,9 +123,11 @@ RT_HD void bvh_node_step(BvhState& s, BvhStackEntry* stack, const float* __restr
         BVH_COUNT_NODE();
         const float* p = nodes + size_t(s.ref) * 16u;
         const KdRow q0 = kd_load_row(p), q1 = kd_load_row(p + 4), q2 = kd_load_row(p + 8), q3 = kd_load_row(p + 12);
+        // the 1-ulp reciprocal is enough under the box slack; a flushed subnormal component behaves like zero (parallel ray)
+        const float ix = kd_rcp_estimate(s.dx), iy = kd_rcp_estimate(s.dy), iz = kd_rcp_estimate(s.dz);
         float in0, out0, in1, out1;
-        bvh_slab(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, in0, out0);
-        bvh_slab(s, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, in1, out1);
+        bvh_slab(s, ix, iy, iz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, in0, out0);
+        bvh_slab(s, ix, iy, iz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, in1, out1);
         const uint32_t ref0 = uint32_t(kd_as_int(q3.x)), ref1 = uint32_t(kd_as_int(q3.y));
         const uint32_t cnt0 = uint32_t(kd_as_int(q3.z)), cnt1 = uint32_t(kd_as_int(q3.w));
         const float e0 = in0 * (1.0f - BVH_SLACK), e1 = in1 * (1.0f - BVH_SLACK);         // widened entry points (>= 0)
