@@ -380,9 +380,19 @@ def main() -> None:
         dom = max(cls, key=cls.get)
         # dominant kernel = the trace kernel class with the largest share of the frame; algorithmic bytes = the REFERENCE
         # algorithm's node + triangle fetches for that ray kind (tests/golden/workloads.json)
-        dom_kernel = {"primary": "k_primary", "secondary": "k_trace_level", "shadow": "k_shadow"}[dom]
+        accel = args.mode.endswith("ordered")
+        dom_kernel = ({"primary": "k_stream_primary", "secondary": "k_stream_level", "shadow": "k_stream_shadow"} if accel else
+                      {"primary": "k_primary", "secondary": "k_trace_level", "shadow": "k_shadow"})[dom]
         n_dom_launch = {"primary": 1, "secondary": max(1, w["max_ray_depth"]), "shadow": 1}[dom]
         ach = kinds[dom]["alg_bytes"] / (cls[dom] * 1e-3) / 1e9 if cls[dom] > 0 else 0.0
+        # dram__bytes_read + dram__bytes_write of that kernel per launch, from the committed ncu --set full capture
+        traffic = None
+        try:
+            with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(w["key"], {}).get(args.mode, {}).get(dom_kernel)
+        except OSError:
+            pass
+        own = (kinds[dom].get("own") or {}) if accel else {}
         fp32_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12          # T FP32 instr/s
         line = {
             "metric": "Mrays/s", "value": rays_all * K / (ms_dev * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K,
@@ -400,7 +410,7 @@ def main() -> None:
                             "rt_render_frame_device per rank + combine + float frame to pinned host memory on rank 0")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                          "launches_per_frame": n_dom_launch, "algorithmic_bytes_per_frame": kinds[dom]["alg_bytes"],
                          "note": ("algorithmic bytes = reference algorithm's 8 B/node + 36 B/triangle-test + ray/hit I/O for this ray "
                                   "kind (tests/golden/workloads.json). " +
@@ -410,6 +420,11 @@ def main() -> None:
                                    if w.get("synthetic") else
                                    "The scene (<1 MB) is L1/L2-resident, so these bytes are served on-chip and DRAM traffic is only "
                                    "the ray/hit/record streams - see roofline_fp32 for the issue-rate view."))},
+            "roofline_own": ({"kernel": dom_kernel, "structure": own.get("structure"), "own_bytes_per_frame": own.get("own_bytes"),
+                              "achieved": own["own_bytes"] / (cls[dom] * 1e-3) / 1e9, "unit": "GB/s",
+                              "note": "bytes the shipped traversal itself asks for (64 B per BVH node visit + 48 B per triangle record "
+                                      "+ ray/hit I/O), counted by running its source on the CPU over the same queries"}
+                             if own.get("own_bytes") and cls[dom] > 0 else None),
             "roofline_fp32": {"kernel": dom_kernel, "achieved": kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12 if cls[dom] else 0.0,
                               "peak": fp32_peak, "unit": "T FP32 op/s (no FMA in exact mode)",
                               "frac": (kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12) / fp32_peak if cls[dom] else 0.0},

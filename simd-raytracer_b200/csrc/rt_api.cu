@@ -457,7 +457,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     int& g_resolve = s->g_resolve;                                                   // persistent grid sizes
     const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0);
     const bool tr = s->d.has_transmissive != 0;
-    if (!g_resolve) g_resolve = grid_for(s, k_resolve);
+    if (!g_resolve) g_resolve = grid_for(s, k_resolve<false>);
     if (!g_shade[has_gi]) g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
     const int fi = m.fast ? 1 : 0;
     if (m.ordered) {
@@ -541,17 +541,25 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
                 });
                 ++slot;
             }
+            const bool fuse_acc = ns == 1;          // one sample in the pass: level 0 resolves straight into the framebuffer
+            const int first_pass = done == 0 ? 1 : 0, divide = (!raw && done + ns == spp) ? 1 : 0;
             for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
-                timed(TC_RESOLVE, [&] { k_resolve<<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot); });
+                timed(TC_RESOLVE, [&] {
+                    if (lvl == 0 && fuse_acc)
+                        k_resolve<true><<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, first_pass, divide,
+                                                                   launched, levels);
+                    else
+                        k_resolve<false><<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels);
+                });
                 ++slot;
             }
             k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, s->h_flags, launched, levels);
             CK(cudaGetLastError());
             // the accumulate kernel skips itself on the device when the pass overflowed its pools
-            timed(TC_RESOLVE, [&] {
-                k_accumulate<<<(fp.plane + 255) / 256, 256, 0, st>>>(s->d, fp, s->recs.p, d_rgb, s->ps, done == 0 ? 1 : 0,
-                                                                      (!raw && done + ns == spp) ? 1 : 0);
-            });
+            if (!fuse_acc)
+                timed(TC_RESOLVE, [&] {
+                    k_accumulate<<<(fp.plane + 255) / 256, 256, 0, st>>>(s->d, fp, s->recs.p, d_rgb, s->ps, first_pass, divide);
+                });
             CK(cudaStreamSynchronize(st));
             const uint64_t used_pool = s->h_flags[0], used_shadow = s->h_flags[1];
             if (s->h_flags[2] == 0) {

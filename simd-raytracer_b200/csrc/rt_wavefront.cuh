@@ -449,20 +449,31 @@ __device__ __forceinline__ V3 child_colour(const Rec* __restrict__ recs, uint32_
     return (__float_as_uint(a.x) == REC_MISS) ? on_miss : mk(b.x, b.y, b.z);
 }
 
+// ACC (level 0 of a one-sample pass): the colour goes straight into the framebuffer - render.hpp:66-74 for one sample, the
+// same operations k_accumulate performs - instead of being written to the record and read back by another kernel.  The
+// pass may still be discarded (pool overflow, or a skipped level that was needed, see k_pass_commit): that is known once
+// the last shade kernel has run, so it is evaluated here and nothing is written then.
+template <bool ACC>
 __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec* __restrict__ recs, const ShadowJob* __restrict__ jobs,
-                                                 PassState* __restrict__ ps, int level, int work_slot) {
+                                                 PassState* __restrict__ ps, int level, int work_slot, float* __restrict__ fb,
+                                                 int first_pass, int divide, uint32_t launched, uint32_t total) {
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const V3 bg = mk(sc.bg[0], sc.bg[1], sc.bg[2]), black = mk(0.0f, 0.0f, 0.0f);
     (void)work_slot;
+    bool discard = false;
+    if (ACC) discard = ps->overflow != 0u || (launched < total && ps->pool_count > ps->lv[launched]);
     for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
         if (i >= end) continue;
         float4* p = reinterpret_cast<float4*>(recs + i);
         const float4 a = p[0];
         const uint32_t kind = __float_as_uint(a.x), fc = __float_as_uint(a.y), fs = __float_as_uint(a.z);
-        if (kind <= REC_MISS) continue;
         V3 out;
-        if (kind == REC_REFLECT) out = child_colour(recs, fc, bg);                                       // :245-249
+        if (kind <= REC_MISS) {
+            if (!ACC) continue;
+            if (kind == REC_MISS) out = bg;
+            else { const float4 b = p[1]; out = mk(b.x, b.y, b.z); }
+        } else if (kind == REC_REFLECT) out = child_colour(recs, fc, bg);                                // :245-249
         else if (kind == REC_TIR) out = child_colour(recs, fc, black);                                   // :271-275
         else if (kind == REC_REFRACT) {
             const V3 refr = child_colour(recs, fc, black), refl = child_colour(recs, fc + 1, black);
@@ -489,7 +500,18 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
                 out = mk(__fdiv_rn(out.x, div), __fdiv_rn(out.y, div), __fdiv_rn(out.z, div));
             }
         }
-        p[1] = make_float4(out.x, out.y, out.z, 0.0f);
+        if (!ACC) { p[1] = make_float4(out.x, out.y, out.z, 0.0f); continue; }
+        // level 0, one sample: entry index == position in the sample plane
+        uint32_t x, y;
+        if (discard || !level0_pixel(fp, i - begin, x, y)) continue;
+        float* px = fb + (size_t(y) * sc.width + x) * 3;
+        V3 sum = first_pass ? mk(0.0f, 0.0f, 0.0f) : mk(px[0], px[1], px[2]);
+        sum = sum + out;
+        if (divide) {
+            const float div = float(fp.spp_total);
+            sum = mk(__fdiv_rn(sum.x, div), __fdiv_rn(sum.y, div), __fdiv_rn(sum.z, div));
+        }
+        px[0] = sum.x; px[1] = sum.y; px[2] = sum.z;
     }
 }
 
