@@ -15,7 +15,7 @@ namespace rtb {
 #define RT_STREAM_BURST 8
 #endif
 #ifndef RT_STREAM_NODE_STEPS
-#define RT_STREAM_NODE_STEPS 3
+#define RT_STREAM_NODE_STEPS 4
 #endif
 #ifndef RT_STREAM_LEAF_MIN
 #define RT_STREAM_LEAF_MIN 8
@@ -41,6 +41,7 @@ __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox
 
 // Policy concept:
 //   bool load(const DScene&, uint32_t& idx, V3& o, V3& d, float& t_far, bool& any_hit)  false: entry needs no query; may remap idx
+//   void entered(uint32_t idx, V3 o, V3 d)                                                  the query touches the scene box and will be traced
 //   bool finish(const DScene&, uint32_t idx, const Hit& h, AccelState& st)                  true: lane re-armed (st re-initialised)
 template <bool CULL, bool FAST, class Policy>
 __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps) {
@@ -69,7 +70,7 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
                     idx = mine;
                     V3 o, d; float t_far; bool any_hit;
                     if (p.load(sc, idx, o, d, t_far, any_hit)) {
-                        if (accel_init(st, sc, o.x, o.y, o.z, d.x, d.y, d.z, t_far, any_hit)) busy = true;
+                        if (accel_init(st, sc, o.x, o.y, o.z, d.x, d.y, d.z, t_far, any_hit)) { busy = true; p.entered(idx, o, d); }
                         else {
                             Hit miss; miss.t = FLT_MAX; miss.u = 0.0f; miss.v = 0.0f; miss.tri = -1;
                             busy = p.finish(sc, idx, miss, st);
@@ -129,14 +130,17 @@ struct PrimaryPolicy {
             store_hit(hits + i, h);
             return false;
         }
-        float rx, ry; uint2 key;
+        float rx, ry;
         primary_sample(sc, *fp, x, y, fp->sample_first + s, rx, ry, key);
         camera_ray(sc, fp->tan_half_fov, rx, ry, o, d);
-        store_ray(rays + i, o, d, key);
         t_far = FLT_MAX; any_hit = false;
         ++n_rays;
         return true;
     }
+    // the ray is only ever read back by the shading of a HIT (k_shade), so a camera ray that misses the scene box - most of
+    // them on the dragon scenes - is never written to memory
+    uint2 key;
+    __device__ __forceinline__ void entered(uint32_t i, V3 o, V3 d) { store_ray(rays + i, o, d, key); }
     __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, AccelState&) {
         store_hit(hits + i, h);
         n_hits += (h.tri >= 0);
@@ -163,6 +167,7 @@ struct LevelPolicy {
         ++n_rays;
         return true;
     }
+    __device__ __forceinline__ void entered(uint32_t, V3, V3) {}
     __device__ __forceinline__ bool finish(const DScene&, uint32_t i, const Hit& h, AccelState&) {
         store_hit(hits + begin + i, h);
         n_hits += (h.tri >= 0);
@@ -204,6 +209,7 @@ struct ShadowPolicy {
         ro = mk(a.x, a.y, a.z); rd = mk(a.w, b.x, b.y); t_far = b.z; any_hit = !TRANSMISSIVE;
         return true;
     }
+    __device__ __forceinline__ void entered(uint32_t, V3, V3) {}
     // the query's origin, direction and remaining max_t are the traversal state's own (st.o*, st.d*, st.t_far)
     __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, AccelState& st) {
         ++n_q;                                                                                           // :116 one closest-hit query
