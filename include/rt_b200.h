@@ -203,6 +203,13 @@ RT_API int rt_trace_occluded_device(rt_scene* s, const float* d_rays, const floa
 RT_API int rt_render_frame(rt_scene* s, const rt_params* p, float* rgb);
 /* same + the PPM writer's quantisation uint8(255.999*clamp(c,0,1)) (io/image/ppm.hpp:17-19) fused on device.   */
 RT_API int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8);
+/* Frame sequences - what a caller of render_frame in a loop does (the reference's animation outputs, the mp4 under outputs/: one
+ * render_frame per camera pose / parameter set, src/main.cpp:13-25).  rt_render_frame_begin renders the frame into one of two
+ * device frames and queues its download into `rgb` on a copy stream, so frame i's PCIe transfer overlaps frame i+1's render;
+ * rt_frame_wait blocks until `rgb` of that ticket is complete.  `rgb` should be pinned for the overlap to take place and must
+ * stay valid until waited for.  Frames complete in ticket order.                                                   */
+RT_API int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t* ticket);
+RT_API int rt_frame_wait(rt_scene* s, uint64_t ticket);
 /* device framebuffer (for the multi-GPU combine): d_rgb = height*width*3 floats in HBM; asynchronous on stream */
 RT_API int rt_render_frame_device(rt_scene* s, const rt_params* p, float* d_rgb, void* stream);
 /* primary rays only: ray generation + intersect<true> (render.hpp:35-64); hits: one per pixel of the tile,

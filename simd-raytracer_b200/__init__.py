@@ -34,7 +34,8 @@ ABI_SYMBOLS = (
     "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_build_kd_accel", "rt_scene_get_bvh_layout",
     "rt_scene_get_geometry",
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
-    "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_device", "rt_trace_primary", "rt_get_counters",
+    "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_begin", "rt_frame_wait", "rt_render_frame_device", "rt_trace_primary",
+    "rt_get_counters",
     "rt_resolve_sum_device",
     "rt_peer_group_create", "rt_peer_group_connect", "rt_peer_group_connect_local", "rt_peer_framebuffer", "rt_peer_result_rgb",
     "rt_peer_result_rgb8", "rt_peer_combine", "rt_peer_signal_ready", "rt_peer_reduce_resolve", "rt_peer_wait_done",
@@ -142,6 +143,8 @@ def _load():
     L.rt_render_frame.argtypes = [vp, C.POINTER(Params), vp]
     L.rt_render_frame_rgb8.argtypes = [vp, C.POINTER(Params), vp]
     L.rt_render_frame_device.argtypes = [vp, C.POINTER(Params), vp, vp]
+    L.rt_render_frame_begin.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(u64)]
+    L.rt_frame_wait.argtypes = [vp, u64]
     L.rt_trace_primary.argtypes = [vp, C.POINTER(Params), vp]
     L.rt_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.rt_resolve_sum_device.argtypes = [vp, vp, u32, vp, vp, vp]
@@ -379,6 +382,17 @@ class Scene:
         img = out if out is not None else np.zeros((self.height, self.width, 3), np.uint8)
         _check(lib.rt_render_frame_rgb8(self.h, C.byref(p), img.ctypes.data))
         return img
+
+    def render_frame_begin(self, params: Params, out: np.ndarray) -> int:
+        """Frame sequences (rt_render_frame_begin): renders now, downloads into `out` (pinned host memory) behind the next
+        frame's render; returns the ticket for frame_wait."""
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.height, self.width, 3)
+        t = C.c_uint64(0)
+        _check(lib.rt_render_frame_begin(self.h, C.byref(params), out.ctypes.data, C.byref(t)))
+        return int(t.value)
+
+    def frame_wait(self, ticket: int) -> None:
+        _check(lib.rt_frame_wait(self.h, ticket))
 
     def render_frame_device(self, params: Params, d_rgb: int, stream: int | None = None) -> None:
         _check(lib.rt_render_frame_device(self.h, C.byref(params), d_rgb, _stream(stream)))

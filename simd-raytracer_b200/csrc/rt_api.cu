@@ -118,6 +118,11 @@ struct rt_scene {
     double pool_factor = 2.0, shadow_factor = 1.0;
     DBuf<float> fb; DBuf<uint8_t> fb8;
     DBuf<float> q_rays, q_maxt; DBuf<Hit> q_hits; DBuf<uint8_t> q_occ;
+    // frame sequences (rt_render_frame_begin / rt_frame_wait): two device frames, downloads on their own stream
+    DBuf<float> seq_fb[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t seq_rendered = nullptr, seq_copied[2] = {nullptr, nullptr};
+    uint64_t seq_issued = 0;         // tickets handed out so far (ticket t lives in slot t & 1)
 
     // counters of the last frame
     rt_counters counters{};
@@ -125,7 +130,7 @@ struct rt_scene {
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     size_t events_used = 0;
-    cudaEvent_t frame_a = nullptr, frame_b = nullptr;
+    cudaEvent_t frame_a = nullptr, frame_b = nullptr, frame_c = nullptr;   // c: counters of the frame are in h_fc
     bool counters_pending = false;
     uint64_t pool_hwm = 0, shadow_hwm = 0;
     uint32_t launches = 0, passes = 0;
@@ -142,6 +147,10 @@ struct rt_scene {
             cudaSetDevice(device);
             if (stream) cudaStreamSynchronize(stream);
             for (void* p : owned) cudaFree(p);
+            if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+            if (seq_rendered) cudaEventDestroy(seq_rendered);
+            for (cudaEvent_t e : seq_copied) if (e) cudaEventDestroy(e);
+            seq_fb[0].release(); seq_fb[1].release();
             rays.release(); hits.release(); recs.release(); jobs.release(); fb.release(); fb8.release();
             q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
             if (ps) cudaFree(ps);
@@ -151,6 +160,7 @@ struct rt_scene {
             for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
             if (frame_a) cudaEventDestroy(frame_a);
             if (frame_b) cudaEventDestroy(frame_b);
+            if (frame_c) cudaEventDestroy(frame_c);
             if (stream) cudaStreamDestroy(stream);
         }
     }
@@ -231,6 +241,7 @@ void upload_scene(rt_scene* s) {
     CK(cudaMallocHost(&s->h_fc, sizeof(FrameCounters)));
     CK(cudaEventCreate(&s->frame_a));
     CK(cudaEventCreate(&s->frame_b));
+    CK(cudaEventCreateWithFlags(&s->frame_c, cudaEventDisableTiming));
     CK(cudaDeviceSynchronize());
     s->info.device_bytes = bytes;
     s->info.upload_seconds = now_s() - t0;
@@ -581,6 +592,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     if (s->levels_hint == 0 || levels_seen > s->levels_hint) s->levels_hint = std::max<uint32_t>(levels_seen, 1);
     CK(cudaEventRecord(s->frame_b, st));
     CK(cudaMemcpyAsync(s->h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s->frame_c, st));
     s->counters_pending = true;
 }
 
@@ -814,6 +826,51 @@ int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8) {
     });
 }
 
+int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t* ticket) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !rgb || !ticket) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        if (!s->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->seq_rendered, cudaEventDisableTiming));
+            for (cudaEvent_t& e : s->seq_copied) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const int slot = int(s->seq_issued & 1);
+        const size_t n = size_t(s->host.width) * s->host.height * 3;
+        s->seq_fb[slot].reserve(n);
+        const Rect r = rect_of(s, *p);
+        // the download of the frame that used this slot two tickets ago must have left the device frame
+        if (s->seq_issued >= 2) CK(cudaStreamWaitEvent(s->stream, s->seq_copied[slot], 0));
+        render_device(s, *p, s->seq_fb[slot].p, s->stream);
+        CK(cudaEventRecord(s->seq_rendered, s->stream));
+        CK(cudaStreamWaitEvent(s->copy_stream, s->seq_rendered, 0));
+        const size_t at = (size_t(r.y0) * s->host.width + r.x0) * 3;
+        CK(cudaMemcpy2DAsync(rgb + at, size_t(s->host.width) * 12, s->seq_fb[slot].p + at, size_t(s->host.width) * 12,
+                             size_t(r.x1 - r.x0) * 12, r.y1 - r.y0, cudaMemcpyDeviceToHost, s->copy_stream));
+        CK(cudaEventRecord(s->seq_copied[slot], s->copy_stream));
+        *ticket = s->seq_issued++;
+        return int(RT_OK);
+    });
+}
+
+int rt_frame_wait(rt_scene* s, uint64_t ticket) {
+    return guarded([&] {
+        require_device(s);
+        cudaEvent_t e = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(s->mtx);
+            if (ticket >= s->seq_issued) throw rt_error(RT_ERR_BAD_ARG, "no such frame ticket");
+            // downloads complete in ticket order on one stream, so the event of the slot's latest download covers this ticket
+            e = s->seq_copied[ticket & 1];
+        }
+        CK(cudaSetDevice(s->device));
+        CK(cudaEventSynchronize(e));
+        return int(RT_OK);
+    });
+}
+
 int rt_trace_primary(rt_scene* s, const rt_params* p, rt_hit* hits) {
     return guarded([&] {
         require_device(s);
@@ -843,8 +900,7 @@ int rt_get_counters(rt_scene* s, rt_counters* c) {
         if (!c) throw rt_error(RT_ERR_BAD_ARG, "null argument");
         if (s->counters_pending) {
             CK(cudaSetDevice(s->device));
-            CK(cudaEventSynchronize(s->frame_b));
-            CK(cudaDeviceSynchronize());
+            CK(cudaEventSynchronize(s->frame_c));      // not a device-wide sync: a frame download may be in flight on the copy stream
             rt_counters k{};
             k.primary = s->h_fc->primary; k.primary_hits = s->h_fc->primary_hits;
             k.shadow = s->h_fc->shadow; k.shadow_hits = s->h_fc->shadow_hits;

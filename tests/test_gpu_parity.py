@@ -400,6 +400,45 @@ def test_empty_level_skipping_never_changes_a_frame(rt):
     warm.close()
 
 
+def test_frame_sequence_equals_single_frames(rt):
+    """rt_render_frame_begin / rt_frame_wait (a caller looping over render_frame, src/main.cpp:13-25): frame i's download runs
+    behind frame i+1's render from one of two device frames.  Every frame of a sequence whose parameters change from frame to
+    frame (recursion depth, tile, sample slice, query mode) must equal the frame rt_render_frame returns, bit for bit, also when
+    tickets are waited for late or out of order; untouched pixels of a tile frame stay untouched."""
+    torch = pytest.importorskip("torch")
+    s, _ = gpu_scene(rt, "hw15_scene2", size=(160, 120))
+    seq = [rt.default_params(max_ray_depth=d, flags=f, x0=x0, y0=y0, x1=x1, y1=y1, samples_per_pixel=1, sample_offset=so, spp_total=st)
+           for d, f, (x0, y0, x1, y1), so, st in [(5, 0, (0, 0, 0, 0), 0, 1), (2, rt.FLAG_ORDERED, (0, 0, 0, 0), 0, 1),
+                                                  (5, rt.FLAG_ORDERED, (16, 8, 120, 100), 0, 1), (3, 0, (0, 0, 0, 0), 3, 8),
+                                                  (5, rt.FLAG_ORDERED, (0, 0, 0, 0), 0, 1), (1, 0, (40, 0, 160, 60), 0, 1),
+                                                  (5, rt.FLAG_ORDERED | rt.FLAG_RAW_SUM, (0, 0, 0, 0), 5, 8)]]
+    want = [s.render_frame(p, out=np.full((120, 160, 3), -7.0, np.float32)) for p in seq]
+    bufs = [torch.full((120, 160, 3), -7.0, dtype=torch.float32).pin_memory().numpy() for _ in seq]
+    # (a) the steady-state pattern: begin i+1, then wait i
+    prev = None
+    for p, b in zip(seq, bufs):
+        t = s.render_frame_begin(p, b)
+        if prev is not None:
+            s.frame_wait(prev)
+        prev = t
+    s.frame_wait(prev)
+    for i, (b, w) in enumerate(zip(bufs, want)):
+        assert np.array_equal(b.view(np.uint32), w.view(np.uint32)), i
+    # (b) all frames in flight before the first wait, waits in reverse order
+    for b in bufs:
+        b.fill(-7.0)
+    tickets = [s.render_frame_begin(p, b) for p, b in zip(seq, bufs)]
+    assert tickets == list(range(tickets[0], tickets[0] + len(seq)))
+    for t in reversed(tickets):
+        s.frame_wait(t)
+    for i, (b, w) in enumerate(zip(bufs, want)):
+        assert np.array_equal(b.view(np.uint32), w.view(np.uint32)), i
+    with pytest.raises(rt.RtError):
+        s.frame_wait(tickets[-1] + 1)
+    # the synchronous entry points still work between sequences
+    assert np.array_equal(s.render_frame(seq[0]).view(np.uint32), want[0].view(np.uint32))
+
+
 # ---- device-pointer entry points, threading ----------------------------------------------------------------------------------------
 def test_device_pointer_api_with_torch(rt, oracle_mod):
     torch = pytest.importorskip("torch")
