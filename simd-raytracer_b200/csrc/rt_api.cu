@@ -118,10 +118,20 @@ struct rt_scene {
     double pool_factor = 2.0, shadow_factor = 1.0;
     DBuf<float> fb; DBuf<uint8_t> fb8;
     DBuf<float> q_rays, q_maxt; DBuf<Hit> q_hits; DBuf<uint8_t> q_occ;
-    // frame sequences (rt_render_frame_begin / rt_frame_wait): two device frames, downloads on their own stream
-    DBuf<float> seq_fb[2];
+    // frame sequences (rt_render_frame_begin / rt_frame_wait): two frames in flight, each with its own device frame, its own
+    // pinned completion words and counters; downloads run on their own stream
+    struct SeqSlot {
+        DBuf<float> fb;
+        cudaEvent_t rendered = nullptr, copied = nullptr, a = nullptr, b = nullptr;
+        uint32_t* h_flags = nullptr;     // pinned: what k_pass_commit published for this frame
+        FrameCounters* h_fc = nullptr;   // pinned
+        bool in_flight = false, deferred = false, used = false;
+        rt_params params{}, key{};
+        float* host_rgb = nullptr;
+        uint64_t n0 = 0;
+        uint32_t launches = 0;
+    } seq[2];
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t seq_rendered = nullptr, seq_copied[2] = {nullptr, nullptr};
     uint64_t seq_issued = 0;         // tickets handed out so far (ticket t lives in slot t & 1)
 
     // counters of the last frame
@@ -148,9 +158,12 @@ struct rt_scene {
             if (stream) cudaStreamSynchronize(stream);
             for (void* p : owned) cudaFree(p);
             if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
-            if (seq_rendered) cudaEventDestroy(seq_rendered);
-            for (cudaEvent_t e : seq_copied) if (e) cudaEventDestroy(e);
-            seq_fb[0].release(); seq_fb[1].release();
+            for (SeqSlot& q : seq) {
+                for (cudaEvent_t e : {q.rendered, q.copied, q.a, q.b}) if (e) cudaEventDestroy(e);
+                if (q.h_flags) cudaFreeHost(q.h_flags);
+                if (q.h_fc) cudaFreeHost(q.h_fc);
+                q.fb.release();
+            }
             rays.release(); hits.release(); recs.release(); jobs.release(); fb.release(); fb8.release();
             q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
             if (ps) cudaFree(ps);
@@ -435,8 +448,160 @@ uint32_t level_count(const rt_scene* s, const rt_params& p) {
 
 constexpr uint64_t PRIMARY_BUDGET = 1ull << 23;     // level-0 entries per pass
 
+// persistent grid sizes of the kernels a frame in this mode launches (occupancy queries, once per scene)
+void ensure_grids(rt_scene* s, Mode m, bool has_gi) {
+    const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0), fi = m.fast ? 1 : 0;
+    const bool tr = s->d.has_transmissive != 0;
+    if (!s->g_resolve) s->g_resolve = grid_for(s, k_resolve<false>);
+    if (!s->g_shade[has_gi]) s->g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
+    if (m.ordered) {
+        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>) : grid_for(s, k_stream_primary<false>);
+        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>) : grid_for(s, k_stream_level<false>);
+        if (!s->gs_shadow[fi * 2 + tr])
+            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>) : grid_for(s, k_stream_shadow<true, false>))
+                                           : (m.fast ? grid_for(s, k_stream_shadow<false, true>) : grid_for(s, k_stream_shadow<false, false>));
+    } else {
+        if (!s->g_primary[mi]) s->g_primary[mi] = m.fast ? grid_for(s, k_primary<true, false>) : grid_for(s, k_primary<false, false>);
+        if (!s->g_trace[mi]) s->g_trace[mi] = m.fast ? grid_for(s, k_trace_level<true, false>) : grid_for(s, k_trace_level<false, false>);
+        if (!s->g_shadow[mi * 2 + tr])
+            s->g_shadow[mi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_shadow<true, true, false>) : grid_for(s, k_shadow<true, false, false>))
+                                          : (m.fast ? grid_for(s, k_shadow<false, true, false>) : grid_for(s, k_shadow<false, false, false>));
+    }
+}
+
+// One pass = `fp.n_samples` samples of every pixel of the tile through the whole wavefront.
+struct PassLaunch {
+    FrameParams fp;
+    Mode m;
+    uint32_t levels, launched;        // levels the frame can reach / levels traced and shaded in this pass
+    bool has_gi;
+    int first_pass, divide;           // framebuffer: overwrite instead of add / divide by spp_total after adding
+};
+
+// Queues the kernels of one pass on `st` (nothing here waits for the device).  launch(class, f) issues f() - the synchronous
+// path wraps every launch in a pair of timing events, the frame-sequence path does not.  k_pass_commit publishes pool usage,
+// the overflow bits and the level count of the pass to `h_flags` (pinned host memory, 4 words).
+template <class Launch>
+void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_flags, cudaStream_t st, Launch&& launch) {
+    const FrameParams& fp = P.fp;
+    const Mode m = P.m;
+    const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0), fi = m.fast ? 1 : 0;
+    const bool tr = s->d.has_transmissive != 0, has_gi = P.has_gi;
+    const uint32_t launched = P.launched, levels = P.levels;
+    const uint32_t n0 = fp.plane * fp.n_samples;
+    int slot = 0;
+    k_pass_init<<<1, 256, 0, st>>>(s->ps, n0);
+    CK(cudaGetLastError());
+    launch(TC_PRIMARY, [&] {
+        if (m.ordered) {
+            if (m.fast) k_stream_primary<true><<<s->gs_primary[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            else k_stream_primary<false><<<s->gs_primary[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+        } else if (m.fast) k_primary<true, false><<<s->g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+        else k_primary<false, false><<<s->g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+    });
+    ++slot;
+    for (uint32_t lvl = 0; lvl < launched; ++lvl) {
+        if (lvl > 0) {
+            launch(TC_SECONDARY, [&] {
+                if (m.ordered) {
+                    if (m.fast) k_stream_level<true><<<s->gs_level[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    else k_stream_level<false><<<s->gs_level[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                } else if (m.fast) k_trace_level<true, false><<<s->g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                else k_trace_level<false, false><<<s->g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+            });
+            ++slot;
+        }
+        launch(TC_SHADE, [&] {
+            if (has_gi) k_shade<true><<<s->g_shade[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
+            else k_shade<false><<<s->g_shade[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
+        });
+        ++slot;
+    }
+    if (!s->host.lights.empty()) {
+        launch(TC_SHADOW, [&] {
+            if (m.ordered) {
+                const int g = s->gs_shadow[fi * 2 + tr];
+                if (tr) { if (m.fast) k_stream_shadow<true, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                          else k_stream_shadow<true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                else { if (m.fast) k_stream_shadow<false, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                       else k_stream_shadow<false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+            } else {
+                const int g = s->g_shadow[mi * 2 + tr];
+                if (tr) { if (m.fast) k_shadow<true, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                          else k_shadow<true, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                else { if (m.fast) k_shadow<false, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
+                       else k_shadow<false, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+            }
+        });
+        ++slot;
+    }
+    const bool fuse_acc = fp.n_samples == 1;          // one sample in the pass: level 0 resolves straight into the framebuffer
+    for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
+        launch(TC_RESOLVE, [&] {
+            if (lvl == 0 && fuse_acc)
+                k_resolve<true><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
+                                                              launched, levels);
+            else
+                k_resolve<false><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels);
+        });
+        ++slot;
+    }
+    k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, h_flags, launched, levels);
+    CK(cudaGetLastError());
+    // the accumulate kernel skips itself on the device when the pass overflowed its pools
+    if (!fuse_acc)
+        launch(TC_RESOLVE, [&] {
+            k_accumulate<<<(fp.plane + 255) / 256, 256, 0, st>>>(s->d, fp, s->recs.p, d_rgb, s->ps, P.first_pass, P.divide);
+        });
+}
+
+// wavefront pools for a pass of n0 level-0 entries, sized from the factors learnt so far; fills fp.pool_cap / fp.shadow_cap
+void reserve_pools(rt_scene* s, FrameParams& fp, uint64_t n0, uint32_t levels) {
+    const uint64_t pool_cap = std::max<uint64_t>(uint64_t(double(n0) * (levels > 1 ? s->pool_factor : 1.0)) + 1024, n0);
+    const uint64_t shadow_cap = uint64_t(double(n0) * s->shadow_factor * std::max<size_t>(s->host.lights.size(), 1)) + 1024;
+    if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
+    s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
+    fp.pool_cap = uint32_t(std::min<uint64_t>(s->rays.cap, 0xFFFFFFFFull));
+    fp.shadow_cap = uint32_t(std::min<uint64_t>(s->jobs.cap, 0xFFFFFFFFull));
+}
+
+// a truncated pass reports lower bounds of what it needed: grow past them (the pass is deterministic and is rendered again)
+void grow_pools_after_overflow(rt_scene* s, const uint32_t* flags, uint64_t n0) {
+    const uint64_t used_pool = flags[0], used_shadow = flags[1];
+    if (flags[2] & 4u) s->levels_hint = 0;              // a skipped level was needed: all levels from now on
+    if (flags[2] & 1u) s->pool_factor = std::max(s->pool_factor * 1.5, double(used_pool) / double(n0) * 1.25);
+    if (flags[2] & 2u)
+        s->shadow_factor = std::max(s->shadow_factor * 1.5, double(used_shadow) / double(n0 * std::max<size_t>(s->host.lights.size(), 1)) * 1.25);
+}
+
+void drain_sequence(rt_scene* s);
+
+// counters of the last synchronously rendered frame: waits for it, reads the per-class CUDA events
+void fetch_counters(rt_scene* s) {
+    if (!s->counters_pending) return;
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->frame_c));      // not a device-wide sync: a frame download may be in flight on the copy stream
+    rt_counters k{};
+    k.primary = s->h_fc->primary; k.primary_hits = s->h_fc->primary_hits;
+    k.shadow = s->h_fc->shadow; k.shadow_hits = s->h_fc->shadow_hits;
+    k.secondary = s->h_fc->secondary; k.secondary_hits = s->h_fc->secondary_hits;
+    k.nodes_pool = s->pool_hwm; k.shadow_pool = s->shadow_hwm;
+    k.kernel_launches = s->launches; k.passes = s->passes;
+    CK(cudaEventElapsedTime(&k.ms_total, s->frame_a, s->frame_b));
+    float by_class[TC_N] = {0, 0, 0, 0, 0};
+    for (const auto& sp : s->spans) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        by_class[sp.cls] += ms;
+    }
+    k.ms_primary = by_class[TC_PRIMARY]; k.ms_secondary = by_class[TC_SECONDARY]; k.ms_shadow = by_class[TC_SHADOW];
+    k.ms_shade = by_class[TC_SHADE]; k.ms_resolve = by_class[TC_RESOLVE];
+    s->counters = k;
+    s->counters_pending = false;
+}
+
 // One frame (or tile / sample slice of one) into a device framebuffer of height*width*3 floats.
-void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t st) {
+void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t st, bool drain = true) {
     check_params(p);
     const Rect rect = rect_of(s, p);
     FrameParams fp = frame_params(s, p, rect);
@@ -445,8 +610,9 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     const uint32_t levels = level_count(s, p);
     const bool raw = (p.flags & RT_FLAG_RAW_SUM) != 0;
 
+    if (drain) drain_sequence(s);                 // frames of a sequence still in flight use the same pools
     // finish the bookkeeping of the previous frame before its events are reused
-    if (s->counters_pending) { rt_counters c; rt_get_counters(s, &c); }
+    fetch_counters(s);
     s->events_used = 0; s->spans.clear();
     s->launches = 0; s->passes = 0; s->pool_hwm = 0; s->shadow_hwm = 0;
     CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
@@ -463,27 +629,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
         s->spans.push_back(sp);
         ++s->launches;
     };
-
-    int (&g_primary)[4] = s->g_primary, (&g_trace)[4] = s->g_trace, (&g_shadow)[8] = s->g_shadow, (&g_shade)[2] = s->g_shade;
-    int& g_resolve = s->g_resolve;                                                   // persistent grid sizes
-    const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0);
-    const bool tr = s->d.has_transmissive != 0;
-    if (!g_resolve) g_resolve = grid_for(s, k_resolve<false>);
-    if (!g_shade[has_gi]) g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
-    const int fi = m.fast ? 1 : 0;
-    if (m.ordered) {
-        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>) : grid_for(s, k_stream_primary<false>);
-        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>) : grid_for(s, k_stream_level<false>);
-        if (!s->gs_shadow[fi * 2 + tr])
-            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>) : grid_for(s, k_stream_shadow<true, false>))
-                                           : (m.fast ? grid_for(s, k_stream_shadow<false, true>) : grid_for(s, k_stream_shadow<false, false>));
-    } else {
-        if (!g_primary[mi]) g_primary[mi] = m.fast ? grid_for(s, k_primary<true, false>) : grid_for(s, k_primary<false, false>);
-        if (!g_trace[mi]) g_trace[mi] = m.fast ? grid_for(s, k_trace_level<true, false>) : grid_for(s, k_trace_level<false, false>);
-        if (!g_shadow[mi * 2 + tr])
-            g_shadow[mi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_shadow<true, true, false>) : grid_for(s, k_shadow<true, false, false>))
-                                       : (m.fast ? grid_for(s, k_shadow<false, true, false>) : grid_for(s, k_shadow<false, false, false>));
-    }
+    ensure_grids(s, m, has_gi);
 
     // same frame parameters as the last frame: launch only the levels that held rays then (checked on device, see k_pass_commit)
     rt_params key = p;
@@ -498,93 +644,19 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
         fp.sample_first = p.sample_offset + done;
         const uint64_t n0 = uint64_t(fp.plane) * ns;
         for (int attempt = 0;; ++attempt) {
-            const uint64_t pool_cap = std::max<uint64_t>(uint64_t(double(n0) * (levels > 1 ? s->pool_factor : 1.0)) + 1024, n0);
-            const uint64_t shadow_cap = uint64_t(double(n0) * s->shadow_factor * std::max<size_t>(s->host.lights.size(), 1)) + 1024;
-            if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
-            s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
-            fp.pool_cap = uint32_t(std::min<uint64_t>(s->rays.cap, 0xFFFFFFFFull));
-            fp.shadow_cap = uint32_t(std::min<uint64_t>(s->jobs.cap, 0xFFFFFFFFull));
-
-            const uint32_t launched = s->levels_hint ? std::min(levels, s->levels_hint) : levels;
-            int slot = 0;
-            k_pass_init<<<1, 256, 0, st>>>(s->ps, uint32_t(n0));
-            CK(cudaGetLastError());
-            timed(TC_PRIMARY, [&] {
-                if (m.ordered) {
-                    if (m.fast) k_stream_primary<true><<<s->gs_primary[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-                    else k_stream_primary<false><<<s->gs_primary[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-                } else if (m.fast) k_primary<true, false><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-                else k_primary<false, false><<<g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-            });
-            ++slot;
-            for (uint32_t lvl = 0; lvl < launched; ++lvl) {
-                if (lvl > 0) {
-                    timed(TC_SECONDARY, [&] {
-                        if (m.ordered) {
-                            if (m.fast) k_stream_level<true><<<s->gs_level[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                            else k_stream_level<false><<<s->gs_level[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                        } else if (m.fast) k_trace_level<true, false><<<g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                        else k_trace_level<false, false><<<g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                    });
-                    ++slot;
-                }
-                timed(TC_SHADE, [&] {
-                    if (has_gi) k_shade<true><<<g_shade[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
-                    else k_shade<false><<<g_shade[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
-                });
-                ++slot;
-            }
-            if (!s->host.lights.empty()) {
-                timed(TC_SHADOW, [&] {
-                    if (m.ordered) {
-                        const int g = s->gs_shadow[fi * 2 + tr];
-                        if (tr) { if (m.fast) k_stream_shadow<true, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                                  else k_stream_shadow<true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
-                        else { if (m.fast) k_stream_shadow<false, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                               else k_stream_shadow<false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
-                    } else {
-                        const int g = g_shadow[mi * 2 + tr];
-                        if (tr) { if (m.fast) k_shadow<true, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                                  else k_shadow<true, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
-                        else { if (m.fast) k_shadow<false, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                               else k_shadow<false, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
-                    }
-                });
-                ++slot;
-            }
-            const bool fuse_acc = ns == 1;          // one sample in the pass: level 0 resolves straight into the framebuffer
-            const int first_pass = done == 0 ? 1 : 0, divide = (!raw && done + ns == spp) ? 1 : 0;
-            for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
-                timed(TC_RESOLVE, [&] {
-                    if (lvl == 0 && fuse_acc)
-                        k_resolve<true><<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, first_pass, divide,
-                                                                   launched, levels);
-                    else
-                        k_resolve<false><<<g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels);
-                });
-                ++slot;
-            }
-            k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, s->h_flags, launched, levels);
-            CK(cudaGetLastError());
-            // the accumulate kernel skips itself on the device when the pass overflowed its pools
-            if (!fuse_acc)
-                timed(TC_RESOLVE, [&] {
-                    k_accumulate<<<(fp.plane + 255) / 256, 256, 0, st>>>(s->d, fp, s->recs.p, d_rgb, s->ps, first_pass, divide);
-                });
+            reserve_pools(s, fp, n0, levels);
+            PassLaunch P{fp, m, levels, s->levels_hint ? std::min(levels, s->levels_hint) : levels, has_gi,
+                         done == 0 ? 1 : 0, (!raw && done + ns == spp) ? 1 : 0};
+            enqueue_pass(s, P, d_rgb, s->h_flags, st, timed);
             CK(cudaStreamSynchronize(st));
-            const uint64_t used_pool = s->h_flags[0], used_shadow = s->h_flags[1];
             if (s->h_flags[2] == 0) {
-                s->pool_hwm = std::max(s->pool_hwm, used_pool);
-                s->shadow_hwm = std::max(s->shadow_hwm, used_shadow);
+                s->pool_hwm = std::max<uint64_t>(s->pool_hwm, s->h_flags[0]);
+                s->shadow_hwm = std::max<uint64_t>(s->shadow_hwm, s->h_flags[1]);
                 levels_seen = std::max(levels_seen, s->h_flags[3]);
                 break;
             }
-            if (s->h_flags[2] & 4u) s->levels_hint = 0;              // a skipped level was needed: all levels from now on
             if (attempt >= 24) throw rt_error(RT_ERR_OOM, "wavefront pools keep overflowing");
-            // the counts of a truncated pass are lower bounds: grow past them and render the pass again (it is deterministic)
-            if (s->h_flags[2] & 1u) s->pool_factor = std::max(s->pool_factor * 1.5, double(used_pool) / double(n0) * 1.25);
-            if (s->h_flags[2] & 2u)
-                s->shadow_factor = std::max(s->shadow_factor * 1.5, double(used_shadow) / double(n0 * std::max<size_t>(s->host.lights.size(), 1)) * 1.25);
+            grow_pools_after_overflow(s, s->h_flags, n0);
         }
         done += ns;
         ++s->passes;
@@ -594,6 +666,112 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     CK(cudaMemcpyAsync(s->h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s->frame_c, st));
     s->counters_pending = true;
+}
+
+// ---- frame sequences ------------------------------------------------------------------------------------------------------
+// A frame of a sequence is queued without waiting for the device: kernels of frame i+1 are already in the stream while frame
+// i runs, and the download of frame i (copy stream) overlaps frame i+1.  What the synchronous path learns at its end-of-pass
+// sync - did the pools overflow, which levels held rays - is read when the frame is waited for; an overflowed frame is then
+// rendered again through the synchronous path (deterministic, so the caller sees the same frame, later).
+
+void copy_rect_to_host(rt_scene* s, const Rect& r, const float* d_rgb, float* rgb, cudaStream_t st) {
+    const size_t at = (size_t(r.y0) * s->host.width + r.x0) * 3;
+    CK(cudaMemcpy2DAsync(rgb + at, size_t(s->host.width) * 12, d_rgb + at, size_t(s->host.width) * 12, size_t(r.x1 - r.x0) * 12,
+                         r.y1 - r.y0, cudaMemcpyDeviceToHost, st));
+}
+
+void finalize_slot(rt_scene* s, int k) {
+    rt_scene::SeqSlot& q = s->seq[k];
+    if (!q.in_flight) return;
+    CK(cudaEventSynchronize(q.copied));
+    q.in_flight = false;
+    if (!q.deferred) return;                                   // rendered by the synchronous path: nothing left to check
+    if (q.h_flags[2] != 0) {
+        grow_pools_after_overflow(s, q.h_flags, q.n0);
+        CK(cudaStreamSynchronize(s->stream));                  // the other frame in flight uses the pools that are about to grow
+        render_device(s, q.params, q.fb.p, s->stream, false);
+        copy_rect_to_host(s, rect_of(s, q.params), q.fb.p, q.host_rgb, s->stream);
+        CK(cudaStreamSynchronize(s->stream));
+        return;
+    }
+    s->pool_hwm = q.h_flags[0]; s->shadow_hwm = q.h_flags[1];
+    if (std::memcmp(&q.key, &s->hint_params, sizeof q.key) == 0 && (s->levels_hint == 0 || q.h_flags[3] > s->levels_hint))
+        s->levels_hint = std::max<uint32_t>(q.h_flags[3], 1);
+    rt_counters c{};
+    c.primary = q.h_fc->primary; c.primary_hits = q.h_fc->primary_hits;
+    c.shadow = q.h_fc->shadow; c.shadow_hits = q.h_fc->shadow_hits;
+    c.secondary = q.h_fc->secondary; c.secondary_hits = q.h_fc->secondary_hits;
+    c.nodes_pool = s->pool_hwm; c.shadow_pool = s->shadow_hwm;
+    c.kernel_launches = q.launches; c.passes = 1;
+    CK(cudaEventElapsedTime(&c.ms_total, q.a, q.b));           // no per-class events inside a queued frame
+    s->counters = c;
+    s->counters_pending = false;
+}
+
+void drain_sequence(rt_scene* s) {
+    if (!s->seq[0].in_flight && !s->seq[1].in_flight) return;
+    const int older = int(s->seq_issued & 1);                  // the slot the next ticket would take holds the older frame
+    finalize_slot(s, older);
+    finalize_slot(s, older ^ 1);
+}
+
+void begin_frame(rt_scene* s, const rt_params& p, float* rgb, uint64_t* ticket) {
+    check_params(p);
+    const Rect rect = rect_of(s, p);
+    if (!s->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (rt_scene::SeqSlot& q : s->seq) {
+            CK(cudaEventCreateWithFlags(&q.rendered, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
+            CK(cudaEventCreate(&q.a));
+            CK(cudaEventCreate(&q.b));
+            CK(cudaMallocHost(&q.h_flags, 4 * sizeof(uint32_t)));
+            CK(cudaMallocHost(&q.h_fc, sizeof(FrameCounters)));
+        }
+    }
+    const int k = int(s->seq_issued & 1);
+    rt_scene::SeqSlot& q = s->seq[k];
+    finalize_slot(s, k);                                       // the frame two tickets back (normally long complete)
+    q.fb.reserve(size_t(s->host.width) * s->host.height * 3);
+    cudaStream_t st = s->stream;
+
+    FrameParams fp = frame_params(s, p, rect);
+    const uint32_t spp = p.samples_per_pixel;
+    const bool one_pass = uint64_t(spp) * fp.plane <= PRIMARY_BUDGET;
+    if (!one_pass) {
+        // several passes re-use the pools and need the pass-by-pass overflow check: synchronous render, overlapped download
+        render_device(s, p, q.fb.p, st);
+        q.deferred = false;
+    } else {
+        fetch_counters(s);
+        const Mode m = mode_of(p.flags);
+        const bool has_gi = fp.gi_rays > 0;
+        const uint32_t levels = level_count(s, p);
+        ensure_grids(s, m, has_gi);
+        rt_params key = p;
+        key.sample_offset = 0; key.samples_per_pixel = 0;
+        if (std::memcmp(&key, &s->hint_params, sizeof key) != 0) { s->levels_hint = 0; s->hint_params = key; }
+        fp.n_samples = spp;
+        fp.sample_first = p.sample_offset;
+        const uint64_t n0 = uint64_t(fp.plane) * spp;
+        reserve_pools(s, fp, n0, levels);
+        PassLaunch P{fp, m, levels, s->levels_hint ? std::min(levels, s->levels_hint) : levels, has_gi, 1,
+                     (p.flags & RT_FLAG_RAW_SUM) ? 0 : 1};
+        uint32_t launches = 0;
+        if (q.used) CK(cudaStreamWaitEvent(st, q.copied, 0));   // the device frame of this slot has been downloaded
+        CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
+        CK(cudaEventRecord(q.a, st));
+        enqueue_pass(s, P, q.fb.p, q.h_flags, st, [&](int, auto&& launch) { launch(); CK(cudaGetLastError()); ++launches; });
+        CK(cudaEventRecord(q.b, st));
+        CK(cudaMemcpyAsync(q.h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+        q.deferred = true; q.params = p; q.key = key; q.n0 = n0; q.launches = launches;
+    }
+    CK(cudaEventRecord(q.rendered, st));
+    CK(cudaStreamWaitEvent(s->copy_stream, q.rendered, 0));
+    copy_rect_to_host(s, rect, q.fb.p, rgb, s->copy_stream);
+    CK(cudaEventRecord(q.copied, s->copy_stream));
+    q.host_rgb = rgb; q.in_flight = true; q.used = true;
+    *ticket = s->seq_issued++;
 }
 
 }  // namespace
@@ -832,25 +1010,7 @@ int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t*
         if (!p || !rgb || !ticket) throw rt_error(RT_ERR_BAD_ARG, "null argument");
         std::lock_guard<std::mutex> lock(s->mtx);
         CK(cudaSetDevice(s->device));
-        if (!s->copy_stream) {
-            CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&s->seq_rendered, cudaEventDisableTiming));
-            for (cudaEvent_t& e : s->seq_copied) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-        const int slot = int(s->seq_issued & 1);
-        const size_t n = size_t(s->host.width) * s->host.height * 3;
-        s->seq_fb[slot].reserve(n);
-        const Rect r = rect_of(s, *p);
-        // the download of the frame that used this slot two tickets ago must have left the device frame
-        if (s->seq_issued >= 2) CK(cudaStreamWaitEvent(s->stream, s->seq_copied[slot], 0));
-        render_device(s, *p, s->seq_fb[slot].p, s->stream);
-        CK(cudaEventRecord(s->seq_rendered, s->stream));
-        CK(cudaStreamWaitEvent(s->copy_stream, s->seq_rendered, 0));
-        const size_t at = (size_t(r.y0) * s->host.width + r.x0) * 3;
-        CK(cudaMemcpy2DAsync(rgb + at, size_t(s->host.width) * 12, s->seq_fb[slot].p + at, size_t(s->host.width) * 12,
-                             size_t(r.x1 - r.x0) * 12, r.y1 - r.y0, cudaMemcpyDeviceToHost, s->copy_stream));
-        CK(cudaEventRecord(s->seq_copied[slot], s->copy_stream));
-        *ticket = s->seq_issued++;
+        begin_frame(s, *p, rgb, ticket);
         return int(RT_OK);
     });
 }
@@ -858,15 +1018,12 @@ int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t*
 int rt_frame_wait(rt_scene* s, uint64_t ticket) {
     return guarded([&] {
         require_device(s);
-        cudaEvent_t e = nullptr;
-        {
-            std::lock_guard<std::mutex> lock(s->mtx);
-            if (ticket >= s->seq_issued) throw rt_error(RT_ERR_BAD_ARG, "no such frame ticket");
-            // downloads complete in ticket order on one stream, so the event of the slot's latest download covers this ticket
-            e = s->seq_copied[ticket & 1];
-        }
+        std::lock_guard<std::mutex> lock(s->mtx);
+        if (ticket >= s->seq_issued) throw rt_error(RT_ERR_BAD_ARG, "no such frame ticket");
         CK(cudaSetDevice(s->device));
-        CK(cudaEventSynchronize(e));
+        // frames complete in ticket order; a ticket older than the two newest was finished when its slot was re-used
+        if (ticket + 2 == s->seq_issued) finalize_slot(s, int(ticket & 1));
+        else if (ticket + 1 == s->seq_issued) { finalize_slot(s, int((ticket & 1) ^ 1)); finalize_slot(s, int(ticket & 1)); }
         return int(RT_OK);
     });
 }
@@ -898,27 +1055,12 @@ int rt_get_counters(rt_scene* s, rt_counters* c) {
     return guarded([&] {
         require_device(s);
         if (!c) throw rt_error(RT_ERR_BAD_ARG, "null argument");
-        if (s->counters_pending) {
+        {
+            std::lock_guard<std::mutex> lock(s->mtx);
             CK(cudaSetDevice(s->device));
-            CK(cudaEventSynchronize(s->frame_c));      // not a device-wide sync: a frame download may be in flight on the copy stream
-            rt_counters k{};
-            k.primary = s->h_fc->primary; k.primary_hits = s->h_fc->primary_hits;
-            k.shadow = s->h_fc->shadow; k.shadow_hits = s->h_fc->shadow_hits;
-            k.secondary = s->h_fc->secondary; k.secondary_hits = s->h_fc->secondary_hits;
-            k.nodes_pool = s->pool_hwm; k.shadow_pool = s->shadow_hwm;
-            k.kernel_launches = s->launches; k.passes = s->passes;
-            CK(cudaEventElapsedTime(&k.ms_total, s->frame_a, s->frame_b));
-            float by_class[TC_N] = {0, 0, 0, 0, 0};
-            for (const auto& sp : s->spans) {
-                float ms = 0;
-                CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
-                by_class[sp.cls] += ms;
-            }
-            k.ms_primary = by_class[TC_PRIMARY]; k.ms_secondary = by_class[TC_SECONDARY]; k.ms_shadow = by_class[TC_SHADOW];
-            k.ms_shade = by_class[TC_SHADE]; k.ms_resolve = by_class[TC_RESOLVE];
-            s->counters = k;
-            s->counters_pending = false;
+            drain_sequence(s);
         }
+        fetch_counters(s);
         *c = s->counters;
         return int(RT_OK);
     });

@@ -439,6 +439,34 @@ def test_frame_sequence_equals_single_frames(rt):
     assert np.array_equal(s.render_frame(seq[0]).view(np.uint32), want[0].view(np.uint32))
 
 
+def test_frame_sequence_on_a_fresh_scene_outgrows_its_pools(rt):
+    """Frames of a sequence are queued without waiting for the device, so a pool overflow (here: the first frames of a fresh
+    scene whose refractive dragon spawns far more secondary queries than the initial pool factor allows, depth 10) is only seen
+    when the frame is waited for; it is then rendered again.  The caller must get the same frames and counters either way."""
+    torch = pytest.importorskip("torch")
+    data = resized(scene_bytes("hw11_scene8"), 192, 108)
+    ref = rt.Scene.from_rtsc(data)
+    ps = [rt.default_params(max_ray_depth=10, flags=f) for f in (rt.FLAG_ORDERED, 0, rt.FLAG_ORDERED)]
+    want = [ref.render_frame(p) for p in ps]
+    cw = ref.counters()
+    ref.close()
+    fresh = rt.Scene.from_rtsc(data)
+    bufs = [torch.zeros((108, 192, 3), dtype=torch.float32).pin_memory().numpy() for _ in ps]
+    tickets = [fresh.render_frame_begin(p, b) for p, b in zip(ps, bufs)]
+    for t in tickets:
+        fresh.frame_wait(t)
+    cf = fresh.counters()
+    for i, (b, w) in enumerate(zip(bufs, want)):
+        assert np.array_equal(b.view(np.uint32), w.view(np.uint32)), i
+    assert (cf.primary, cf.shadow, cf.secondary, cf.secondary_hits) == (cw.primary, cw.shadow, cw.secondary, cw.secondary_hits)
+    # steady state afterwards: same frames again, now without a re-render
+    tickets = [fresh.render_frame_begin(p, b) for p, b in zip(ps, bufs)]
+    fresh.frame_wait(tickets[-1])
+    for i, (b, w) in enumerate(zip(bufs, want)):
+        assert np.array_equal(b.view(np.uint32), w.view(np.uint32)), i
+    fresh.close()
+
+
 # ---- device-pointer entry points, threading ----------------------------------------------------------------------------------------
 def test_device_pointer_api_with_torch(rt, oracle_mod):
     torch = pytest.importorskip("torch")
