@@ -20,6 +20,9 @@
 #ifndef BVH_COUNT_NODE
 #define BVH_COUNT_NODE() ((void)0)
 #endif
+#ifndef BVH_COUNT_LEAF
+#define BVH_COUNT_LEAF() ((void)0)
+#endif
 
 namespace rtb {
 
@@ -148,6 +151,7 @@ RT_HD void bvh_node_step(BvhState& s, BvhStackEntry* stack, const float* __restr
 template <bool CULL, bool FAST>
 RT_HD void bvh_leaf_step(BvhState& s, const BvhStackEntry* stack, const float* __restrict__ tris, float eps) {
     if (!(s.t0 > kd_min(s.best.t, s.t_far))) {
+        BVH_COUNT_LEAF();
         kd_test_leaf<CULL, FAST>(tris + size_t(s.ref) * KD8_TRI_FLOATS, s.cnt, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
         if (s.any_hit && s.best.t <= s.t_far) { s.phase = KD8_DONE; return; }
     }

@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kd_build.hpp"
@@ -23,7 +25,12 @@ namespace rtb {
 namespace {
 
 constexpr int BVH_BINS = 16;
-constexpr double BVH_COST_STEP = 1.0, BVH_COST_TRI = 1.0;
+// cost of one node step relative to one triangle test in the leaf-or-split decision (RT_B200_BVH_COST: tuning sweeps only)
+constexpr double BVH_COST_TRI = 1.0;
+static double bvh_cost_step() {
+    static const double v = [] { double x = 1.0; if (const char* e = std::getenv("RT_B200_BVH_COST")) std::sscanf(e, "%lf", &x); return x; }();
+    return v;
+}
 
 inline double half_area(const float* lo, const float* hi) {
     const double dx = double(hi[0]) - lo[0], dy = double(hi[1]) - lo[1], dz = double(hi[2]) - lo[2];
@@ -90,7 +97,7 @@ struct BvhPolicy {
             }
         }
         if (best_axis >= 0 && N <= max_leaf && area > 0) {
-            const double split_cost = BVH_COST_STEP + BVH_COST_TRI * best_cost / area;
+            const double split_cost = bvh_cost_step() + BVH_COST_TRI * best_cost / area;
             if (BVH_COST_TRI * double(N) <= split_cost) return false;        // cheaper as a leaf
         }
         c0.depth = c1.depth = w.depth + 1;

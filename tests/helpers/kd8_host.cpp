@@ -2,16 +2,22 @@
 // CUDA kernels run) as plain C++ so that tests/test_kd8_host.py can check the algorithm and the flattened tree against the
 // oracle on a machine without a GPU.  Built with -ffp-contract=off (the device TU is built with -fmad=false).
 #include <cstdint>
-static uint64_t g_kd8_nodes, g_kd8_tris;                 // visit counters (rt_kd8.cuh instrumentation hooks)
+static uint64_t g_kd8_nodes, g_kd8_tris, g_bvh_leaves;   // visit counters (rt_kd8.cuh / rt_bvh.cuh instrumentation hooks)
 #define KD8_COUNT_NODE() (++g_kd8_nodes)
 #define KD8_COUNT_TRI() (++g_kd8_tris)
 #define BVH_COUNT_NODE() (++g_kd8_nodes)
+#define BVH_COUNT_LEAF() (++g_bvh_leaves)
 #include "../../simd-raytracer_b200/csrc/rt_bvh.cuh"          // includes rt_kd8.cuh
 
 extern "C" void kd8_counters(uint64_t* nodes, uint64_t* tris, int reset) {
     if (nodes) *nodes = g_kd8_nodes;
     if (tris) *tris = g_kd8_tris;
     if (reset) g_kd8_nodes = g_kd8_tris = 0;
+}
+extern "C" uint64_t bvh_leaf_visits(int reset) {
+    const uint64_t v = g_bvh_leaves;
+    if (reset) g_bvh_leaves = 0;
+    return v;
 }
 
 extern "C" void kd8_trace_batch(const uint32_t* nodes8, const float* tris, const float* root6, const float* rays6, uint64_t n,
