@@ -269,16 +269,44 @@ def main() -> None:
         dist.all_gather_object(handles, peer.handle)
         peer.connect(handles)
         dist.barrier()
-    fb_ptr = peer.framebuffer if peer else fb.data_ptr()
+    # N > 1, peer combine: one step = the render of frame i (main stream) and, concurrently on a second stream, the fused
+    # wait+reduce+resolve of frame i-1 (rt_peer_* keeps two frame slots per rank).  The combine is released by the step's
+    # start event, so every timed step [a, b] contains exactly one render and one combine; nothing runs during the L2 flush.
+    side = torch.cuda.Stream() if peer else None
+    ev_done = torch.cuda.Event() if peer else None
+    outputs = rt.PEER_OUT_RGB                      # N = 1 leaves a float frame in HBM; so does the combine (rank 0)
+    pending = [False]
 
     def frame_device():
-        scene.render_frame_device(params, fb_ptr, stream=stream.cuda_stream)
+        """serial frame: render, then combine, on the launching stream (warm-up, verification, NCCL baseline)"""
         if peer:
+            scene.render_frame_device(params, peer.framebuffer, stream=stream.cuda_stream)
             peer.combine(spp_total, rt.PEER_OUT_RGB | rt.PEER_OUT_RGB8, stream=stream.cuda_stream)
-        elif world > 1:
+            return
+        scene.render_frame_device(params, fb.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
             dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 scene.resolve_sum_device(fb.data_ptr(), spp_total, d_rgb=fb.data_ptr(), d_rgb8=rgb8.data_ptr(), stream=stream.cuda_stream)
+
+    def combine_pending(start_event):
+        """the combine of the frame signalled last, on the side stream, not before `start_event`"""
+        side.wait_event(start_event)
+        peer.reduce_resolve(spp_total, outputs, stream=side.cuda_stream)
+        peer.wait_done(stream=side.cuda_stream)
+        ev_done.record(side)
+
+    def step_pipelined(a, b):
+        a.record(stream)
+        if pending[0]:
+            combine_pending(a)
+        t = scene.render_frame_device_begin(params, peer.framebuffer, stream=stream.cuda_stream)     # queued, no host sync
+        peer.signal_ready(stream.cuda_stream)                                                        # flips the frame slot
+        if pending[0]:
+            stream.wait_event(ev_done)             # frame i+1 renders into the slot the combined frame used
+        pending[0] = True
+        b.record(stream)
+        return t
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,34 +324,64 @@ def main() -> None:
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     acc = {k: 0.0 for k in ("ms_primary", "ms_secondary", "ms_shadow", "ms_shade", "ms_resolve", "ms_total")}
     launches = 0
+    rerendered = 0
+    if peer:
+        # prime the pipeline (untimed): frame -1 rendered and signalled, its combine is the first timed step's
+        e0 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        scene.frame_wait(step_pipelined(*e0))
     barrier()
     with ClockSampler(local) as clocks:
         t_wall0 = time.perf_counter()
         for a, b in ev:
             flush.fill_(1)
-            a.record(stream)
-            frame_device()
-            b.record(stream)
-            c = scene.counters()            # blocks until the frame is done; reads the per-class CUDA events of this frame
+            if peer:
+                rerendered += bool(scene.frame_wait(step_pipelined(a, b)))
+                b.synchronize()
+                c = scene.counters()        # of the queued frame: device time of the render; no per-kernel events inside it
+                launches += c.kernel_launches + 3
+            else:
+                a.record(stream)
+                frame_device()
+                b.record(stream)
+                c = scene.counters()        # blocks until the frame is done; reads the per-class CUDA events of this frame
+                launches += c.kernel_launches + (1 if world > 1 and rank == 0 else 0)
             for k in acc:
                 acc[k] += getattr(c, k)
-            launches += c.kernel_launches + (3 if peer else (1 if world > 1 and rank == 0 else 0))
         barrier()
         t_wall = time.perf_counter() - t_wall0
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    if peer:
+        # drain (untimed): the combine of the last timed frame
+        e1 = torch.cuda.Event()
+        e1.record(stream)
+        combine_pending(e1)
+        stream.wait_event(ev_done)
+        pending[0] = False
+        barrier()
+        if rerendered:
+            raise SystemExit("a timed frame had to be rendered again (pool overflow after warm-up): the measurement is void")
+        # per-kernel-class times: the queued frames carry no per-kernel events, so the split comes from serial frames
+        for k in acc:
+            acc[k] = 0.0
+        for _ in range(3):
+            frame_device()
+            c = scene.counters()
+            for k in acc:
+                acc[k] += getattr(c, k) * args.steps / 3.0
+        barrier()
 
-    # ---- timed: end to end through the C ABI with a host framebuffer (rank-local frame; N>1 adds the reduce above) -------
+    # ---- timed: end to end through the C ABI with a host framebuffer ---------------------------------------------------------
     e2e_params = rt.default_params(samples_per_pixel=count, sample_offset=first, spp_total=spp_total, max_ray_depth=w["max_ray_depth"],
                                    diffuse_reflection_ray_count=w["gi_rays"], flags=flags)
     host_np = host.numpy()
-
-    host2_np = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory().numpy() if world == 1 else None
+    host2_np = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory().numpy()
 
     def frame_e2e():
+        """one call per frame, synchronous"""
         if world == 1:
             scene.render_frame(e2e_params, out=host_np)          # params in, float frame out to pinned host memory
             return
-        # N > 1: every rank renders its slice, the fused peer kernel combines, rank 0 downloads the float frame
+        # N > 1: every rank renders its slice, the combine runs, rank 0 downloads the float frame
         frame_device()
         if rank == 0:
             if peer:
@@ -334,20 +392,11 @@ def main() -> None:
         else:
             stream.synchronize()
 
-    for _ in range(3):
-        frame_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        frame_e2e()
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    t_e2e_sync = None
-    if world == 1:
-        # the same K frames as a frame SEQUENCE (rt_render_frame_begin / rt_frame_wait): every frame still takes its parameters
-        # from the host and lands as a float frame in pinned host memory inside the timed region; frame i's download overlaps
-        # frame i+1's render.  This is the e2e headline; the one-call-per-frame number is kept beside it.
-        def sequence(k):
+    def sequence(k):
+        """the same k frames as a frame SEQUENCE: every frame still takes its parameters from the host and lands as a float
+        frame in pinned host memory inside the timed region; frame i's download (and, N > 1, its combine over NVLink) overlaps
+        frame i+1's render, nothing waits for the host in between"""
+        if world == 1:
             prev = None
             for i in range(k):
                 t = scene.render_frame_begin(e2e_params, host2_np if i & 1 else host_np)
@@ -355,13 +404,47 @@ def main() -> None:
                     scene.frame_wait(prev)
                 prev = t
             scene.frame_wait(prev)
+            return 0
+        redo = 0
+        ev_dl = torch.cuda.Event()
+        for i in range(k + 1):
+            e = torch.cuda.Event()
+            e.record(stream)
+            if i > 0:
+                combine_pending(e)                                # frame i-1: reduce + resolve into rank 0, side stream
+                if rank == 0:
+                    peer.download_result(host2_np if (i - 1) & 1 else host_np, stream=side.cuda_stream)
+                    ev_dl.record(side)
+            t = None
+            if i < k:
+                t = scene.render_frame_device_begin(params, peer.framebuffer, stream=stream.cuda_stream)
+                peer.signal_ready(stream.cuda_stream)
+                if i > 0:
+                    stream.wait_event(ev_done)
+            if i > 0:
+                (ev_dl if rank == 0 else ev_done).synchronize()   # frame i-1 is in host memory
+            if t is not None:
+                redo += bool(scene.frame_wait(t))
+        return redo
+
+    for _ in range(3):
+        frame_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame_e2e()
+    barrier()
+    t_e2e_sync = time.perf_counter() - t0
+    t_e2e = t_e2e_sync
+    if world == 1 or peer:
         sequence(3)
         barrier()
-        t_e2e_sync = t_e2e
         t0 = time.perf_counter()
-        sequence(args.steps)
+        redo = sequence(args.steps)
         barrier()
         t_e2e = time.perf_counter() - t0
+        if redo:
+            raise SystemExit("a timed frame of the sequence had to be rendered again after warm-up: the measurement is void")
 
     # ---- N > 1: the combined frame must be the single-GPU frame at spp = N (bit for bit with one sample per rank) ----------
     verify = None
@@ -383,13 +466,13 @@ def main() -> None:
                 verify = {"combined_frame_finite": bool(np.isfinite(got).all()), "rgb8_nonzero": int((got8 != 0).sum())}
         barrier()
 
-    t = torch.tensor([ms_dev, t_e2e, float(rays_frame)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_dev, t_e2e, float(rays_frame), t_e2e_sync], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_dev, t_e2e, rays_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        ms_dev, t_e2e, rays_all, t_e2e_sync = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3])
     else:
         rays_all = float(rays_frame)
 
@@ -431,9 +514,13 @@ def main() -> None:
                     "d2h_bytes_per_step": int(host.numel() * 4),
                     "api": ("rt_render_frame_begin + rt_frame_wait (frame sequence: params in, float frame out to pinned host memory "
                             "every step; frame i's download overlaps frame i+1's render)" if world == 1 else
-                            "rt_render_frame_device per rank + combine + float frame to pinned host memory on rank 0"),
+                            ("rt_render_frame_device_begin per rank, rt_peer_* combine + rt_peer_download_result on a second stream "
+                             "(frame i's combine and download overlap frame i+1's render), float frame in pinned host memory on rank 0 "
+                             "every step" if peer else
+                             "rt_render_frame_device per rank + ncclReduce + resolve + float frame to pinned host memory on rank 0")),
                     "one_call_per_frame": ({"value": rays_all * K / t_e2e_sync / 1e6, "ms_per_frame": 1e3 * t_e2e_sync / K,
-                                            "api": "rt_render_frame (synchronous: render, download, return)"} if t_e2e_sync else None)},
+                                            "api": ("rt_render_frame (synchronous: render, download, return)" if world == 1 else
+                                                    "serial: render, combine, download, per frame")} if (world == 1 or peer) else None)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
@@ -456,7 +543,8 @@ def main() -> None:
                               "frac": (kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12) / fp32_peak if cls[dom] else 0.0},
             "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall,
-            "combine": (None if world == 1 else ("rt_peer_combine: fused wait+reduce+resolve over NVLink peer memory" if peer else
+            "combine": (None if world == 1 else ("rt_peer_*: fused wait+reduce+resolve over NVLink peer memory, frame i-1's combine on a "
+                                                 "second stream inside frame i's timed step (two frame slots per rank)" if peer else
                                                  "ncclReduce(sum) to rank 0 + rt_resolve_sum_device")),
             "verify": verify,
             "scene": {"triangles": int(scene.info.n_triangles), "kd_nodes": int(scene.info.n_nodes), "packets": int(scene.info.n_packets),

@@ -36,7 +36,8 @@ typedef enum rt_status {
     RT_ERR_IO = 4,             /* scene / texture file could not be read */
     RT_ERR_PARSE = 5,          /* malformed .crtscene / RTSC; unknown material or texture type */
     RT_ERR_OOM = 6,
-    RT_ERR_UNSUPPORTED = 7     /* e.g. a bitmap format the loader cannot decode */
+    RT_ERR_UNSUPPORTED = 7,    /* e.g. a bitmap format the loader cannot decode */
+    RT_FRAME_RERENDERED = 8    /* rt_frame_wait on an rt_render_frame_device_begin ticket: not an error, see there */
 } rt_status;
 
 /* ---- scene description: what io/json/loader.hpp:235-265 produces, flattened -------------------------------- */
@@ -210,6 +211,11 @@ RT_API int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8);
  * stay valid until waited for.  Frames complete in ticket order.                                                   */
 RT_API int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t* ticket);
 RT_API int rt_frame_wait(rt_scene* s, uint64_t ticket);
+/* The same queued render into the CALLER's device frame (no download), asynchronous on `stream` (all queued frames of a
+ * scene must use the same stream).  Work queued behind it on that stream (a peer combine, a copy) runs without a host round
+ * trip.  rt_frame_wait then returns RT_OK, or RT_FRAME_RERENDERED when the queued attempt outgrew the wavefront pools (first
+ * frames of a scene): d_rgb has been rendered again and is correct now, but whatever consumed it before must be redone.      */
+RT_API int rt_render_frame_device_begin(rt_scene* s, const rt_params* p, float* d_rgb, void* stream, uint64_t* ticket);
 /* device framebuffer (for the multi-GPU combine): d_rgb = height*width*3 floats in HBM; asynchronous on stream */
 RT_API int rt_render_frame_device(rt_scene* s, const rt_params* p, float* d_rgb, void* stream);
 /* primary rays only: ray generation + intersect<true> (render.hpp:35-64); hits: one per pixel of the tile,
@@ -239,6 +245,9 @@ RT_API int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint3
 RT_API int rt_peer_group_connect(rt_peer_group* g, const uint8_t* handles /* world x RT_PEER_HANDLE_BYTES, rank order */);
 /* all ranks inside one process (one GPU emulating several ranks, or several peer GPUs driven by one host thread) */
 RT_API int rt_peer_group_connect_local(rt_peer_group* const* groups, uint32_t world);
+/* Every rank owns TWO frame slots: frame e+1 can be rendered while frame e is being combined.  rt_peer_framebuffer is where
+ * the NEXT frame (the one that will be signalled next) is rendered; it flips with every rt_peer_signal_ready.  The result
+ * pointers are those of the frame signalled LAST (rank 0's copy holds the combined frame once every rank is done).        */
 RT_API float* rt_peer_framebuffer(rt_peer_group* g);      /* device pointers into this rank's block */
 RT_API float* rt_peer_result_rgb(rt_peer_group* g);
 RT_API uint8_t* rt_peer_result_rgb8(rt_peer_group* g);
@@ -248,7 +257,12 @@ RT_API int rt_peer_combine(rt_peer_group* g, uint32_t spp_total, uint32_t output
 RT_API int rt_peer_signal_ready(rt_peer_group* g, void* stream);
 RT_API int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void* stream);
 RT_API int rt_peer_wait_done(rt_peer_group* g, void* stream);
-/* rank 0: copy the combined frame to host buffers (either may be null); synchronises `stream`                   */
+/* Pipelined use: render frame e+1 on one stream while rt_peer_reduce_resolve + rt_peer_wait_done of frame e run on another
+ * (after rt_peer_signal_ready(e) on the render stream); the render stream must wait for that rt_peer_wait_done before frame
+ * e+2 is rendered into the slot frame e used.                                                                              */
+/* rank 0: copy the combined frame of the frame signalled last to host buffers (either may be null).
+ * rt_peer_download_result only queues the copies on `stream`; rt_peer_read_result also synchronises `stream`.              */
+RT_API int rt_peer_download_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream);
 RT_API int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream);
 RT_API void rt_peer_group_destroy(rt_peer_group* g);
 

@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")
 
 RT_OK, RT_ERR_BAD_ARG, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_OOM, RT_ERR_UNSUPPORTED = range(8)
+RT_FRAME_RERENDERED = 8
 FLAG_RAW_SUM, FLAG_FAST_MATH, FLAG_ORDERED = 1, 2, 4
 DEVICE_HOST_ONLY = -1
 TEX_ALBEDO, TEX_EDGES, TEX_CHECKER, TEX_BITMAP = range(4)
@@ -34,12 +35,12 @@ ABI_SYMBOLS = (
     "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_build_kd_accel", "rt_scene_get_bvh_layout",
     "rt_scene_get_geometry",
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
-    "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_begin", "rt_frame_wait", "rt_render_frame_device", "rt_trace_primary",
+    "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_begin", "rt_frame_wait", "rt_render_frame_device_begin", "rt_render_frame_device", "rt_trace_primary",
     "rt_get_counters",
     "rt_resolve_sum_device",
     "rt_peer_group_create", "rt_peer_group_connect", "rt_peer_group_connect_local", "rt_peer_framebuffer", "rt_peer_result_rgb",
     "rt_peer_result_rgb8", "rt_peer_combine", "rt_peer_signal_ready", "rt_peer_reduce_resolve", "rt_peer_wait_done",
-    "rt_peer_read_result", "rt_peer_group_destroy",
+    "rt_peer_download_result", "rt_peer_read_result", "rt_peer_group_destroy",
 )
 
 
@@ -145,6 +146,7 @@ def _load():
     L.rt_render_frame_device.argtypes = [vp, C.POINTER(Params), vp, vp]
     L.rt_render_frame_begin.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(u64)]
     L.rt_frame_wait.argtypes = [vp, u64]
+    L.rt_render_frame_device_begin.argtypes = [vp, C.POINTER(Params), vp, vp, C.POINTER(u64)]
     L.rt_trace_primary.argtypes = [vp, C.POINTER(Params), vp]
     L.rt_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.rt_resolve_sum_device.argtypes = [vp, vp, u32, vp, vp, vp]
@@ -159,6 +161,7 @@ def _load():
     L.rt_peer_reduce_resolve.argtypes = [vp, u32, u32, vp]
     L.rt_peer_wait_done.argtypes = [vp, vp]
     L.rt_peer_read_result.argtypes = [vp, vp, vp, vp]
+    L.rt_peer_download_result.argtypes = [vp, vp, vp, vp]
     L.rt_peer_group_destroy.argtypes = [vp]
     L.rt_peer_group_destroy.restype = None
     return L
@@ -391,8 +394,18 @@ class Scene:
         _check(lib.rt_render_frame_begin(self.h, C.byref(params), out.ctypes.data, C.byref(t)))
         return int(t.value)
 
-    def frame_wait(self, ticket: int) -> None:
-        _check(lib.rt_frame_wait(self.h, ticket))
+    def frame_wait(self, ticket: int) -> bool:
+        """True when the frame had to be rendered again (only reported for render_frame_device_begin tickets)"""
+        st = lib.rt_frame_wait(self.h, ticket)
+        if st == RT_FRAME_RERENDERED:
+            return True
+        _check(st)
+        return False
+
+    def render_frame_device_begin(self, params: Params, d_rgb: int, stream: int | None = None) -> int:
+        t = C.c_uint64(0)
+        _check(lib.rt_render_frame_device_begin(self.h, C.byref(params), d_rgb, _stream(stream), C.byref(t)))
+        return int(t.value)
 
     def render_frame_device(self, params: Params, d_rgb: int, stream: int | None = None) -> None:
         _check(lib.rt_render_frame_device(self.h, C.byref(params), d_rgb, _stream(stream)))
@@ -466,6 +479,11 @@ class PeerGroup:
         rgb8 = np.zeros((self.height, self.width, 3), np.uint8) if want_rgb8 else None
         _check(lib.rt_peer_read_result(self.h, rgb.ctypes.data, rgb8.ctypes.data if want_rgb8 else None, _stream(stream)))
         return rgb, rgb8
+
+    def download_result(self, rgb: np.ndarray, stream: int | None = None) -> None:
+        """rank 0: queue the copy of the combined float frame (of the frame signalled last) into pinned `rgb`; no sync"""
+        assert rgb.dtype == np.float32 and rgb.size == self.height * self.width * 3 and rgb.flags["C_CONTIGUOUS"]
+        _check(lib.rt_peer_download_result(self.h, rgb.ctypes.data, None, _stream(stream)))
 
     def close(self) -> None:
         if self.h:

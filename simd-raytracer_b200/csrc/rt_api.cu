@@ -127,7 +127,10 @@ struct rt_scene {
         FrameCounters* h_fc = nullptr;   // pinned
         bool in_flight = false, deferred = false, used = false;
         rt_params params{}, key{};
-        float* host_rgb = nullptr;
+        float* host_rgb = nullptr;       // download target (frame sequences to the host), or null
+        float* target = nullptr;         // device frame the slot renders into: its own `fb`, or the caller's (rt_render_frame_device_begin)
+        cudaStream_t stream = nullptr;
+        bool rerendered = false;         // the frame overflowed its pools when first queued and was rendered again at wait time
         uint64_t n0 = 0;
         uint32_t launches = 0;
     } seq[2];
@@ -688,10 +691,11 @@ void finalize_slot(rt_scene* s, int k) {
     if (!q.deferred) return;                                   // rendered by the synchronous path: nothing left to check
     if (q.h_flags[2] != 0) {
         grow_pools_after_overflow(s, q.h_flags, q.n0);
-        CK(cudaStreamSynchronize(s->stream));                  // the other frame in flight uses the pools that are about to grow
-        render_device(s, q.params, q.fb.p, s->stream, false);
-        copy_rect_to_host(s, rect_of(s, q.params), q.fb.p, q.host_rgb, s->stream);
-        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaStreamSynchronize(q.stream));                   // the other frame in flight uses the pools that are about to grow
+        render_device(s, q.params, q.target, q.stream, false);
+        if (q.host_rgb) copy_rect_to_host(s, rect_of(s, q.params), q.target, q.host_rgb, q.stream);
+        CK(cudaStreamSynchronize(q.stream));
+        q.rerendered = true;
         return;
     }
     s->pool_hwm = q.h_flags[0]; s->shadow_hwm = q.h_flags[1];
@@ -715,7 +719,8 @@ void drain_sequence(rt_scene* s) {
     finalize_slot(s, older ^ 1);
 }
 
-void begin_frame(rt_scene* s, const rt_params& p, float* rgb, uint64_t* ticket) {
+// rgb: host frame to download into (frame sequences) or null; d_ext: the caller's device frame or null (then the slot's own)
+void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cudaStream_t st, uint64_t* ticket) {
     check_params(p);
     const Rect rect = rect_of(s, p);
     if (!s->copy_stream) {
@@ -732,15 +737,16 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, uint64_t* ticket) 
     const int k = int(s->seq_issued & 1);
     rt_scene::SeqSlot& q = s->seq[k];
     finalize_slot(s, k);                                       // the frame two tickets back (normally long complete)
-    q.fb.reserve(size_t(s->host.width) * s->host.height * 3);
-    cudaStream_t st = s->stream;
+    if (!d_ext) q.fb.reserve(size_t(s->host.width) * s->host.height * 3);
+    float* const target = d_ext ? d_ext : q.fb.p;
+    q.rerendered = false;
 
     FrameParams fp = frame_params(s, p, rect);
     const uint32_t spp = p.samples_per_pixel;
     const bool one_pass = uint64_t(spp) * fp.plane <= PRIMARY_BUDGET;
     if (!one_pass) {
         // several passes re-use the pools and need the pass-by-pass overflow check: synchronous render, overlapped download
-        render_device(s, p, q.fb.p, st);
+        render_device(s, p, target, st);
         q.deferred = false;
     } else {
         fetch_counters(s);
@@ -761,16 +767,20 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, uint64_t* ticket) 
         if (q.used) CK(cudaStreamWaitEvent(st, q.copied, 0));   // the device frame of this slot has been downloaded
         CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
         CK(cudaEventRecord(q.a, st));
-        enqueue_pass(s, P, q.fb.p, q.h_flags, st, [&](int, auto&& launch) { launch(); CK(cudaGetLastError()); ++launches; });
+        enqueue_pass(s, P, target, q.h_flags, st, [&](int, auto&& launch) { launch(); CK(cudaGetLastError()); ++launches; });
         CK(cudaEventRecord(q.b, st));
         CK(cudaMemcpyAsync(q.h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
         q.deferred = true; q.params = p; q.key = key; q.n0 = n0; q.launches = launches;
     }
-    CK(cudaEventRecord(q.rendered, st));
-    CK(cudaStreamWaitEvent(s->copy_stream, q.rendered, 0));
-    copy_rect_to_host(s, rect, q.fb.p, rgb, s->copy_stream);
-    CK(cudaEventRecord(q.copied, s->copy_stream));
-    q.host_rgb = rgb; q.in_flight = true; q.used = true;
+    if (rgb) {
+        CK(cudaEventRecord(q.rendered, st));
+        CK(cudaStreamWaitEvent(s->copy_stream, q.rendered, 0));
+        copy_rect_to_host(s, rect, target, rgb, s->copy_stream);
+        CK(cudaEventRecord(q.copied, s->copy_stream));
+    } else {
+        CK(cudaEventRecord(q.copied, st));                     // "complete" = rendered
+    }
+    q.host_rgb = rgb; q.target = target; q.stream = st; q.in_flight = true; q.used = true;
     *ticket = s->seq_issued++;
 }
 
@@ -791,6 +801,7 @@ const char* rt_status_string(int status) {
         case RT_ERR_PARSE: return "parse error";
         case RT_ERR_OOM: return "out of memory";
         case RT_ERR_UNSUPPORTED: return "unsupported";
+        case RT_FRAME_RERENDERED: return "frame was rendered again (its first, queued attempt outgrew the wavefront pools)";
         default: return "unknown status";
     }
 }
@@ -1010,7 +1021,18 @@ int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t*
         if (!p || !rgb || !ticket) throw rt_error(RT_ERR_BAD_ARG, "null argument");
         std::lock_guard<std::mutex> lock(s->mtx);
         CK(cudaSetDevice(s->device));
-        begin_frame(s, *p, rgb, ticket);
+        begin_frame(s, *p, rgb, nullptr, s->stream, ticket);
+        return int(RT_OK);
+    });
+}
+
+int rt_render_frame_device_begin(rt_scene* s, const rt_params* p, float* d_rgb, void* stream, uint64_t* ticket) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !d_rgb || !ticket) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        begin_frame(s, *p, nullptr, d_rgb, stream ? static_cast<cudaStream_t>(stream) : s->stream, ticket);
         return int(RT_OK);
     });
 }
@@ -1024,7 +1046,10 @@ int rt_frame_wait(rt_scene* s, uint64_t ticket) {
         // frames complete in ticket order; a ticket older than the two newest was finished when its slot was re-used
         if (ticket + 2 == s->seq_issued) finalize_slot(s, int(ticket & 1));
         else if (ticket + 1 == s->seq_issued) { finalize_slot(s, int((ticket & 1) ^ 1)); finalize_slot(s, int(ticket & 1)); }
-        return int(RT_OK);
+        else return int(RT_OK);
+        const rt_scene::SeqSlot& q = s->seq[ticket & 1];
+        // a caller-owned device frame may already have been consumed (e.g. combined with other ranks) before the re-render
+        return (q.rerendered && !q.host_rgb) ? int(RT_FRAME_RERENDERED) : int(RT_OK);
     });
 }
 
@@ -1086,13 +1111,15 @@ struct rt_peer_group {
     uint32_t world = 1, rank = 0;
     int device = 0;
     uint64_t n = 0;                         // floats per framebuffer
-    uint8_t* block = nullptr;               // local allocation: [raw sums][result rgb][result rgb8][flags]
-    size_t off_rgb = 0, off_rgb8 = 0, off_flags = 0, bytes = 0;
+    uint8_t* block = nullptr;               // local allocation: 2 x { [raw sums][result rgb][result rgb8] } + [flags]
+    size_t slot_bytes = 0, off_rgb = 0, off_rgb8 = 0, off_flags = 0, bytes = 0;   // off_rgb / off_rgb8 are relative to a slot
     uint8_t* peer[PEER_MAX] = {};           // every rank's block as mapped here (own entry = block)
     bool opened[PEER_MAX] = {};
     bool connected = false;
-    uint32_t epoch = 0;
+    uint32_t epoch = 0;                     // frames signalled so far; frame e lives in slot (e - 1) & 1
     PeerTable table{};
+    size_t next_slot() const { return size_t(epoch & 1u) * slot_bytes; }           // where the NEXT frame is rendered
+    size_t last_slot() const { return size_t((epoch - 1u) & 1u) * slot_bytes; }    // the frame signalled last
 };
 
 namespace {
@@ -1126,7 +1153,8 @@ int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t wid
         g->n = uint64_t(width) * height * 3;
         g->off_rgb = align256(g->n * 4);
         g->off_rgb8 = g->off_rgb + align256(g->n * 4);
-        g->off_flags = g->off_rgb8 + align256(g->n);
+        g->slot_bytes = g->off_rgb8 + align256(g->n);
+        g->off_flags = 2 * g->slot_bytes;
         g->bytes = g->off_flags + align256(PEER_FLAG_COUNT * 4);
         CK(cudaMalloc(&g->block, g->bytes));
         CK(cudaMemset(g->block, 0, g->bytes));
@@ -1190,9 +1218,9 @@ int rt_peer_group_connect_local(rt_peer_group* const* groups, uint32_t world) {
     });
 }
 
-float* rt_peer_framebuffer(rt_peer_group* g) { return g ? reinterpret_cast<float*>(g->block) : nullptr; }
-float* rt_peer_result_rgb(rt_peer_group* g) { return g ? reinterpret_cast<float*>(g->block + g->off_rgb) : nullptr; }
-uint8_t* rt_peer_result_rgb8(rt_peer_group* g) { return g ? g->block + g->off_rgb8 : nullptr; }
+float* rt_peer_framebuffer(rt_peer_group* g) { return g ? reinterpret_cast<float*>(g->block + g->next_slot()) : nullptr; }
+float* rt_peer_result_rgb(rt_peer_group* g) { return g && g->epoch ? reinterpret_cast<float*>(g->block + g->last_slot() + g->off_rgb) : nullptr; }
+uint8_t* rt_peer_result_rgb8(rt_peer_group* g) { return g && g->epoch ? g->block + g->last_slot() + g->off_rgb8 : nullptr; }
 
 int rt_peer_signal_ready(rt_peer_group* g, void* stream) {
     return guarded([&] {
@@ -1216,9 +1244,9 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
         CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g->device));
         const uint64_t want = (g1 - g0 + 255) / 256;
         const int blocks = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(n_sm) * 8)));
-        uint8_t* root = g->peer[0];
+        uint8_t* root = g->peer[0] + g->last_slot();
         k_peer_reduce_resolve<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            g->table, int(g->world), int(g->rank), g0, g1, float(spp_total),
+            g->table, uint64_t(g->last_slot() / 4), int(g->world), int(g->rank), g0, g1, float(spp_total),
             (outputs & 1u) ? reinterpret_cast<float*>(root + g->off_rgb) : nullptr, (outputs & 2u) ? root + g->off_rgb8 : nullptr,
             g->epoch, n4 * 4, g->n);
         CK(cudaGetLastError());
@@ -1243,14 +1271,22 @@ int rt_peer_combine(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void
     return st;
 }
 
-int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream) {
+int rt_peer_download_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream) {
     return guarded([&] {
-        if (!g) throw rt_error(RT_ERR_BAD_ARG, "null peer group");
+        if (!g || !g->epoch) throw rt_error(RT_ERR_BAD_ARG, "no combined frame yet");
         CK(cudaSetDevice(g->device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        if (rgb) CK(cudaMemcpyAsync(rgb, g->block + g->off_rgb, g->n * 4, cudaMemcpyDeviceToHost, st));
-        if (rgb8) CK(cudaMemcpyAsync(rgb8, g->block + g->off_rgb8, g->n, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if (rgb) CK(cudaMemcpyAsync(rgb, g->block + g->last_slot() + g->off_rgb, g->n * 4, cudaMemcpyDeviceToHost, st));
+        if (rgb8) CK(cudaMemcpyAsync(rgb8, g->block + g->last_slot() + g->off_rgb8, g->n, cudaMemcpyDeviceToHost, st));
+        return int(RT_OK);
+    });
+}
+
+int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream) {
+    const int st = rt_peer_download_result(g, rgb, rgb8, stream);
+    if (st != RT_OK) return st;
+    return guarded([&] {
+        CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
         return int(RT_OK);
     });
 }

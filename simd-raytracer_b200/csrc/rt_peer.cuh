@@ -25,9 +25,11 @@ constexpr int PEER_FLAG_DONE = PEER_MAX;      // flags[PEER_FLAG_DONE + r]  = la
 constexpr int PEER_FLAG_COUNT = 2 * PEER_MAX + 2;   // [2*PEER_MAX] = block counter of the local reduce kernel
 
 struct PeerTable {
-    const float* fb[PEER_MAX];                // every rank's raw sample sums (height*width*3 floats)
+    const float* fb[PEER_MAX];                // every rank's raw sample sums (height*width*3 floats), frame slot 0
     uint32_t* flags[PEER_MAX];                // every rank's flag block
 };
+// Two frame slots per rank (frame e lives in slot (e - 1) & 1): frame e+1 can be rendered while frame e is being reduced;
+// a slot is rendered into again only after every rank has published DONE for the frame that used it (k_peer_wait_done).
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -56,7 +58,7 @@ __device__ __forceinline__ uint8_t peer_quantise(float c) {          // io/image
 }
 
 // n4 = number of float4 groups of the whole frame; this rank owns groups [g0, g1)
-__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, int world, int rank, uint64_t g0, uint64_t g1, float div,
+__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, uint64_t slot_floats, int world, int rank, uint64_t g0, uint64_t g1, float div,
                                                              float* __restrict__ root_rgb, uint8_t* __restrict__ root_rgb8,
                                                              uint32_t epoch, uint64_t n_tail_begin, uint64_t n_total) {
     // ---- wait until every peer has rendered frame `epoch` (flags are in MY memory, peers store into them) ----
@@ -64,12 +66,20 @@ __global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, int wo
         while (ld_acquire_sys(t.flags[rank] + PEER_FLAG_READY + threadIdx.x) < epoch) __nanosleep(32);
     __syncthreads();
 
+    // slot_floats: offset of this frame's slot inside every rank's block (the blocks have the same layout)
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     for (uint64_t g = g0 + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < g1; g += stride) {
-        float4 s = __ldcg(reinterpret_cast<const float4*>(t.fb[0]) + g);
-        for (int r = 1; r < world; ++r) {                                // rank order = sample order (render.hpp:66-72)
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(t.fb[r]) + g);
-            s.x = s.x + v.x; s.y = s.y + v.y; s.z = s.z + v.z; s.w = s.w + v.w;
+        float4 s = __ldcg(reinterpret_cast<const float4*>(t.fb[0] + slot_floats) + g);
+        // all peers' loads are issued before the first add (one NVLink round trip per eight ranks, not one per rank);
+        // the adds stay in rank order = sample order (render.hpp:66-72)
+        for (int r0 = 1; r0 < world; r0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (r0 + k < world) v[k] = __ldcg(reinterpret_cast<const float4*>(t.fb[r0 + k] + slot_floats) + g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (r0 + k < world) { s.x = s.x + v[k].x; s.y = s.y + v[k].y; s.z = s.z + v[k].z; s.w = s.w + v[k].w; }
         }
         s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);   // :74
         if (root_rgb) reinterpret_cast<float4*>(root_rgb)[g] = s;
@@ -79,8 +89,8 @@ __global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, int wo
     // the last rank also owns the (< 4 element) tail of a frame whose size is not a multiple of four floats
     if (rank == world - 1 && blockIdx.x == 0) {
         for (uint64_t i = n_tail_begin + threadIdx.x; i < n_total; i += blockDim.x) {
-            float s = __ldcg(t.fb[0] + i);
-            for (int r = 1; r < world; ++r) s = s + __ldcg(t.fb[r] + i);
+            float s = __ldcg(t.fb[0] + slot_floats + i);
+            for (int r = 1; r < world; ++r) s = s + __ldcg(t.fb[r] + slot_floats + i);
             s = __fdiv_rn(s, div);
             if (root_rgb) root_rgb[i] = s;
             if (root_rgb8) root_rgb8[i] = peer_quantise(s);

@@ -378,6 +378,80 @@ def test_peer_combine_equals_single_gpu_frame(rt, size):
         g.close()
 
 
+def test_peer_combine_pipelined_over_two_frame_slots(rt):
+    """The pipelined use of the peer combine (bench.py --gpus N): frame i is queued on each rank's render stream
+    (rt_render_frame_device_begin, no host sync) while frame i-1 is reduced on a second stream; every rank owns two frame
+    slots.  Two ranks are emulated on this GPU, each with its own scene handle and streams; the frames differ (seed), and every
+    combined frame must equal the single-GPU frame at spp = 2 with that seed, bit for bit."""
+    torch = pytest.importorskip("torch")
+    size, world, frames = (200, 120), 2, 5
+    data = resized(scene_bytes("hw15_scene2"), *size)
+    scenes = [rt.Scene.from_rtsc(data) for _ in range(world)]
+    kw = dict(max_ray_depth=4, diffuse_reflection_ray_count=1)
+    want = [scenes[0].render_frame(rt.default_params(samples_per_pixel=world, seed=100 + f, **kw)) for f in range(frames)]
+    for sc in scenes:                                     # warm the pools: the queued frames below must not be re-rendered
+        sc.render_frame(rt.default_params(samples_per_pixel=1, spp_total=world, flags=rt.FLAG_RAW_SUM, **kw))
+    groups = [rt.PeerGroup(world, r, 0, *size) for r in range(world)]
+    rt.PeerGroup.connect_local(groups)
+    main = [torch.cuda.Stream() for _ in range(world)]
+    side = [torch.cuda.Stream() for _ in range(world)]
+    done = [torch.cuda.Event() for _ in range(world)]
+    got = [torch.zeros((size[1], size[0], 3), dtype=torch.float32).pin_memory().numpy() for _ in range(frames)]
+    tickets = []
+    for i in range(frames + 1):
+        starts = []
+        for r in range(world):
+            e = torch.cuda.Event()
+            e.record(main[r])
+            starts.append(e)
+        if i > 0:
+            for r in range(world):
+                side[r].wait_event(starts[r])
+                groups[r].reduce_resolve(world, rt.PEER_OUT_RGB, stream=side[r].cuda_stream)
+                groups[r].wait_done(side[r].cuda_stream)
+                done[r].record(side[r])
+            groups[0].download_result(got[i - 1], stream=side[0].cuda_stream)
+        if i < frames:
+            for r in range(world):
+                first, count = rt.spp_slice(world, r, world)
+                p = rt.default_params(samples_per_pixel=count, sample_offset=first, spp_total=world, seed=100 + i,
+                                      flags=rt.FLAG_RAW_SUM, **kw)
+                tickets.append((r, scenes[r].render_frame_device_begin(p, groups[r].framebuffer, stream=main[r].cuda_stream)))
+                groups[r].signal_ready(main[r].cuda_stream)
+                if i > 0:
+                    main[r].wait_event(done[r])
+    torch.cuda.synchronize()
+    assert not any(scenes[r].frame_wait(t) for r, t in tickets[-2 * world:])
+    for f in range(frames):
+        assert np.array_equal(got[f].view(np.uint32), want[f].view(np.uint32)), f
+    for g in groups:
+        g.close()
+    for sc in scenes:
+        sc.close()
+
+
+def test_queued_device_frame_reports_a_rerender(rt):
+    """rt_render_frame_device_begin on a fresh scene: the queued attempt outgrows the initial pools, rt_frame_wait renders the
+    frame again into the caller's buffer and says so (RT_FRAME_RERENDERED); the second time it does not."""
+    torch = pytest.importorskip("torch")
+    data = resized(scene_bytes("hw15_scene2"), 192, 108)               # closed box: every diffuse hit spawns three GI children
+    ref = rt.Scene.from_rtsc(data)
+    p = rt.default_params(max_ray_depth=3, diffuse_reflection_ray_count=3, flags=rt.FLAG_ORDERED)
+    want = ref.render_frame(p)
+    assert ref.counters().nodes_pool > 3 * 192 * 108                 # more than the initial pool factor (2x) allows
+    ref.close()
+    fresh = rt.Scene.from_rtsc(data)
+    st = torch.cuda.current_stream()
+    fb = torch.zeros((108, 192, 3), dtype=torch.float32, device="cuda")
+    assert fresh.frame_wait(fresh.render_frame_device_begin(p, fb.data_ptr(), stream=st.cuda_stream)) is True
+    assert np.array_equal(fb.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    fb.zero_()
+    assert fresh.frame_wait(fresh.render_frame_device_begin(p, fb.data_ptr(), stream=st.cuda_stream)) is False
+    st.synchronize()
+    assert np.array_equal(fb.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    fresh.close()
+
+
 def test_empty_level_skipping_never_changes_a_frame(rt):
     """The host launches only the recursion levels that held rays in the previous pass with the same frame parameters; if a
     skipped level turns out to be needed (GI paths of another sample slice reach deeper) the device flags the pass and it is
@@ -441,14 +515,15 @@ def test_frame_sequence_equals_single_frames(rt):
 
 def test_frame_sequence_on_a_fresh_scene_outgrows_its_pools(rt):
     """Frames of a sequence are queued without waiting for the device, so a pool overflow (here: the first frames of a fresh
-    scene whose refractive dragon spawns far more secondary queries than the initial pool factor allows, depth 10) is only seen
+    scene whose GI rays need several times the initial pool) is only seen
     when the frame is waited for; it is then rendered again.  The caller must get the same frames and counters either way."""
     torch = pytest.importorskip("torch")
-    data = resized(scene_bytes("hw11_scene8"), 192, 108)
+    data = resized(scene_bytes("hw15_scene2"), 192, 108)               # closed box: every diffuse hit spawns three GI children
     ref = rt.Scene.from_rtsc(data)
-    ps = [rt.default_params(max_ray_depth=10, flags=f) for f in (rt.FLAG_ORDERED, 0, rt.FLAG_ORDERED)]
+    ps = [rt.default_params(max_ray_depth=3, diffuse_reflection_ray_count=3, flags=f) for f in (rt.FLAG_ORDERED, 0, rt.FLAG_ORDERED)]
     want = [ref.render_frame(p) for p in ps]
     cw = ref.counters()
+    assert cw.nodes_pool > 3 * 192 * 108                             # more than the initial pool factor (2x) allows
     ref.close()
     fresh = rt.Scene.from_rtsc(data)
     bufs = [torch.zeros((108, 192, 3), dtype=torch.float32).pin_memory().numpy() for _ in ps]
