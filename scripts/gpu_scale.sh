@@ -1,11 +1,10 @@
 #!/bin/bash
-# developer helper (gpurun --gpus N): the default bench at N ranks, as the driver launches it
+# developer helper (gpurun --gpus N): the default bench at N ranks, as the driver launches it, then config 5 (1M triangles)
 n=${1:-8}; tag=${2:-scale}
 out=gpurun_out
-nvidia-smi -L | head -8
-for c in peer nccl; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $n --steps 100 --warmup 5 --combine $c > $out/${tag}_n${n}_$c.json 2> $out/${tag}_n${n}_$c.err; echo "n$n $c rc=$?"
-done
+nvidia-smi -L | wc -l; nproc; free -g | head -2
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $n --steps 200 --warmup 10 > $out/${tag}_n${n}_cfg2.json 2> $out/${tag}_n${n}_cfg2.err; echo "n$n cfg2 rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus $n --workload cfg5 --tris 1000000 --steps 10 --warmup 3 > $out/${tag}_n${n}_cfg5_1M.json 2> $out/${tag}_n${n}_cfg5_1M.err; echo "n$n cfg5 rc=$?"
 python - <<PY
 import json,glob
 for f in sorted(glob.glob("$out/${tag}_n${n}_*.json")):

@@ -1026,6 +1026,14 @@ int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t*
     });
 }
 
+void* rt_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    const cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(RT_ERR_OOM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+void rt_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
 int rt_render_frame_device_begin(rt_scene* s, const rt_params* p, float* d_rgb, void* stream, uint64_t* ticket) {
     return guarded([&] {
         require_device(s);

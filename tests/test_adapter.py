@@ -41,6 +41,8 @@ int main() {
     std::printf("intersect without device: %s\n", h ? "hit" : "nullopt");
     try { auto img = render_frame<b200_accel<float>, float>(a, scheduling_type::BUCKET_TILES); std::printf("render_frame: %zu rows\n", img.get_height()); }
     catch (const std::exception& e) { std::printf("render_frame: %s\n", e.what()); }
+    try { b200_frame_sequence<float> seq(a); seq.submit(); seq.submit(); auto img = seq.next(); std::printf("sequence: %zu rows\n", img.get_height()); }
+    catch (const std::exception& e) { std::printf("sequence: %s\n", e.what()); }
     return 0;
 }
 '''
@@ -64,3 +66,4 @@ def test_adapter_compiles_against_reference_and_dispatches(rt, tmp_path):
         assert "intersect without device: nullopt" in out
         # the device overload was chosen (the generic CPU render_frame would have returned 4 rows)
         assert "render_frame: b200 render_frame: no usable sm_100 CUDA device" in out
+        assert "sequence: b200" in out and "rows" not in out.split("sequence:")[1]
