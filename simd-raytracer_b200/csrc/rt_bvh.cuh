@@ -74,7 +74,27 @@ struct BvhState {
 
 constexpr float BVH_SLACK = 1e-5f;
 
+// RT_BVH_FMA_SLAB: slab test as one fused multiply-add per plane, t = l * (1/d) - o * (1/d), and no relative widening.
+// The box tests only have to be conservative, and the builder pads every box by 2e-5 of the scene scale: the error of this
+// form is <= |o| * 2^-23 (+ the 1-ulp reciprocal, a relative error of t that moves entry and exit together) in space units,
+// far inside the padding as long as the origin is within BVH_FAR_ORIGIN scene extents of the scene box; rays from farther
+// away are answered by the reference-order traversal (bvh_init marks them KD_RERUN).
+#ifndef RT_BVH_FMA_SLAB
+#define RT_BVH_FMA_SLAB 1
+#endif
+constexpr float BVH_FAR_ORIGIN = 8.0f;
+
 // entry and exit parameter of the ray in a box; entry clamped to 0, NaNs (0 * inf) ignored
+#if RT_BVH_FMA_SLAB
+RT_HD void bvh_slab(float ix, float iy, float iz, float cx, float cy, float cz, float lx, float ly, float lz, float hx, float hy, float hz,
+                    float& t_in, float& t_out) {
+    const float ax = kd_fma(lx, ix, cx), bx = kd_fma(hx, ix, cx);
+    const float ay = kd_fma(ly, iy, cy), by = kd_fma(hy, iy, cy);
+    const float az = kd_fma(lz, iz, cz), bz = kd_fma(hz, iz, cz);
+    t_in = bvh_max(bvh_max(bvh_min(ax, bx), bvh_min(ay, by)), bvh_max(bvh_min(az, bz), 0.0f));
+    t_out = bvh_min(bvh_min(bvh_max(ax, bx), bvh_max(ay, by)), bvh_max(az, bz));
+}
+#else
 RT_HD void bvh_slab(const BvhState& s, float ix, float iy, float iz, float lx, float ly, float lz, float hx, float hy, float hz,
                     float& t_in, float& t_out) {
     const float ax = (lx - s.ox) * ix, bx = (hx - s.ox) * ix;
@@ -83,6 +103,7 @@ RT_HD void bvh_slab(const BvhState& s, float ix, float iy, float iz, float lx, f
     t_in = bvh_max(bvh_max(bvh_min(ax, bx), bvh_min(ay, by)), bvh_max(bvh_min(az, bz), 0.0f));
     t_out = bvh_min(bvh_min(bvh_max(ax, bx), bvh_max(ay, by)), bvh_max(az, bz));
 }
+#endif
 
 // returns false when the ray misses the scene (the query is then finished: a miss).  ref_min / ref_max is the REFERENCE's
 // root box (union of the mesh boxes, kd_tree_simd.hpp:101-104) and the test is the reference's own slab arithmetic with its
@@ -107,21 +128,62 @@ RT_HD bool bvh_init(BvhState& s, const float* ref_min, const float* ref_max, flo
     // tests then depends on its own leaf boxes, so such rays (rare) are answered by the reference-order traversal: the lane
     // finishes at once with the KD_RERUN mark
     if (!(0.0f < t1)) { s.best.tri = KD_RERUN; return true; }
+#if RT_BVH_FMA_SLAB
+    {   // l * inf - o * inf is NaN where (l - o) * inf is a signed infinity: a ray parallel to an axis (a direction component that
+        // is zero or flushes to zero in rcp.approx.ftz) is answered by the reference-order traversal
+        constexpr float TINY = 1e-30f;
+        if (!(fabsf(dx) >= TINY) | !(fabsf(dy) >= TINY) | !(fabsf(dz) >= TINY)) { s.best.tri = KD_RERUN; return true; }
+    }
+    {   // an origin many scene extents away (or not finite): the padded boxes no longer cover the slab rounding
+        const float ext = kd_max(kd_max(ref_max[0] - ref_min[0], ref_max[1] - ref_min[1]), ref_max[2] - ref_min[2]) * BVH_FAR_ORIGIN;
+        const float far = kd_max(kd_max(kd_max(ref_min[0] - ox, ox - ref_max[0]), kd_max(ref_min[1] - oy, oy - ref_max[1])),
+                                 kd_max(ref_min[2] - oz, oz - ref_max[2]));
+        if (!(far <= ext)) { s.best.tri = KD_RERUN; return true; }
+    }
+#endif
     s.phase = KD8_WALK;
     return true;
 }
 
-RT_HD void bvh_pop(BvhState& s, const BvhStackEntry* stack) {
+// Next subtree from the stack.  An entry whose box starts beyond the closest hit so far is dropped HERE, so the entry
+// parameter of the current node never has to live in the traversal state: a node reached by descending was tested against the
+// same limit a moment ago.  At most RT_BVH_POP_CULL entries are looked at per call (in lock step a longer loop would stall the
+// whole warp behind one lane that is emptying its stack); if all of them were dropped the lane stands at the pseudo node
+// BVH_SKIP and goes on dropping at its next node step.  RT_BVH_POP_CULL = 0: the older form, s.t0 re-checked at every step.
+#ifndef RT_BVH_POP_CULL
+#define RT_BVH_POP_CULL 2
+#endif
+constexpr uint32_t BVH_SKIP = 0xFFFFFFFEu;
+RT_HD void bvh_pop(BvhState& s, const BvhStackEntry* stack, float lim) {
+#if RT_BVH_POP_CULL
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < RT_BVH_POP_CULL; ++k) {
+        if (!s.sp) { s.phase = KD8_DONE; return; }
+        --s.sp;
+        float t0;
+        bvh_stack_get(stack + s.sp, s.ref, s.cnt, t0);
+        if (!(t0 > lim)) { s.phase = s.cnt ? KD8_LEAF : KD8_WALK; return; }
+    }
+    s.ref = BVH_SKIP; s.cnt = 0; s.phase = KD8_WALK;
+#else
+    (void)lim;
     if (!s.sp) { s.phase = KD8_DONE; return; }
     --s.sp;
     bvh_stack_get(stack + s.sp, s.ref, s.cnt, s.t0);
     s.phase = s.cnt ? KD8_LEAF : KD8_WALK;
+#endif
 }
 
 // One inner-node visit (phase WALK): test both children's boxes, go to the nearer one, push the other.
 RT_HD void bvh_node_step(BvhState& s, BvhStackEntry* stack, const float* __restrict__ nodes) {
     const float lim = kd_min(s.best.t, s.t_far);
+#if RT_BVH_POP_CULL
+    bool pop = s.ref == BVH_SKIP;                                            // still dropping stack entries (bvh_pop)
+#else
     bool pop = s.t0 > lim;                                                   // the box starts beyond the closest hit so far
+#endif
     if (!pop) {
         BVH_COUNT_NODE();
         const float* p = nodes + size_t(s.ref) * 16u;
@@ -129,6 +191,16 @@ RT_HD void bvh_node_step(BvhState& s, BvhStackEntry* stack, const float* __restr
         // the 1-ulp reciprocal is enough under the box slack; a flushed subnormal component behaves like zero (parallel ray)
         const float ix = kd_rcp_estimate(s.dx), iy = kd_rcp_estimate(s.dy), iz = kd_rcp_estimate(s.dz);
         float in0, out0, in1, out1;
+#if RT_BVH_FMA_SLAB
+        const float cx = -(s.ox * ix), cy = -(s.oy * iy), cz = -(s.oz * iz);
+        bvh_slab(ix, iy, iz, cx, cy, cz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, in0, out0);
+        bvh_slab(ix, iy, iz, cx, cy, cz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, in1, out1);
+        const uint32_t ref0 = uint32_t(kd_as_int(q3.x)), ref1 = uint32_t(kd_as_int(q3.y));
+        const uint32_t cnt0 = uint32_t(kd_as_int(q3.z)), cnt1 = uint32_t(kd_as_int(q3.w));
+        const float e0 = in0, e1 = in1;
+        const bool hit0 = (cnt0 != BVH_NO_CHILD) & (e0 <= out0) & (e0 <= lim);
+        const bool hit1 = (cnt1 != BVH_NO_CHILD) & (e1 <= out1) & (e1 <= lim);
+#else
         bvh_slab(s, ix, iy, iz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, in0, out0);
         bvh_slab(s, ix, iy, iz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, in1, out1);
         const uint32_t ref0 = uint32_t(kd_as_int(q3.x)), ref1 = uint32_t(kd_as_int(q3.y));
@@ -136,26 +208,32 @@ RT_HD void bvh_node_step(BvhState& s, BvhStackEntry* stack, const float* __restr
         const float e0 = in0 * (1.0f - BVH_SLACK), e1 = in1 * (1.0f - BVH_SLACK);         // widened entry points (>= 0)
         const bool hit0 = (cnt0 != BVH_NO_CHILD) & (e0 <= out0 * (1.0f + BVH_SLACK)) & (e0 <= lim);
         const bool hit1 = (cnt1 != BVH_NO_CHILD) & (e1 <= out1 * (1.0f + BVH_SLACK)) & (e1 <= lim);
+#endif
         const bool first1 = hit1 & (!hit0 | (e1 < e0));                     // child 1 is visited first
         if (hit0 & hit1) { bvh_stack_put(stack + s.sp, first1 ? ref0 : ref1, first1 ? cnt0 : cnt1, first1 ? e0 : e1); ++s.sp; }
         pop = !(hit0 | hit1);
         s.ref = first1 ? ref1 : ref0;
         s.cnt = first1 ? cnt1 : cnt0;
+#if !RT_BVH_POP_CULL
         s.t0 = first1 ? e1 : e0;
+#endif
         s.phase = s.cnt ? KD8_LEAF : KD8_WALK;
     }
-    if (pop) bvh_pop(s, stack);
+    if (pop) bvh_pop(s, stack, lim);
 }
 
 // A leaf (phase LEAF): test its triangles, then pop the next subtree or finish.
 template <bool CULL, bool FAST>
 RT_HD void bvh_leaf_step(BvhState& s, const BvhStackEntry* stack, const float* __restrict__ tris, float eps) {
-    if (!(s.t0 > kd_min(s.best.t, s.t_far))) {
+#if !RT_BVH_POP_CULL
+    if (!(s.t0 > kd_min(s.best.t, s.t_far)))
+#endif
+    {
         BVH_COUNT_LEAF();
         kd_test_leaf<CULL, FAST>(tris + size_t(s.ref) * KD8_TRI_FLOATS, s.cnt, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
         if (s.any_hit && s.best.t <= s.t_far) { s.phase = KD8_DONE; return; }
     }
-    bvh_pop(s, stack);
+    bvh_pop(s, stack, kd_min(s.best.t, s.t_far));
 }
 
 // Closest hit with t <= t_far (t_far = FLT_MAX for a plain query).  any_hit: return at the first hit inside [.., t_far].

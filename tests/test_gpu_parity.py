@@ -81,6 +81,15 @@ def random_rays(n, seed, lo=-2.0, hi=2.0):
     rays[3, 3:] = (0, 0, 0)
     rays[4, :3] = np.nan
     rays[5, 3:] = (-0.0, 1, 0)
+    # nearly axis-parallel: a component that flushes to zero in rcp.approx.ftz, a denormal one, huge finite reciprocals
+    rays[6, 3:] = (1e-39, 0.6, 0.8)
+    rays[7, 3:] = (0.6, -1e-35, 0.8)
+    rays[8, 3:] = (0.6, 0.8, 1e-20)
+    rays[9, 3:] = (-1e-25, -1e-25, 1)
+    # axis-parallel rays from many origins (the special rows above start wherever the generator put them)
+    k = min(len(rays) // 4, 3000)
+    axes = np.eye(3, dtype=np.float32)[np.arange(k) % 3] * np.where(np.arange(k) % 2, -1.0, 1.0).astype(np.float32)[:, None]
+    rays[10:10 + k, 3:] = axes
     return rays
 
 

@@ -56,6 +56,9 @@ def scene_rays(o, s, n=150_000, seed=3):
     rays = np.concatenate([org, d], axis=1).astype(np.float32)
     rays[0, 3:] = (0, 0, -1); rays[1, 3:] = (1, 0, 0); rays[2, 3:] = (0, -1, 0); rays[3, 3:] = (0, 0, 0); rays[4, :3] = np.nan
     rays[5, 3:] = (-0.0, 1, 0); rays[6, :3] = c; rays[7, :3] = bx[0, :3]
+    rays[8, 3:] = (1e-39, 0.6, 0.8); rays[9, 3:] = (0.6, -1e-35, 0.8); rays[10, 3:] = (0.6, 0.8, 1e-20); rays[11, 3:] = (-1e-25, -1e-25, 1)
+    k = min(n // 4, 3000)                                  # axis-parallel rays from many origins
+    rays[12:12 + k, 3:] = np.eye(3, dtype=np.float32)[np.arange(k) % 3] * np.where(np.arange(k) % 2, -1.0, 1.0).astype(np.float32)[:, None]
     return rays
 
 
@@ -71,10 +74,11 @@ def test_kd8_equals_reference_traversal(rt, oracle_mod, kd8, name):
     for rays, cull in ((o.primary_rays(), True), (scene_rays(o, s), False)):
         want_tuv, want_tri = o.trace(rays, cull)
         tuv, tri, tie = kd8(s, rays, cull)
-        assert np.array_equal(tri >= 0, want_tri >= 0)
-        h = want_tri >= 0
+        rr = tri == -3                                      # KD_RERUN: handed to the reference-order traversal on the device
+        assert np.array_equal((tri >= 0)[~rr], (want_tri >= 0)[~rr])
+        h = (want_tri >= 0) & ~rr
         assert np.array_equal(tuv[h, 0].view(np.uint32), want_tuv[h, 0].view(np.uint32))
-        assert tie.mean() < 2e-3, (name, cull, tie.mean())
+        assert tie.mean() < (2e-3 if cull else 2.5e-2), (name, cull, tie.mean())     # incoherent set: 2 % axis-parallel rays are re-run
         assert np.array_equal(tri[~tie], want_tri[~tie])
         assert np.array_equal(tuv[h & ~tie].view(np.uint32), want_tuv[h & ~tie].view(np.uint32))
 
@@ -87,7 +91,8 @@ def test_kd8_synthetic_mesh(rt, oracle_mod, kd8, kd, accel):
     for rays, cull in ((o.primary_rays(), True), (scene_rays(o, s, 60_000), False)):
         want_tuv, want_tri = o.trace(rays, cull)
         tuv, tri, tie = kd8(s, rays, cull)
-        assert np.array_equal(tri[~tie], want_tri[~tie]) and np.array_equal(tri >= 0, want_tri >= 0)
+        rr = tri == -3
+        assert np.array_equal(tri[~tie], want_tri[~tie]) and np.array_equal((tri >= 0)[~rr], (want_tri >= 0)[~rr])
         h = (want_tri >= 0) & ~tie
         assert np.array_equal(tuv[h].view(np.uint32), want_tuv[h].view(np.uint32))
 
@@ -106,7 +111,9 @@ def test_kd8_any_hit_and_far_limit(rt, oracle_mod, kd8):
     assert np.array_equal(tri[inside], want_tri[inside]) and np.array_equal(tuv[inside, 0], want_tuv[inside, 0])
     assert not np.any((tri >= 0) & (tuv[:, 0] <= far) & ~((want_tri >= 0) & (want_tuv[:, 0] <= far)))
     tuv, tri, _ = kd8(s, rays, False, t_far=far, any_hit=True)
-    assert np.array_equal((tri >= 0) & (tuv[:, 0] <= far), (want_tri >= 0) & (want_tuv[:, 0] <= far))
+    rr = tri == -3                                          # KD_RERUN (axis-parallel rays): re-run in reference order on the device
+    assert rr.mean() < 0.05
+    assert np.array_equal(((tri >= 0) & (tuv[:, 0] <= far))[~rr], ((want_tri >= 0) & (want_tuv[:, 0] <= far))[~rr])
 
 
 def test_origin_on_split_planes_stays_cheap(rt, oracle_mod, kd8):
