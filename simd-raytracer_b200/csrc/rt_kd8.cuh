@@ -102,12 +102,13 @@ RT_HD void kd_test_tri(float v0x, float v0y, float v0z, float e1x, float e1y, fl
         const float pvy = dz * e2x - dx * e2z;                                                           // :28
         const float pvz = dx * e2y - dy * e2x;                                                           // :29
         const float det = e1x * pvx + e1y * pvy + e1z * pvz;                                             // :31
-        if (!(CULL ? (eps <= det) : (eps <= fabsf(det)))) return;                                        // :33-38
         const float tx = ox - v0x, ty = oy - v0y, tz = oz - v0z;                                         // :42-44
         const float un = tx * pvx + ty * pvy + tz * pvz;
         const float r = kd_rcp_estimate(det);
         const float ua = un * r;
-        if ((ua < -M) | (ua > 1.0f + M)) return;
+        // the determinant test (:33-38) rarely rejects: it shares the branch of the first pre-filter, so that the three rows of
+        // the triangle are loaded together instead of v0 waiting behind a branch of its own
+        if (!(CULL ? (eps <= det) : (eps <= fabsf(det))) | (ua < -M) | (ua > 1.0f + M)) return;
         const float qx = ty * e1z - tz * e1y;                                                            // :49
         const float qy = tz * e1x - tx * e1z;                                                            // :50
         const float qz = tx * e1y - ty * e1x;                                                            // :51
