@@ -1026,6 +1026,15 @@ int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t*
     });
 }
 
+#ifdef RT_STREAM_STATS
+// developer builds only (not declared in include/rt_b200.h): lane-occupancy counters of the stream kernels since the last reset
+extern "C" __attribute__((visibility("default"))) int rt_debug_stream_stats(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, rtb::g_stream_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return RT_ERR_CUDA;
+    if (reset) { unsigned long long z[16] = {}; if (cudaMemcpyToSymbol(rtb::g_stream_stats, z, sizeof z) != cudaSuccess) return RT_ERR_CUDA; }
+    return RT_OK;
+}
+#endif
+
 void* rt_alloc_pinned(uint64_t bytes) {
     void* p = nullptr;
     const cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);

@@ -31,6 +31,17 @@ constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node step
 constexpr int STREAM_LEAF_MIN = RT_STREAM_LEAF_MIN;          // run the leaf phase when this many lanes are parked (or nobody can walk on)
 constexpr int STREAM_REFILL_BELOW = RT_STREAM_REFILL_BELOW;  // go and fetch new queries when fewer lanes than this are traversing
 
+// RT_STREAM_STATS (developer builds only, scripts/gpu_stream_stats.py): where the lanes of a warp are while it executes node
+// steps and leaf phases.  [0] node-step slots, [1] lanes walking in them, [2] lanes parked at a leaf, [3] lanes finished and
+// waiting for the completion phase, [4] lanes without a query, [5] leaf phases, [6] lanes in them, [7] refill rounds,
+// [8] completion phases, [9] bursts
+#ifdef RT_STREAM_STATS
+__device__ unsigned long long g_stream_stats[16];
+#define STREAM_STAT(i, v) (stats[i] += (v))
+#else
+#define STREAM_STAT(i, v) ((void)0)
+#endif
+
 // The reference-order re-run of a tied query is rare; keeping it out of line keeps its register needs out of the hot loop.
 template <bool CULL, bool FAST>
 __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
@@ -53,12 +64,16 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
     st.ox = st.oy = st.oz = st.dx = st.dy = st.dz = 0.0f;
     bool busy = false, exhausted = false;
     uint32_t idx = 0;
+#ifdef RT_STREAM_STATS
+    unsigned long long stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (;;) {
         // ---- refill idle lanes ----
 #pragma unroll 1
         for (int round = 0; round < 8 && !exhausted; ++round) {
             const uint32_t idle = __ballot_sync(FULL, !busy);
             if (32 - __popc(idle) >= STREAM_REFILL_BELOW) break;
+            STREAM_STAT(7, 1);
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
             if (lane == uint32_t(leader)) base = atomicAdd(counter, uint32_t(__popc(idle)));
@@ -83,22 +98,35 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
             if (exhausted) break;
             continue;
         }
+        STREAM_STAT(9, 1);
         // ---- burst: lanes walk inner nodes in lock step (one node per step, the same code for every lane); a lane that
         // reaches a leaf parks, and parked lanes test their leaves together - neither phase runs with a handful of lanes ----
 #pragma unroll 1
         for (int it = 0; it < STREAM_BURST; ++it) {
 #pragma unroll 1
-            for (int k = 0; k < STREAM_NODE_STEPS; ++k)
+            for (int k = 0; k < STREAM_NODE_STEPS; ++k) {
+#ifdef RT_STREAM_STATS
+                const int nw = __popc(__ballot_sync(FULL, busy && st.phase == KD8_WALK));
+                if (nw) {
+                    stats[0] += 1; stats[1] += nw;
+                    stats[2] += __popc(__ballot_sync(FULL, busy && st.phase == KD8_LEAF));
+                    stats[3] += __popc(__ballot_sync(FULL, busy && st.phase == KD8_DONE));
+                    stats[4] += __popc(__ballot_sync(FULL, !busy));
+                }
+#endif
                 if (busy && st.phase == KD8_WALK) accel_node_step(st, stack, sc);
+            }
             const uint32_t parked = __ballot_sync(FULL, busy && st.phase == KD8_LEAF);
             const uint32_t walking = __ballot_sync(FULL, busy && st.phase == KD8_WALK);
             if (parked && (__popc(parked) >= STREAM_LEAF_MIN || !walking)) {
+                STREAM_STAT(5, 1); STREAM_STAT(6, __popc(parked));
                 if (busy && st.phase == KD8_LEAF) accel_leaf_step<CULL, FAST>(st, stack, sc, eps);
             }
             const int running = __popc(__ballot_sync(FULL, busy && st.phase != KD8_DONE));
             if (running == 0 || (!exhausted && running < STREAM_REFILL_BELOW)) break;
         }
         // ---- completion (warp-uniform) ----
+        STREAM_STAT(8, 1);
         const bool fin = busy && st.phase == KD8_DONE;
         Hit h; h.t = st.best.t; h.u = st.best.u; h.v = st.best.v; h.tri = st.best.tri;
         const bool tie = fin && (st.best.tri == KD_RERUN || (!st.any_hit && st.best.tri >= 0 && st.best.tie_t == st.best.t));
@@ -108,6 +136,10 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
         }
         if (fin) busy = p.finish(sc, idx, h, st);
     }
+#ifdef RT_STREAM_STATS
+    if (lane == 0)
+        for (int i = 0; i < 10; ++i) atomicAdd(&g_stream_stats[i], stats[i]);
+#endif
 }
 
 template <class T>
