@@ -111,6 +111,7 @@ struct rt_scene {
 
     // wavefront pools (grow-only, reused across frames)
     DBuf<Ray> rays; DBuf<Hit> hits; DBuf<Rec> recs; DBuf<ShadowJob> jobs;
+    DBuf<uint32_t> mask0;            // sparse level 0: one word per 8x4 pixel tile, bit = the camera ray hit something; zero between passes
     PassState* ps = nullptr;
     FrameCounters* fc = nullptr;
     uint32_t* h_flags = nullptr;     // pinned: pool_count, shadow_count, overflow of the last pass
@@ -153,7 +154,7 @@ struct rt_scene {
 
     std::mutex mtx;
     int g_primary[4] = {0, 0, 0, 0}, g_trace[4] = {0, 0, 0, 0}, g_shadow[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g_shade[2] = {0, 0}, g_resolve = 0;
-    int gs_primary[2] = {0, 0}, gs_level[2] = {0, 0}, gs_shadow[4] = {0, 0, 0, 0};   // stream kernels (accelerated mode)
+    int gs_primary[2] = {0, 0}, gs_sparse[2] = {0, 0}, gs_level[2] = {0, 0}, gs_shadow[4] = {0, 0, 0, 0};   // stream kernels (accelerated mode)
 
     ~rt_scene() {
         if (device >= 0) {
@@ -167,7 +168,7 @@ struct rt_scene {
                 if (q.h_fc) cudaFreeHost(q.h_fc);
                 q.fb.release();
             }
-            rays.release(); hits.release(); recs.release(); jobs.release(); fb.release(); fb8.release();
+            rays.release(); hits.release(); recs.release(); jobs.release(); mask0.release(); fb.release(); fb8.release();
             q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
             if (ps) cudaFree(ps);
             if (fc) cudaFree(fc);
@@ -459,6 +460,7 @@ void ensure_grids(rt_scene* s, Mode m, bool has_gi) {
     if (!s->g_shade[has_gi]) s->g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
     if (m.ordered) {
         if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>) : grid_for(s, k_stream_primary<false>);
+        if (!s->gs_sparse[fi]) s->gs_sparse[fi] = m.fast ? grid_for(s, k_stream_primary_sparse<true>) : grid_for(s, k_stream_primary_sparse<false>);
         if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>) : grid_for(s, k_stream_level<false>);
         if (!s->gs_shadow[fi * 2 + tr])
             s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>) : grid_for(s, k_stream_shadow<true, false>))
@@ -486,8 +488,10 @@ struct PassLaunch {
 // the overflow bits and the level count of the pass to `h_flags` (pinned host memory, 4 words).
 template <class Launch>
 void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_flags, cudaStream_t st, Launch&& launch) {
-    const FrameParams& fp = P.fp;
+    FrameParams fp = P.fp;
     const Mode m = P.m;
+    // a one-sample pass that overwrites the framebuffer keeps only the HITS of its camera rays as level-0 entries (rt_stream.cuh)
+    fp.sparse0 = (m.ordered && fp.n_samples == 1 && P.first_pass) ? 1u : 0u;
     const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0), fi = m.fast ? 1 : 0;
     const bool tr = s->d.has_transmissive != 0, has_gi = P.has_gi;
     const uint32_t launched = P.launched, levels = P.levels;
@@ -496,7 +500,10 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     k_pass_init<<<1, 256, 0, st>>>(s->ps, n0);
     CK(cudaGetLastError());
     launch(TC_PRIMARY, [&] {
-        if (m.ordered) {
+        if (fp.sparse0) {
+            if (m.fast) k_stream_primary_sparse<true><<<s->gs_sparse[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
+            else k_stream_primary_sparse<false><<<s->gs_sparse[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
+        } else if (m.ordered) {
             if (m.fast) k_stream_primary<true><<<s->gs_primary[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
             else k_stream_primary<false><<<s->gs_primary[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
         } else if (m.fast) k_primary<true, false><<<s->g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
@@ -515,8 +522,8 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
             ++slot;
         }
         launch(TC_SHADE, [&] {
-            if (has_gi) k_shade<true><<<s->g_shade[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
-            else k_shade<false><<<s->g_shade[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot);
+            if (has_gi) k_shade<true><<<s->g_shade[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
+            else k_shade<false><<<s->g_shade[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
         });
         ++slot;
     }
@@ -543,9 +550,9 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         launch(TC_RESOLVE, [&] {
             if (lvl == 0 && fuse_acc)
                 k_resolve<true><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
-                                                              launched, levels);
+                                                              launched, levels, s->mask0.p);
             else
-                k_resolve<false><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels);
+                k_resolve<false><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels, nullptr);
         });
         ++slot;
     }
@@ -564,6 +571,11 @@ void reserve_pools(rt_scene* s, FrameParams& fp, uint64_t n0, uint32_t levels) {
     const uint64_t shadow_cap = uint64_t(double(n0) * s->shadow_factor * std::max<size_t>(s->host.lights.size(), 1)) + 1024;
     if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
     s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
+    if (s->mask0.cap < n0 / 32 + 1) {
+        s->mask0.reserve(n0 / 32 + 1);
+        CK(cudaMemset(s->mask0.p, 0, s->mask0.cap * sizeof(uint32_t)));
+        CK(cudaDeviceSynchronize());                      // the render streams do not synchronise with the null stream
+    }
     fp.pool_cap = uint32_t(std::min<uint64_t>(s->rays.cap, 0xFFFFFFFFull));
     fp.shadow_cap = uint32_t(std::min<uint64_t>(s->jobs.cap, 0xFFFFFFFFull));
 }

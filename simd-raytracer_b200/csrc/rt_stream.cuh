@@ -188,6 +188,59 @@ __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DS
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 
+// ---- primary rays, sparse level 0 ------------------------------------------------------------------------------------------
+// One-sample passes that overwrite the framebuffer (first_pass): a camera ray that hits nothing - 86 % of them on the dragon
+// scenes - is finished the moment its query is: the lane writes the miss colour of render.hpp:66-74 ((0 + background) / spp)
+// into the pixel and nothing else.  Only HITS become level-0 entries: ray and hit are stored at the entry's place in the
+// sample plane as before, and the entry's bit is set in `mask0` (one word per 8x4 pixel tile), so the level-0 shade and resolve
+// kernels skip every tile without a hit and never touch the entries of the misses.  Entries keep their pixel order (the
+// shadow jobs and child rays they spawn stay coherent).  The ray is the traversal state's own (st.o*, st.d*).
+struct SparsePrimaryPolicy {
+    const FrameParams* fp; Ray* rays; Hit* hits; uint32_t* mask0; float* fb;
+    V3 miss_rgb;
+    uint32_t n_rays = 0, n_hits = 0;
+    __device__ __forceinline__ bool load(const DScene& sc, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
+        uint32_t x, y;
+        if (!level0_pixel(*fp, i, x, y)) return false;                                                   // padding of the 8x4 tiles
+        float rx, ry; uint2 key;
+        primary_sample(sc, *fp, x, y, fp->sample_first, rx, ry, key);
+        camera_ray(sc, fp->tan_half_fov, rx, ry, o, d);
+        t_far = FLT_MAX; any_hit = false;
+        ++n_rays;
+        return true;
+    }
+    __device__ __forceinline__ void entered(uint32_t, V3, V3) {}
+    __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, AccelState& st) {
+        uint32_t x, y;
+        level0_pixel(*fp, i, x, y);
+        if (h.tri >= 0) {
+            float rx, ry; uint2 key;
+            primary_sample(sc, *fp, x, y, fp->sample_first, rx, ry, key);                                // the path key of the pixel
+            store_ray(rays + i, mk(st.ox, st.oy, st.oz), mk(st.dx, st.dy, st.dz), key);
+            store_hit(hits + i, h);
+            atomicOr(mask0 + (i >> 5), 1u << (i & 31u));
+            ++n_hits;
+        } else {
+            float* px = fb + (size_t(y) * sc.width + x) * 3;
+            px[0] = miss_rgb.x; px[1] = miss_rgb.y; px[2] = miss_rgb.z;
+        }
+        return false;
+    }
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+                                                               uint32_t* __restrict__ mask0, float* __restrict__ fb, int divide,
+                                                               PassState* __restrict__ ps, int work_slot) {
+    SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb;
+    // the operations k_resolve<true> performs for a miss of the first pass: (0 + background), divided once when the frame ends here
+    V3 m = mk(0.0f, 0.0f, 0.0f) + mk(sc.bg[0], sc.bg[1], sc.bg[2]);
+    if (divide) { const float div = float(fp.spp_total); m = mk(__fdiv_rn(m.x, div), __fdiv_rn(m.y, div), __fdiv_rn(m.z, div)); }
+    p.miss_rgb = m;
+    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], fp.plane, fp.eps);                               // render.hpp:64, culling ON
+    warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
+}
+
 // ---- level d >= 1 ------------------------------------------------------------------------------------------------------------
 struct LevelPolicy {
     const Ray* rays; Hit* hits; uint32_t begin;

@@ -41,6 +41,7 @@ struct FrameParams {
     uint32_t x0, y0, tw, th;            // tile rectangle
     uint32_t tiles_x, plane;            // 8x4 pixel tiles per row; entries per sample plane (= tiles * 32)
     uint32_t pool_cap, shadow_cap;
+    uint32_t sparse0, reserved;         // sparse0: only the HITS of the camera rays are level-0 entries (k_stream_primary_sparse)
 };
 
 struct FrameCounters {                  // device memory, reset at the start of every frame
@@ -301,13 +302,19 @@ __device__ __forceinline__ float sin_f(float x) { return float(sin(double(x))); 
 template <bool HAS_GI>
 __global__ void __launch_bounds__(256) k_shade(DScene sc, FrameParams fp, Ray* __restrict__ rays, const Hit* __restrict__ hits,
                                                Rec* __restrict__ recs, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
-                                               int level, int work_slot) {
+                                               int level, int work_slot, const uint32_t* __restrict__ mask0) {
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const float PI = 3.14159265358979323846f;
+    const bool sparse = level == 0 && fp.sparse0 != 0u;           // level 0 starts at entry 0: chunk c is tile c, mask0[c] its hits
     (void)work_slot;
     for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
-        const bool live = i < end;
+        bool live = i < end;
+        if (sparse) {
+            const uint32_t word = __ldg(mask0 + (base >> 5));
+            if (word == 0u) continue;                                                                    // warp-uniform: a tile without a hit
+            live = live && ((word >> (threadIdx.x & 31u)) & 1u);
+        }
 
         uint32_t kind = REC_DONE, n_child = 0, n_shadow = 0;
         float fresnel = 0.0f;
@@ -456,7 +463,11 @@ __device__ __forceinline__ V3 child_colour(const Rec* __restrict__ recs, uint32_
 template <bool ACC>
 __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec* __restrict__ recs, const ShadowJob* __restrict__ jobs,
                                                  PassState* __restrict__ ps, int level, int work_slot, float* __restrict__ fb,
-                                                 int first_pass, int divide, uint32_t launched, uint32_t total) {
+                                                 int first_pass, int divide, uint32_t launched, uint32_t total,
+                                                 uint32_t* __restrict__ mask0) {
+    // sparse level 0: the misses wrote their pixels in k_stream_primary_sparse, mask0[tile] holds the hits.  The word is cleared
+    // here, by its last reader, so the mask is all zero again when the pass ends (kept or discarded)
+    const bool sparse = ACC && fp.sparse0 != 0u;
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const V3 bg = mk(sc.bg[0], sc.bg[1], sc.bg[2]), black = mk(0.0f, 0.0f, 0.0f);
     (void)work_slot;
@@ -464,6 +475,13 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
     if (ACC) discard = ps->overflow != 0u || (launched < total && ps->pool_count > ps->lv[launched]);
     for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
+        if (sparse) {
+            const uint32_t word = mask0[base >> 5];
+            if (word == 0u) continue;                                                                    // warp-uniform
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0u) mask0[base >> 5] = 0u;
+            if (!((word >> (threadIdx.x & 31u)) & 1u)) continue;
+        }
         if (i >= end) continue;
         float4* p = reinterpret_cast<float4*>(recs + i);
         const float4 a = p[0];

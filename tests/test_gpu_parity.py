@@ -241,6 +241,29 @@ def test_textures_exact(rt, oracle_mod):
     assert np.array_equal(img.view(np.uint32), oi.view(np.uint32))
 
 
+def test_sparse_level0_equals_dense_frames(rt):
+    """accelerated mode, one-sample passes: camera rays that miss write their pixel at once and only hits become level-0
+    entries (k_stream_primary_sparse).  Same float frame and counts as the reference-order mode (dense level 0) for odd
+    frame sizes, tile rectangles that cut the 8x4 pixel tiles, raw sums (no divide), GI keys and a multi-sample frame whose
+    passes hold one sample each only when the budget forces it (dense accumulate path)."""
+    for name, size in (("hw09_scene5", (203, 117)), ("hw15_scene2", (97, 61))):
+        s, _ = gpu_scene(rt, name, size=size)
+        for kw in (dict(), dict(diffuse_reflection_ray_count=2, max_ray_depth=3), dict(flags=rt.FLAG_RAW_SUM, spp_total=3, sample_offset=1),
+                   dict(samples_per_pixel=2)):
+            flags = kw.pop("flags", 0)
+            want = s.render_frame(rt.default_params(flags=flags, **kw))
+            cw = s.counters()
+            got = s.render_frame(rt.default_params(flags=flags | rt.FLAG_ORDERED, **kw))
+            cg = s.counters()
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (name, kw)
+            assert (cw.primary, cw.primary_hits, cw.shadow, cw.secondary) == (cg.primary, cg.primary_hits, cg.shadow, cg.secondary)
+            tiled = np.full_like(want, -7.0)
+            W, H = size
+            for x0, y0, x1, y1 in ((0, 0, 77, H), (77, 0, W, 33), (77, 33, W, H)):
+                s.render_frame(rt.default_params(x0=x0, y0=y0, x1=x1, y1=y1, flags=flags | rt.FLAG_ORDERED, **kw), out=tiled)
+            assert np.array_equal(want.view(np.uint32), tiled.view(np.uint32)), (name, kw, "tiles")
+
+
 def test_depth_zero_and_empty_scene(rt):
     s, _ = gpu_scene(rt, "hw12_scene4", size=(64, 40))
     img = s.render_frame(rt.default_params(max_ray_depth=0))          # every hit returns the background (render.hpp:138)
