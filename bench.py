@@ -339,6 +339,16 @@ def main() -> None:
                 b.synchronize()
                 c = scene.counters()        # of the queued frame: device time of the render; no per-kernel events inside it
                 launches += c.kernel_launches + 3
+            elif world == 1:
+                # the frame is QUEUED (rt_render_frame_device_begin): no per-kernel timing events between its kernels, so the
+                # kernels of the pass chain through programmatic dependent launch exactly as they do in a frame sequence
+                a.record(stream)
+                t = scene.render_frame_device_begin(params, fb.data_ptr(), stream=stream.cuda_stream)
+                b.record(stream)
+                rerendered += bool(scene.frame_wait(t))
+                b.synchronize()
+                c = scene.counters()
+                launches += c.kernel_launches
             else:
                 a.record(stream)
                 frame_device()
@@ -358,6 +368,7 @@ def main() -> None:
         stream.wait_event(ev_done)
         pending[0] = False
         barrier()
+    if peer or world == 1:
         if rerendered:
             raise SystemExit("a timed frame had to be rendered again (pool overflow after warm-up): the measurement is void")
         # per-kernel-class times: the queued frames carry no per-kernel events, so the split comes from serial frames
@@ -508,7 +519,10 @@ def main() -> None:
                      "primary_mrays_s": c0.primary / cls["primary"] / 1e3 if cls["primary"] else None,
                      "shadow_mrays_s": c0.shadow / cls["shadow"] / 1e3 if cls["shadow"] else None,
                      "secondary_mrays_s": c0.secondary / cls["secondary"] / 1e3 if cls["secondary"] else None,
-                     "ms": {k: v / K for k, v in acc.items()}},
+                     "ms": {k: v / K for k, v in acc.items()},
+                     "ms_source": ("per-class times from serial frames with a CUDA event pair around every launch (which also "
+                                   "switches programmatic dependent launch off between them); ms_per_step is the queued frame"
+                                   if (world == 1 or peer) else "CUDA event pair around every launch of the timed frames")},
             "e2e": {"value": rays_all * K / t_e2e / 1e6, "unit": "Mrays/s", "ms_per_frame": 1e3 * t_e2e / K,
                     "h2d_bytes_per_step": int(np.dtype(np.uint8).itemsize * __import__("ctypes").sizeof(rt.Params)),
                     "d2h_bytes_per_step": int(host.numel() * 4),

@@ -390,6 +390,7 @@ void launch_occluded_batch(rt_scene* s, const float* d_rays, const float* d_maxt
 }
 
 __global__ void k_pass_init(PassState* ps, uint32_t n0) {
+    pdl_wait();
     uint32_t* w = reinterpret_cast<uint32_t*>(ps);
     for (uint32_t i = threadIdx.x; i < sizeof(PassState) / 4; i += blockDim.x) w[i] = 0u;
     __syncthreads();
@@ -400,6 +401,7 @@ __global__ void k_pass_init(PassState* ps, uint32_t n0) {
 // same frame parameters left empty); if the last launched level spawned children after all, the pass is marked truncated
 // (overflow bit 4) and the host renders it again with every level.  out[3] = levels that held entries.
 __global__ void k_pass_commit(PassState* ps, FrameCounters* fc, uint32_t* out, uint32_t launched, uint32_t total) {
+    pdl_wait();
     uint32_t used = 0;
     for (uint32_t d = 0; d < launched; ++d)
         if (ps->lv[d + 1] > ps->lv[d]) used = d + 1;
@@ -486,6 +488,25 @@ struct PassLaunch {
 // Queues the kernels of one pass on `st` (nothing here waits for the device).  launch(class, f) issues f() - the synchronous
 // path wraps every launch in a pair of timing events, the frame-sequence path does not.  k_pass_commit publishes pool usage,
 // the overflow bits and the level count of the pass to `h_flags` (pinned host memory, 4 words).
+// Every kernel of a pass is launched with programmatic stream serialisation (programmatic dependent launch): the next kernel
+// of the stream is set up and its blocks take the SM slots the current kernel's blocks leave in its tail, and they wait in
+// pdl_wait() (rt_device.cuh, griddepcontrol.wait) until the current kernel has completed and its writes are visible.  What
+// this removes is the launch gap between the 7-25 dependent kernels of a frame.  RT_B200_NO_PDL=1 turns it off (A/B runs).
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("RT_B200_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <class... KArgs, class... Args>
+void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 template <class Launch>
 void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_flags, cudaStream_t st, Launch&& launch) {
     FrameParams fp = P.fp;
@@ -497,33 +518,33 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     const uint32_t launched = P.launched, levels = P.levels;
     const uint32_t n0 = fp.plane * fp.n_samples;
     int slot = 0;
-    k_pass_init<<<1, 256, 0, st>>>(s->ps, n0);
+    launch_k(k_pass_init, 1, 256, st, s->ps, n0);
     CK(cudaGetLastError());
     launch(TC_PRIMARY, [&] {
         if (fp.sparse0) {
-            if (m.fast) k_stream_primary_sparse<true><<<s->gs_sparse[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
-            else k_stream_primary_sparse<false><<<s->gs_sparse[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
+            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
+            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
         } else if (m.ordered) {
-            if (m.fast) k_stream_primary<true><<<s->gs_primary[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-            else k_stream_primary<false><<<s->gs_primary[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-        } else if (m.fast) k_primary<true, false><<<s->g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-        else k_primary<false, false><<<s->g_primary[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            if (m.fast) launch_k(k_stream_primary<true>, s->gs_primary[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            else launch_k(k_stream_primary<false>, s->gs_primary[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+        } else if (m.fast) launch_k(k_primary<true, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+        else launch_k(k_primary<false, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
     });
     ++slot;
     for (uint32_t lvl = 0; lvl < launched; ++lvl) {
         if (lvl > 0) {
             launch(TC_SECONDARY, [&] {
                 if (m.ordered) {
-                    if (m.fast) k_stream_level<true><<<s->gs_level[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                    else k_stream_level<false><<<s->gs_level[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                } else if (m.fast) k_trace_level<true, false><<<s->g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                else k_trace_level<false, false><<<s->g_trace[mi], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    if (m.fast) launch_k(k_stream_level<true>, s->gs_level[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    else launch_k(k_stream_level<false>, s->gs_level[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                } else if (m.fast) launch_k(k_trace_level<true, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                else launch_k(k_trace_level<false, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
             });
             ++slot;
         }
         launch(TC_SHADE, [&] {
-            if (has_gi) k_shade<true><<<s->g_shade[1], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
-            else k_shade<false><<<s->g_shade[0], 256, 0, st>>>(s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
+            if (has_gi) launch_k(k_shade<true>, s->g_shade[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
+            else launch_k(k_shade<false>, s->g_shade[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
         });
         ++slot;
     }
@@ -531,16 +552,16 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         launch(TC_SHADOW, [&] {
             if (m.ordered) {
                 const int g = s->gs_shadow[fi * 2 + tr];
-                if (tr) { if (m.fast) k_stream_shadow<true, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                          else k_stream_shadow<true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
-                else { if (m.fast) k_stream_shadow<false, true><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                       else k_stream_shadow<false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                if (tr) { if (m.fast) launch_k(k_stream_shadow<true, true>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
+                          else launch_k(k_stream_shadow<true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
+                else { if (m.fast) launch_k(k_stream_shadow<false, true>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
+                       else launch_k(k_stream_shadow<false, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
             } else {
                 const int g = s->g_shadow[mi * 2 + tr];
-                if (tr) { if (m.fast) k_shadow<true, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                          else k_shadow<true, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
-                else { if (m.fast) k_shadow<false, true, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot);
-                       else k_shadow<false, false, false><<<g, 256, 0, st>>>(s->d, fp, s->jobs.p, s->ps, slot); }
+                if (tr) { if (m.fast) launch_k(k_shadow<true, true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
+                          else launch_k(k_shadow<true, false, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
+                else { if (m.fast) launch_k(k_shadow<false, true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
+                       else launch_k(k_shadow<false, false, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
             }
         });
         ++slot;
@@ -549,19 +570,19 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
         launch(TC_RESOLVE, [&] {
             if (lvl == 0 && fuse_acc)
-                k_resolve<true><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
+                launch_k(k_resolve<true>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
                                                               launched, levels, s->mask0.p);
             else
-                k_resolve<false><<<s->g_resolve, 256, 0, st>>>(s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels, nullptr);
+                launch_k(k_resolve<false>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels, nullptr);
         });
         ++slot;
     }
-    k_pass_commit<<<1, 1, 0, st>>>(s->ps, s->fc, h_flags, launched, levels);
+    launch_k(k_pass_commit, 1, 1, st, s->ps, s->fc, h_flags, launched, levels);
     CK(cudaGetLastError());
     // the accumulate kernel skips itself on the device when the pass overflowed its pools
     if (!fuse_acc)
         launch(TC_RESOLVE, [&] {
-            k_accumulate<<<(fp.plane + 255) / 256, 256, 0, st>>>(s->d, fp, s->recs.p, d_rgb, s->ps, P.first_pass, P.divide);
+            launch_k(k_accumulate, (fp.plane + 255) / 256, 256, st, s->d, fp, s->recs.p, d_rgb, s->ps, P.first_pass, P.divide);
         });
 }
 

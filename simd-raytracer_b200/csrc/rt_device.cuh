@@ -17,6 +17,17 @@
 
 namespace rtb {
 
+// Programmatic dependent launch (rt_api.cu launch_k): first statement of every kernel of a pass.  Waits until the kernel in
+// front of this one in the stream has completed and its writes are visible, then lets the next kernel of the stream be set up.
+// A no-op when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+
 // ---- resident scene (all pointers into HBM) -------------------------------------------------------------------
 struct DMaterial { uint32_t kind; float albedo[3]; float ior; uint32_t smooth; int32_t texture; };       // 28 B
 struct DTexture { uint32_t kind; float c0[3], c1[3], scalar; uint32_t w, h, off; };                      // 44 B

@@ -183,6 +183,7 @@ struct PrimaryPolicy {
 template <bool FAST>
 __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                         PassState* __restrict__ ps, int work_slot) {
+    pdl_wait();
     PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
     stream_loop<true, FAST>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
@@ -232,6 +233,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                                uint32_t* __restrict__ mask0, float* __restrict__ fb, int divide,
                                                                PassState* __restrict__ ps, int work_slot) {
+    pdl_wait();
     SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb;
     // the operations k_resolve<true> performs for a miss of the first pass: (0 + background), divided once when the frame ends here
     V3 m = mk(0.0f, 0.0f, 0.0f) + mk(sc.bg[0], sc.bg[1], sc.bg[2]);
@@ -263,6 +265,7 @@ struct LevelPolicy {
 template <bool FAST>
 __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                       PassState* __restrict__ ps, int level, int work_slot) {
+    pdl_wait();
     const uint32_t begin = ps->lv[level];
     const uint32_t end = min(ps->pool_count, fp.pool_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) ps->lv[level + 1] = end;
@@ -322,6 +325,7 @@ struct ShadowPolicy {
 template <bool TRANSMISSIVE, bool FAST>
 __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                        int work_slot) {
+    pdl_wait();
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
     ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.shadow_bias = fp.shadow_bias;
     p.n_lights = sc.n_lights; p.n_jobs = end;

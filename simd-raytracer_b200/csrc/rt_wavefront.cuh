@@ -152,6 +152,7 @@ __device__ __forceinline__ bool level0_pixel(const FrameParams& fp, uint32_t j, 
 template <bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                  PassState* __restrict__ ps, int work_slot) {
+    pdl_wait();
     FrameCounters* fc = &ps->pc;
     const uint32_t n0 = fp.plane * fp.n_samples;
     unsigned long long n_rays = 0, n_hits = 0;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) k_primary(DScene sc, FrameParams fp, Ray*
 template <bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_trace_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                      PassState* __restrict__ ps, int level, int work_slot) {
+    pdl_wait();
     FrameCounters* fc = &ps->pc;
     const uint32_t begin = ps->lv[level];
     const uint32_t end = min(ps->pool_count, fp.pool_cap);
@@ -247,6 +249,7 @@ __device__ __forceinline__ bool occluded_query(const DScene& sc, bool active, V3
 template <bool TRANSMISSIVE, bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                 int work_slot) {
+    pdl_wait();
     FrameCounters* fc = &ps->pc;
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
     unsigned long long n_q = 0, n_h = 0;
@@ -303,6 +306,7 @@ template <bool HAS_GI>
 __global__ void __launch_bounds__(256) k_shade(DScene sc, FrameParams fp, Ray* __restrict__ rays, const Hit* __restrict__ hits,
                                                Rec* __restrict__ recs, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                int level, int work_slot, const uint32_t* __restrict__ mask0) {
+    pdl_wait();
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const float PI = 3.14159265358979323846f;
     const bool sparse = level == 0 && fp.sparse0 != 0u;           // level 0 starts at entry 0: chunk c is tile c, mask0[c] its hits
@@ -465,6 +469,7 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
                                                  PassState* __restrict__ ps, int level, int work_slot, float* __restrict__ fb,
                                                  int first_pass, int divide, uint32_t launched, uint32_t total,
                                                  uint32_t* __restrict__ mask0) {
+    pdl_wait();
     // sparse level 0: the misses wrote their pixels in k_stream_primary_sparse, mask0[tile] holds the hits.  The word is cleared
     // here, by its last reader, so the mask is all zero again when the pass ends (kept or discarded)
     const bool sparse = ACC && fp.sparse0 != 0u;
@@ -537,6 +542,7 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
 // render.hpp:66-74: per pixel, samples are summed in order and divided by samples_per_pixel once
 __global__ void __launch_bounds__(256) k_accumulate(DScene sc, FrameParams fp, const Rec* __restrict__ recs, float* __restrict__ fb,
                                                     const PassState* __restrict__ ps, int first_pass, int divide) {
+    pdl_wait();
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= fp.plane || ps->overflow) return;      // an overflowed pass is discarded and rendered again by the host
     uint32_t x, y;
