@@ -111,6 +111,7 @@ struct rt_scene {
 
     // wavefront pools (grow-only, reused across frames)
     DBuf<Ray> rays; DBuf<Hit> hits; DBuf<Rec> recs; DBuf<ShadowJob> jobs;
+    DBuf<uint32_t> tiles0;           // sparse level 0: the tiles k_tile_cull kept
     DBuf<uint32_t> mask0;            // sparse level 0: one word per 8x4 pixel tile, bit = the camera ray hit something; zero between passes
     PassState* ps = nullptr;
     FrameCounters* fc = nullptr;
@@ -168,7 +169,7 @@ struct rt_scene {
                 if (q.h_fc) cudaFreeHost(q.h_fc);
                 q.fb.release();
             }
-            rays.release(); hits.release(); recs.release(); jobs.release(); mask0.release(); fb.release(); fb8.release();
+            rays.release(); hits.release(); recs.release(); jobs.release(); mask0.release(); tiles0.release(); fb.release(); fb8.release();
             q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
             if (ps) cudaFree(ps);
             if (fc) cudaFree(fc);
@@ -520,10 +521,19 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     int slot = 0;
     launch_k(k_pass_init, 1, 256, st, s->ps, n0);
     CK(cudaGetLastError());
+    // a camera outside the scene's root box: tiles whose rays cannot reach the box are finished by k_tile_cull (rt_stream.cuh)
+    bool cull_tiles = false;
+    if (fp.sparse0)
+        for (int k = 0; k < 3; ++k) cull_tiles = cull_tiles || !(s->d.root_min[k] <= s->d.cam_pos[k] && s->d.cam_pos[k] <= s->d.root_max[k]);
+    if (cull_tiles)
+        launch(TC_PRIMARY, [&] {
+            launch_k(k_tile_cull, std::min<unsigned>((fp.plane / 32 + 255) / 256, unsigned(s->g_resolve)), 256, st, s->d, fp, d_rgb, P.divide, s->ps, s->tiles0.p);
+        });
     launch(TC_PRIMARY, [&] {
         if (fp.sparse0) {
-            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
-            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot);
+            const uint32_t* tiles = cull_tiles ? s->tiles0.p : nullptr;
+            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot, tiles);
+            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot, tiles);
         } else if (m.ordered) {
             if (m.fast) launch_k(k_stream_primary<true>, s->gs_primary[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
             else launch_k(k_stream_primary<false>, s->gs_primary[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
@@ -592,6 +602,7 @@ void reserve_pools(rt_scene* s, FrameParams& fp, uint64_t n0, uint32_t levels) {
     const uint64_t shadow_cap = uint64_t(double(n0) * s->shadow_factor * std::max<size_t>(s->host.lights.size(), 1)) + 1024;
     if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
     s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
+    s->tiles0.reserve(n0 / 32 + 1);
     if (s->mask0.cap < n0 / 32 + 1) {
         s->mask0.reserve(n0 / 32 + 1);
         CK(cudaMemset(s->mask0.p, 0, s->mask0.cap * sizeof(uint32_t)));

@@ -198,9 +198,11 @@ __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DS
 // shadow jobs and child rays they spawn stay coherent).  The ray is the traversal state's own (st.o*, st.d*).
 struct SparsePrimaryPolicy {
     const FrameParams* fp; Ray* rays; Hit* hits; uint32_t* mask0; float* fb;
+    const uint32_t* tile_list;          // tiles k_tile_cull kept (work item i = pixel i & 31 of tile tile_list[i >> 5]), or null: every tile
     V3 miss_rgb;
     uint32_t n_rays = 0, n_hits = 0;
     __device__ __forceinline__ bool load(const DScene& sc, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
+        if (tile_list) i = __ldg(tile_list + (i >> 5)) * 32u + (i & 31u);
         uint32_t x, y;
         if (!level0_pixel(*fp, i, x, y)) return false;                                                   // padding of the 8x4 tiles
         float rx, ry; uint2 key;
@@ -229,17 +231,93 @@ struct SparsePrimaryPolicy {
     }
 };
 
+// the operations k_resolve<true> performs for a miss of the first pass: (0 + background), divided once when the frame ends here
+__device__ __forceinline__ V3 first_pass_miss_colour(const DScene& sc, const FrameParams& fp, int divide) {
+    V3 m = mk(0.0f, 0.0f, 0.0f) + mk(sc.bg[0], sc.bg[1], sc.bg[2]);
+    if (divide) { const float div = float(fp.spp_total); m = mk(__fdiv_rn(m.x, div), __fdiv_rn(m.y, div), __fdiv_rn(m.z, div)); }
+    return m;
+}
+
+// ---- tile culling in front of the sparse primary kernel -----------------------------------------------------------------------
+// The camera rays of an 8x4 pixel tile (any sample position inside the pixels) lie in the pyramid spanned by the directions
+// through the tile's four corners: the un-normalised direction is affine in the raster position (render.hpp:47-60).  If the
+// scene's root box lies outside one of the pyramid's four side planes, no ray of the tile can enter it, and every such ray is a
+// miss in the reference too (its first act is the slab test of the root box, kd_tree_simd.hpp:200-203).  The test is
+// conservative by a margin of 1e-3 of the camera-to-box distance - about half a pixel at 1080p, a thousand times the rounding
+// of the reference's slab test and of this plane arithmetic - so tiles that graze the box are traced as before.  A NaN
+// anywhere keeps the tile.  Culled tiles get their miss colour here; the tiles that remain are listed for the stream kernel.
+__device__ __forceinline__ V3 tile_corner_dir(const DScene& sc, float tan_half_fov, float x, float y) {
+    const float aspect = float(sc.width) / float(sc.height);
+    const float sx = ((2.0f * (x / float(sc.width))) - 1.0f) * aspect * tan_half_fov;
+    const float sy = (1.0f - (2.0f * (y / float(sc.height)))) * tan_half_fov;
+    const float* m = sc.cam_m;
+    return mk(m[0] * sx + m[3] * sy - m[6], m[1] * sx + m[4] * sy - m[7], m[2] * sx + m[5] * sy - m[8]);
+}
+__device__ __forceinline__ bool tile_misses_box(const DScene& sc, const FrameParams& fp, float x0, float y0, float x1, float y1) {
+    const float th = float(fp.tan_half_fov);
+    const V3 c[4] = {tile_corner_dir(sc, th, x0, y0), tile_corner_dir(sc, th, x1, y0), tile_corner_dir(sc, th, x1, y1),
+                     tile_corner_dir(sc, th, x0, y1)};
+    const V3 centre = (c[0] + c[1]) + (c[2] + c[3]);
+    const V3 o = mk(sc.cam_pos[0], sc.cam_pos[1], sc.cam_pos[2]);
+    const V3 lo = mk(sc.root_min[0], sc.root_min[1], sc.root_min[2]) - o, hi = mk(sc.root_max[0], sc.root_max[1], sc.root_max[2]) - o;
+    const float reach = fmaxf(fabsf(lo.x), fabsf(hi.x)) + fmaxf(fabsf(lo.y), fabsf(hi.y)) + fmaxf(fabsf(lo.z), fabsf(hi.z));
+    bool outside = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        V3 n = cross(c[e], c[(e + 1) & 3]);
+        if (dot(n, centre) > 0.0f) n = -n;                                       // the pyramid is the side n . p <= 0
+        // the box corner that is deepest on the pyramid's side of the plane
+        const float d = n.x * (n.x > 0.0f ? lo.x : hi.x) + n.y * (n.y > 0.0f ? lo.y : hi.y) + n.z * (n.z > 0.0f ? lo.z : hi.z);
+        outside = outside || (d > 1e-3f * reach * __fsqrt_rn(len2(n)));
+    }
+    return outside;
+}
+
+__global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, float* __restrict__ fb, int divide, PassState* __restrict__ ps,
+                                                   uint32_t* __restrict__ tile_list) {
+    pdl_wait();
+    const uint32_t n_tiles = fp.plane >> 5, lane = threadIdx.x & 31u, FULL = 0xFFFFFFFFu;
+    const V3 miss = first_pass_miss_colour(sc, fp, divide);
+    uint32_t n_culled = 0;
+    for (uint32_t base = first_chunk(); base < n_tiles; base += chunk_stride()) {                        // 32 tiles per warp and round
+        const uint32_t t = base + lane;
+        uint32_t lx0 = 0, ly0 = 0, w = 0, h = 0;
+        bool cull = false;
+        if (t < n_tiles) {
+            lx0 = (t % fp.tiles_x) * 8u; ly0 = (t / fp.tiles_x) * 4u;
+            w = min(8u, fp.tw - lx0); h = min(4u, fp.th - ly0);
+            cull = tile_misses_box(sc, fp, float(fp.x0 + lx0), float(fp.y0 + ly0), float(fp.x0 + lx0 + w), float(fp.y0 + ly0 + h));
+        }
+        const uint32_t keep = __ballot_sync(FULL, t < n_tiles && !cull);
+        uint32_t slot = 0;
+        if (lane == 0 && keep) slot = atomicAdd(&ps->n_tiles0, uint32_t(__popc(keep)));
+        slot = __shfl_sync(FULL, slot, 0);
+        if (t < n_tiles && !cull) tile_list[slot + uint32_t(__popc(keep & ((1u << lane) - 1u)))] = t;
+        // culled tiles, one at a time, the warp's lanes being the tile's 32 pixels
+        uint32_t todo = __ballot_sync(FULL, cull);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t px = __shfl_sync(FULL, lx0, src) + (lane & 7u), py = __shfl_sync(FULL, ly0, src) + (lane >> 3);
+            const uint32_t tw = __shfl_sync(FULL, w, src), tht = __shfl_sync(FULL, h, src);
+            if ((lane & 7u) < tw && (lane >> 3) < tht) {
+                float* q = fb + (size_t(fp.y0 + py) * sc.width + (fp.x0 + px)) * 3;
+                q[0] = miss.x; q[1] = miss.y; q[2] = miss.z;
+                ++n_culled;
+            }
+        }
+    }
+    warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, n_culled, 0u);
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                                uint32_t* __restrict__ mask0, float* __restrict__ fb, int divide,
-                                                               PassState* __restrict__ ps, int work_slot) {
+                                                               PassState* __restrict__ ps, int work_slot, const uint32_t* __restrict__ tile_list) {
     pdl_wait();
-    SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb;
-    // the operations k_resolve<true> performs for a miss of the first pass: (0 + background), divided once when the frame ends here
-    V3 m = mk(0.0f, 0.0f, 0.0f) + mk(sc.bg[0], sc.bg[1], sc.bg[2]);
-    if (divide) { const float div = float(fp.spp_total); m = mk(__fdiv_rn(m.x, div), __fdiv_rn(m.y, div), __fdiv_rn(m.z, div)); }
-    p.miss_rgb = m;
-    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], fp.plane, fp.eps);                               // render.hpp:64, culling ON
+    SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb; p.tile_list = tile_list;
+    p.miss_rgb = first_pass_miss_colour(sc, fp, divide);
+    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], tile_list ? ps->n_tiles0 * 32u : fp.plane, fp.eps);   // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 

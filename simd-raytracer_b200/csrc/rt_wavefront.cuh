@@ -49,7 +49,8 @@ struct FrameCounters {                  // device memory, reset at the start of 
 };
 
 struct PassState {                      // device memory, reset at the start of every pass
-    uint32_t pool_count, shadow_count, overflow, pad;
+    uint32_t pool_count, shadow_count, overflow;
+    uint32_t n_tiles0;                  // sparse level 0: tiles k_tile_cull left for the primary stream kernel
     uint32_t lv[MAX_LEVELS + 2];        // level d = pool entries [lv[d], lv[d+1])
     uint32_t work[N_WORK];
     FrameCounters pc;                   // this pass's ray counts; folded into the frame's when the pass is kept

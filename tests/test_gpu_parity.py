@@ -264,6 +264,40 @@ def test_sparse_level0_equals_dense_frames(rt):
             assert np.array_equal(want.view(np.uint32), tiled.view(np.uint32)), (name, kw, "tiles")
 
 
+def test_tile_culling_is_conservative(rt):
+    """k_tile_cull finishes 8x4 pixel tiles whose camera rays cannot reach the scene's root box.  A small constant-colour
+    quad seen by rotated / sheared cameras from many positions (box in a corner of the frame, partly off-screen, behind the
+    camera, camera on the box's faces): every pixel the exact primary query reports as a hit must carry the quad's colour, every
+    other pixel the background - culling a tile one of whose rays hits would leave a background pixel there."""
+    rng = np.random.default_rng(7)
+    v = np.asarray([[-0.3, -0.2, 0.0], [0.3, -0.2, 0.0], [0.3, 0.2, 0.05], [-0.3, 0.2, 0.05]], np.float32)
+    tri = np.asarray([[0, 1, 2], [0, 2, 3], [2, 1, 0], [3, 2, 0]], np.uint32)          # both windings: culling ON still sees a face
+    bg, col = (0.125, 0.25, 0.5), (0.9, 0.8, 0.7)
+    checked = hits_seen = 0
+    for k in range(24):
+        ang = rng.uniform(-1.2, 1.2, 3)
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        R = (np.asarray([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]) @ np.asarray([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+             np.asarray([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]))
+        if k % 5 == 4:
+            R = R @ np.asarray([[1.0, 0.3, 0.0], [0.0, 0.8, 0.0], [0.1, 0.0, 1.2]])     # not a rotation: the argument is affine only
+        pos = rng.uniform(-1.5, 1.5, 3) if k % 6 else np.asarray([0.3, rng.uniform(-0.2, 0.2), 0.02])   # k % 6 == 0: on the box's face
+        size = [(64, 40), (203, 117), (97, 61)][k % 3]
+        s = rt.Scene.from_arrays(width=size[0], height=size[1], background=bg, camera_position=tuple(pos), camera_matrix=tuple(R.reshape(-1)),
+                                 materials=[dict(kind=3, albedo=col)], meshes=[(0, v, None, tri)])
+        for fov in (40.0, 90.0, 140.0):
+            p = rt.default_params(flags=rt.FLAG_ORDERED, fov_degrees=fov)
+            img = s.render_frame(p)
+            hit = s.trace_primary(rt.default_params(fov_degrees=fov))["tri"].reshape(size[1], size[0]) >= 0
+            want = np.where(hit[..., None], np.asarray(col, np.float32), np.asarray(bg, np.float32))
+            assert np.array_equal(img, want), (k, fov)
+            c = s.counters()
+            assert (c.primary, c.primary_hits) == (size[0] * size[1], int(hit.sum()))
+            checked += 1; hits_seen += int(hit.any())
+        s.close()
+    assert hits_seen >= checked // 4          # the quad is on screen often enough for the test to mean something
+
+
 def test_depth_zero_and_empty_scene(rt):
     s, _ = gpu_scene(rt, "hw12_scene4", size=(64, 40))
     img = s.render_frame(rt.default_params(max_ray_depth=0))          # every hit returns the background (render.hpp:138)
