@@ -23,12 +23,16 @@ namespace rtb {
 #ifndef RT_STREAM_REFILL_BELOW
 #define RT_STREAM_REFILL_BELOW 22
 #endif
+#ifndef RT_STREAM_LEAF_FRAC
+#define RT_STREAM_LEAF_FRAC 3
+#endif
 #ifndef RT_STREAM_MIN_BLOCKS
 #define RT_STREAM_MIN_BLOCKS 3
 #endif
 constexpr int STREAM_BURST = RT_STREAM_BURST;                // rounds (node steps + one leaf phase) between completion phases
 constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
-constexpr int STREAM_LEAF_MIN = RT_STREAM_LEAF_MIN;          // run the leaf phase when this many lanes are parked (or nobody can walk on)
+constexpr int STREAM_LEAF_MIN = RT_STREAM_LEAF_MIN;          // run the leaf phase when this many lanes are parked ...
+constexpr int STREAM_LEAF_FRAC = RT_STREAM_LEAF_FRAC;        // ... or when parked * this >= walking (0: only when nobody can walk on)
 constexpr int STREAM_REFILL_BELOW = RT_STREAM_REFILL_BELOW;  // go and fetch new queries when fewer lanes than this are traversing
 
 // RT_STREAM_STATS (developer builds only, scripts/gpu_stream_stats.py): where the lanes of a warp are while it executes node
@@ -118,7 +122,9 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
             }
             const uint32_t parked = __ballot_sync(FULL, busy && st.phase == KD8_LEAF);
             const uint32_t walking = __ballot_sync(FULL, busy && st.phase == KD8_WALK);
-            if (parked && (__popc(parked) >= STREAM_LEAF_MIN || !walking)) {
+            // the leaf phase runs when enough lanes are parked - in absolute terms, or relative to the lanes still walking: in the
+            // tail of a launch a warp holds a handful of queries, and a parked one must not wait for eight
+            if (parked && (__popc(parked) >= STREAM_LEAF_MIN || __popc(parked) * STREAM_LEAF_FRAC >= __popc(walking))) {
                 STREAM_STAT(5, 1); STREAM_STAT(6, __popc(parked));
                 if (busy && st.phase == KD8_LEAF) accel_leaf_step<CULL, FAST>(st, stack, sc, eps);
             }
