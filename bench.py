@@ -562,6 +562,14 @@ def main() -> None:
             "roofline_fp32": {"kernel": dom_kernel, "achieved": kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12 if cls[dom] else 0.0,
                               "peak": fp32_peak, "unit": "T FP32 op/s (no FMA in exact mode)",
                               "frac": (kinds[dom]["alg_flop"] / (cls[dom] * 1e-3) / 1e12) / fp32_peak if cls[dom] else 0.0},
+            # every ray kind against both rooflines (north star: "each number as an absolute value and as a fraction of its
+            # roofline"): reference-algorithm bytes and flop of that kind / the time of that kind's kernels
+            "roofline_by_kind": {k: {"mrays_s": (n / cls[k] / 1e3 if cls[k] else None),
+                                     "hbm_gbs": (kinds[k]["alg_bytes"] / (cls[k] * 1e-3) / 1e9 if cls[k] else None),
+                                     "hbm_frac": (kinds[k]["alg_bytes"] / (cls[k] * 1e-3) / 1e9 / peaks["hbm_gbs"] if cls[k] else None),
+                                     "fp32_tops": (kinds[k]["alg_flop"] / (cls[k] * 1e-3) / 1e12 if cls[k] else None),
+                                     "fp32_frac": (kinds[k]["alg_flop"] / (cls[k] * 1e-3) / 1e12 / fp32_peak if cls[k] else None)}
+                                 for k, n in (("primary", int(c0.primary)), ("secondary", int(c0.secondary)), ("shadow", int(c0.shadow)))},
             "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall,
             "combine": (None if world == 1 else ("rt_peer_*: fused wait+reduce+resolve over NVLink peer memory, frame i-1's combine on a "

@@ -20,6 +20,22 @@ for r in rows[2:]:
     for k in keys:
         if k in hdr:
             print(f"  {k}: {r[hdr.index(k)]} {units[hdr.index(k)]}")
+    # traversal fetches against the chip's bandwidths (north star): sectors are 32 B
+    def num(k):
+        return float(r[hdr.index(k)].replace(",", "")) if k in hdr and r[hdr.index(k)] else None
+    dur = num("gpu__time_duration.sum")
+    dur_s = dur * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(units[hdr.index("gpu__time_duration.sum")], 1e-6) if dur else None
+    for k, label in (("l1tex__t_sectors.sum", "L1 (l1tex__t_sectors.sum x 32 B)"), ("lts__t_sectors.sum", "L2 (lts__t_sectors.sum x 32 B)")):
+        v = num(k)
+        if v is not None and dur_s:
+            print(f"  {label}: {v * 32 / 1e6:.1f} MB per launch = {v * 32 / dur_s / 1e9:.0f} GB/s")
+    for k in ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+              "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+              "smsp__inst_executed_pipe_fp32.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"):
+        if k in hdr and r[hdr.index(k)]:
+            print(f"  {k}: {r[hdr.index(k)]} {units[hdr.index(k)]}")
     st = [(hdr[i], float(r[i])) for i in range(len(hdr)) if hdr[i].startswith("smsp__average_warps_issue_stalled") and hdr[i].endswith("per_issue_active.ratio") and r[i]]
     st.sort(key=lambda x: -x[1])
     for k, v in st[:7]:
