@@ -1,7 +1,7 @@
 #!/bin/bash
 # developer helper (one gpurun call, 1 GPU): GPU parity tests, default bench + reference arm, ncu launch list of the bench
 # command and ncu --set full captures of one default-mode frame (cfg2).  Outputs land in gpurun_out/ with the given tag.
-tag=${1:-r1f}
+tag=${1:-r1g}
 out=gpurun_out
 nvidia-smi -L; nproc
 timeout 900 python -m pytest tests -q -m gpu > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $out/${tag}_pytest_gpu.log
