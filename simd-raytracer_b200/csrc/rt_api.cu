@@ -723,6 +723,10 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
 
 void copy_rect_to_host(rt_scene* s, const Rect& r, const float* d_rgb, float* rgb, cudaStream_t st) {
     const size_t at = (size_t(r.y0) * s->host.width + r.x0) * 3;
+    if (r.x0 == 0 && r.x1 == s->host.width) {                  // whole rows: one contiguous transfer
+        CK(cudaMemcpyAsync(rgb + at, d_rgb + at, size_t(s->host.width) * 12 * (r.y1 - r.y0), cudaMemcpyDeviceToHost, st));
+        return;
+    }
     CK(cudaMemcpy2DAsync(rgb + at, size_t(s->host.width) * 12, d_rgb + at, size_t(s->host.width) * 12, size_t(r.x1 - r.x0) * 12,
                          r.y1 - r.y0, cudaMemcpyDeviceToHost, st));
 }
