@@ -1081,6 +1081,12 @@ extern "C" __attribute__((visibility("default"))) int rt_debug_stream_stats(unsi
     if (reset) { unsigned long long z[16] = {}; if (cudaMemcpyToSymbol(rtb::g_stream_stats, z, sizeof z) != cudaSuccess) return RT_ERR_CUDA; }
     return RT_OK;
 }
+// per-warp log of the last stream kernel that ran: n_warps x { start ns, end ns, queries taken, node-step slots }
+extern "C" __attribute__((visibility("default"))) int rt_debug_stream_log(unsigned long long* out, int n_warps) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return RT_ERR_CUDA;
+    const size_t n = size_t(std::min(n_warps, rtb::STREAM_LOG_WARPS)) * 4 * sizeof(unsigned long long);
+    return cudaMemcpyFromSymbol(out, rtb::g_stream_log, n) == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+}
 #endif
 
 void* rt_alloc_pinned(uint64_t bytes) {

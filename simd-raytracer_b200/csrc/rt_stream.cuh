@@ -41,6 +41,10 @@ constexpr int STREAM_REFILL_BELOW = RT_STREAM_REFILL_BELOW;  // go and fetch new
 // [8] completion phases, [9] bursts
 #ifdef RT_STREAM_STATS
 __device__ unsigned long long g_stream_stats[16];
+// per-warp log of the LAST stream kernel that ran: { start ns, end ns, queries taken, node-step slots } (scripts/gpu_stream_log.py)
+constexpr int STREAM_LOG_WARPS = 8192;
+__device__ unsigned long long g_stream_log[STREAM_LOG_WARPS][4];
+__device__ __forceinline__ unsigned long long stream_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define STREAM_STAT(i, v) (stats[i] += (v))
 #else
 #define STREAM_STAT(i, v) ((void)0)
@@ -70,6 +74,8 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
     uint32_t idx = 0;
 #ifdef RT_STREAM_STATS
     unsigned long long stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long log_t0 = stream_now_ns();
+    unsigned long long log_taken = 0;
 #endif
     for (;;) {
         // ---- refill idle lanes ----
@@ -86,6 +92,9 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
             if (!busy) {
                 const uint32_t mine = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
                 if (mine < end) {
+#ifdef RT_STREAM_STATS
+                    ++log_taken;
+#endif
                     idx = mine;
                     V3 o, d; float t_far; bool any_hit;
                     if (p.load(sc, idx, o, d, t_far, any_hit)) {
@@ -143,8 +152,12 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
         if (fin) busy = p.finish(sc, idx, h, st);
     }
 #ifdef RT_STREAM_STATS
-    if (lane == 0)
+    for (int o = 16; o; o >>= 1) log_taken += __shfl_xor_sync(FULL, log_taken, o);
+    if (lane == 0) {
         for (int i = 0; i < 10; ++i) atomicAdd(&g_stream_stats[i], stats[i]);
+        const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (w < uint32_t(STREAM_LOG_WARPS)) { g_stream_log[w][0] = log_t0; g_stream_log[w][1] = stream_now_ns(); g_stream_log[w][2] = log_taken; g_stream_log[w][3] = stats[0]; }
+    }
 #endif
 }
 
