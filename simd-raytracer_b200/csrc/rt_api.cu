@@ -512,8 +512,10 @@ template <class Launch>
 void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_flags, cudaStream_t st, Launch&& launch) {
     FrameParams fp = P.fp;
     const Mode m = P.m;
-    // a one-sample pass that overwrites the framebuffer keeps only the HITS of its camera rays as level-0 entries (rt_stream.cuh)
-    fp.sparse0 = (m.ordered && fp.n_samples == 1 && P.first_pass) ? 1u : 0u;
+    // only the HITS of the camera rays become level-0 entries (rt_stream.cuh): in a one-sample pass that overwrites the
+    // framebuffer the misses write their pixels at once, in a multi-sample pass k_accumulate adds them
+    fp.sparse0 = (m.ordered && (fp.n_samples > 1 || P.first_pass)) ? 1u : 0u;
+    float* const miss_fb = fp.n_samples == 1 ? d_rgb : nullptr;
     const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0), fi = m.fast ? 1 : 0;
     const bool tr = s->d.has_transmissive != 0, has_gi = P.has_gi;
     const uint32_t launched = P.launched, levels = P.levels;
@@ -527,13 +529,13 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         for (int k = 0; k < 3; ++k) cull_tiles = cull_tiles || !(s->d.root_min[k] <= s->d.cam_pos[k] && s->d.cam_pos[k] <= s->d.root_max[k]);
     if (cull_tiles)
         launch(TC_PRIMARY, [&] {
-            launch_k(k_tile_cull, std::min<unsigned>((fp.plane / 32 + 255) / 256, unsigned(s->g_resolve)), 256, st, s->d, fp, d_rgb, P.divide, s->ps, s->tiles0.p);
+            launch_k(k_tile_cull, std::min<unsigned>((fp.plane / 32 + 255) / 256, unsigned(s->g_resolve)), 256, st, s->d, fp, miss_fb, P.divide, s->ps, s->tiles0.p);
         });
     launch(TC_PRIMARY, [&] {
         if (fp.sparse0) {
             const uint32_t* tiles = cull_tiles ? s->tiles0.p : nullptr;
-            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot, tiles);
-            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, d_rgb, P.divide, s->ps, slot, tiles);
+            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
+            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
         } else if (m.ordered) {
             if (m.fast) launch_k(k_stream_primary<true>, s->gs_primary[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
             else launch_k(k_stream_primary<false>, s->gs_primary[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
@@ -583,7 +585,7 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
                 launch_k(k_resolve<true>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
                                                               launched, levels, s->mask0.p);
             else
-                launch_k(k_resolve<false>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels, nullptr);
+                launch_k(k_resolve<false>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels, s->mask0.p);
         });
         ++slot;
     }
@@ -592,7 +594,7 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     // the accumulate kernel skips itself on the device when the pass overflowed its pools
     if (!fuse_acc)
         launch(TC_RESOLVE, [&] {
-            launch_k(k_accumulate, (fp.plane + 255) / 256, 256, st, s->d, fp, s->recs.p, d_rgb, s->ps, P.first_pass, P.divide);
+            launch_k(k_accumulate, (fp.plane + 255) / 256, 256, st, s->d, fp, s->recs.p, d_rgb, s->ps, P.first_pass, P.divide, s->mask0.p);
         });
 }
 

@@ -209,23 +209,29 @@ __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DS
 }
 
 // ---- primary rays, sparse level 0 ------------------------------------------------------------------------------------------
-// One-sample passes that overwrite the framebuffer (first_pass): a camera ray that hits nothing - 86 % of them on the dragon
-// scenes - is finished the moment its query is: the lane writes the miss colour of render.hpp:66-74 ((0 + background) / spp)
-// into the pixel and nothing else.  Only HITS become level-0 entries: ray and hit are stored at the entry's place in the
+// A camera ray that hits nothing - 86 % of them on the dragon scenes - is finished the moment its query is.  In a one-sample
+// pass that overwrites the framebuffer (first_pass) the lane writes the miss colour of render.hpp:66-74 ((0 + background) / spp)
+// into the pixel and nothing else; in a multi-sample pass it writes nothing at all and k_accumulate adds the background for
+// every sample whose bit is not set.  Only HITS become level-0 entries: ray and hit are stored at the entry's place in the
 // sample plane as before, and the entry's bit is set in `mask0` (one word per 8x4 pixel tile), so the level-0 shade and resolve
 // kernels skip every tile without a hit and never touch the entries of the misses.  Entries keep their pixel order (the
 // shadow jobs and child rays they spawn stay coherent).  The ray is the traversal state's own (st.o*, st.d*).
 struct SparsePrimaryPolicy {
-    const FrameParams* fp; Ray* rays; Hit* hits; uint32_t* mask0; float* fb;
-    const uint32_t* tile_list;          // tiles k_tile_cull kept (work item i = pixel i & 31 of tile tile_list[i >> 5]), or null: every tile
+    const FrameParams* fp; Ray* rays; Hit* hits; uint32_t* mask0;
+    float* fb;                          // one-sample pass: misses write their pixel here; null in a multi-sample pass (k_accumulate adds them)
+    const uint32_t* tile_list;          // tiles k_tile_cull kept, or null: every tile
+    uint32_t per_sample;                // work items per sample = 32 * (tiles kept, or all tiles)
     V3 miss_rgb;
     uint32_t n_rays = 0, n_hits = 0;
+    // work item -> level-0 entry: sample s, pixel (w & 31) of the (w >> 5)-th listed tile; entry = s * plane + tile * 32 + pixel
     __device__ __forceinline__ bool load(const DScene& sc, uint32_t& i, V3& o, V3& d, float& t_far, bool& any_hit) {
-        if (tile_list) i = __ldg(tile_list + (i >> 5)) * 32u + (i & 31u);
+        const uint32_t s = i / per_sample, w = i - s * per_sample;
+        const uint32_t j = tile_list ? __ldg(tile_list + (w >> 5)) * 32u + (w & 31u) : w;
+        i = s * fp->plane + j;
         uint32_t x, y;
-        if (!level0_pixel(*fp, i, x, y)) return false;                                                   // padding of the 8x4 tiles
+        if (!level0_pixel(*fp, j, x, y)) return false;                                                   // padding of the 8x4 tiles
         float rx, ry; uint2 key;
-        primary_sample(sc, *fp, x, y, fp->sample_first, rx, ry, key);
+        primary_sample(sc, *fp, x, y, fp->sample_first + s, rx, ry, key);
         camera_ray(sc, fp->tan_half_fov, rx, ry, o, d);
         t_far = FLT_MAX; any_hit = false;
         ++n_rays;
@@ -233,16 +239,17 @@ struct SparsePrimaryPolicy {
     }
     __device__ __forceinline__ void entered(uint32_t, V3, V3) {}
     __device__ __forceinline__ bool finish(const DScene& sc, uint32_t i, const Hit& h, AccelState& st) {
+        const uint32_t s = i / fp->plane;
         uint32_t x, y;
-        level0_pixel(*fp, i, x, y);
+        level0_pixel(*fp, i - s * fp->plane, x, y);
         if (h.tri >= 0) {
             float rx, ry; uint2 key;
-            primary_sample(sc, *fp, x, y, fp->sample_first, rx, ry, key);                                // the path key of the pixel
+            primary_sample(sc, *fp, x, y, fp->sample_first + s, rx, ry, key);                            // the path key of the sample
             store_ray(rays + i, mk(st.ox, st.oy, st.oz), mk(st.dx, st.dy, st.dz), key);
             store_hit(hits + i, h);
             atomicOr(mask0 + (i >> 5), 1u << (i & 31u));
             ++n_hits;
-        } else {
+        } else if (fb) {
             float* px = fb + (size_t(y) * sc.width + x) * 3;
             px[0] = miss_rgb.x; px[1] = miss_rgb.y; px[2] = miss_rgb.z;
         }
@@ -320,9 +327,11 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
             const uint32_t px = __shfl_sync(FULL, lx0, src) + (lane & 7u), py = __shfl_sync(FULL, ly0, src) + (lane >> 3);
             const uint32_t tw = __shfl_sync(FULL, w, src), tht = __shfl_sync(FULL, h, src);
             if ((lane & 7u) < tw && (lane >> 3) < tht) {
-                float* q = fb + (size_t(fp.y0 + py) * sc.width + (fp.x0 + px)) * 3;
-                q[0] = miss.x; q[1] = miss.y; q[2] = miss.z;
-                ++n_culled;
+                if (fb) {                                                           // null in a multi-sample pass: k_accumulate adds the misses
+                    float* q = fb + (size_t(fp.y0 + py) * sc.width + (fp.x0 + px)) * 3;
+                    q[0] = miss.x; q[1] = miss.y; q[2] = miss.z;
+                }
+                n_culled += fp.n_samples;
             }
         }
     }
@@ -335,8 +344,9 @@ __global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary_sp
                                                                PassState* __restrict__ ps, int work_slot, const uint32_t* __restrict__ tile_list) {
     pdl_wait();
     SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb; p.tile_list = tile_list;
+    p.per_sample = tile_list ? ps->n_tiles0 * 32u : fp.plane;
     p.miss_rgb = first_pass_miss_colour(sc, fp, divide);
-    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], tile_list ? ps->n_tiles0 * 32u : fp.plane, fp.eps);   // render.hpp:64, culling ON
+    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], p.per_sample * fp.n_samples, fp.eps);             // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 

@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
     pdl_wait();
     // sparse level 0: the misses wrote their pixels in k_stream_primary_sparse, mask0[tile] holds the hits.  The word is cleared
     // here, by its last reader, so the mask is all zero again when the pass ends (kept or discarded)
-    const bool sparse = ACC && fp.sparse0 != 0u;
+    const bool sparse = level == 0 && fp.sparse0 != 0u;
     const uint32_t begin = ps->lv[level], end = ps->lv[level + 1];
     const V3 bg = mk(sc.bg[0], sc.bg[1], sc.bg[2]), black = mk(0.0f, 0.0f, 0.0f);
     (void)work_slot;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
             const uint32_t word = mask0[base >> 5];
             if (word == 0u) continue;                                                                    // warp-uniform
             __syncwarp();
-            if ((threadIdx.x & 31u) == 0u) mask0[base >> 5] = 0u;
+            if (ACC && (threadIdx.x & 31u) == 0u) mask0[base >> 5] = 0u;       // multi-sample pass: k_accumulate reads it last
             if (!((word >> (threadIdx.x & 31u)) & 1u)) continue;
         }
         if (i >= end) continue;
@@ -542,16 +542,28 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
 // ---- kernel: accumulate ------------------------------------------------------------------------------------------------
 // render.hpp:66-74: per pixel, samples are summed in order and divided by samples_per_pixel once
 __global__ void __launch_bounds__(256) k_accumulate(DScene sc, FrameParams fp, const Rec* __restrict__ recs, float* __restrict__ fb,
-                                                    const PassState* __restrict__ ps, int first_pass, int divide) {
+                                                    const PassState* __restrict__ ps, int first_pass, int divide, uint32_t* __restrict__ mask0) {
     pdl_wait();
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= fp.plane || ps->overflow) return;      // an overflowed pass is discarded and rendered again by the host
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;               // plane is a multiple of 32: a warp is one 8x4 tile
+    if (j >= fp.plane) return;
+    const bool discard = ps->overflow != 0u;        // an overflowed pass is discarded and rendered again by the host
     uint32_t x, y;
-    if (!level0_pixel(fp, j, x, y)) return;
+    const bool valid = level0_pixel(fp, j, x, y);
     float* px = fb + (size_t(y) * sc.width + x) * 3;
-    V3 sum = first_pass ? mk(0.0f, 0.0f, 0.0f) : mk(px[0], px[1], px[2]);
+    V3 sum = (first_pass || !valid || discard) ? mk(0.0f, 0.0f, 0.0f) : mk(px[0], px[1], px[2]);
     const V3 bg = mk(sc.bg[0], sc.bg[1], sc.bg[2]);
-    for (uint32_t s = 0; s < fp.n_samples; ++s) sum = sum + child_colour(recs, s * fp.plane + j, bg);
+    if (fp.sparse0) {
+        // sparse level 0: a sample without its bit in mask0 missed everything; the word is cleared here, by its last reader
+        for (uint32_t s = 0; s < fp.n_samples; ++s) {
+            const uint32_t e = s * fp.plane + j;
+            const uint32_t word = mask0[e >> 5];
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0u && word) mask0[e >> 5] = 0u;
+            sum = sum + (((word >> (j & 31u)) & 1u) ? child_colour(recs, e, bg) : bg);
+        }
+    } else
+        for (uint32_t s = 0; s < fp.n_samples; ++s) sum = sum + child_colour(recs, s * fp.plane + j, bg);
+    if (!valid || discard) return;
     if (divide) {
         const float div = float(fp.spp_total);
         sum = mk(__fdiv_rn(sum.x, div), __fdiv_rn(sum.y, div), __fdiv_rn(sum.z, div));

@@ -242,14 +242,15 @@ def test_textures_exact(rt, oracle_mod):
 
 
 def test_sparse_level0_equals_dense_frames(rt):
-    """accelerated mode, one-sample passes: camera rays that miss write their pixel at once and only hits become level-0
-    entries (k_stream_primary_sparse).  Same float frame and counts as the reference-order mode (dense level 0) for odd
-    frame sizes, tile rectangles that cut the 8x4 pixel tiles, raw sums (no divide), GI keys and a multi-sample frame whose
-    passes hold one sample each only when the budget forces it (dense accumulate path)."""
+    """accelerated mode: only the hits of the camera rays become level-0 entries (k_stream_primary_sparse); misses write
+    their pixel at once (one-sample passes) or are added by k_accumulate (multi-sample passes).  Same float frame and counts
+    as the reference-order mode (dense level 0) for odd frame sizes, tile rectangles that cut the 8x4 pixel tiles, raw sums
+    (no divide), GI keys and multi-sample passes."""
     for name, size in (("hw09_scene5", (203, 117)), ("hw15_scene2", (97, 61))):
         s, _ = gpu_scene(rt, name, size=size)
         for kw in (dict(), dict(diffuse_reflection_ray_count=2, max_ray_depth=3), dict(flags=rt.FLAG_RAW_SUM, spp_total=3, sample_offset=1),
-                   dict(samples_per_pixel=2)):
+                   dict(samples_per_pixel=2), dict(samples_per_pixel=3, diffuse_reflection_ray_count=1, max_ray_depth=2),
+                   dict(samples_per_pixel=2, sample_offset=2, spp_total=5, flags=rt.FLAG_RAW_SUM)):
             flags = kw.pop("flags", 0)
             want = s.render_frame(rt.default_params(flags=flags, **kw))
             cw = s.counters()
