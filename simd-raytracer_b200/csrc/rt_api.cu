@@ -352,9 +352,9 @@ struct Mode { bool fast, ordered; };
 Mode mode_of(uint32_t flags) { return Mode{(flags & RT_FLAG_FAST_MATH) != 0, (flags & RT_FLAG_ORDERED) != 0}; }
 
 template <class K>
-int grid_for(rt_scene* s, K kernel) {
+int grid_for(rt_scene* s, K kernel, int threads = 256) {
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
     return s->n_sm * std::max(per_sm, 1);
 }
 
@@ -462,12 +462,12 @@ void ensure_grids(rt_scene* s, Mode m, bool has_gi) {
     if (!s->g_resolve) s->g_resolve = grid_for(s, k_resolve<false>);
     if (!s->g_shade[has_gi]) s->g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
     if (m.ordered) {
-        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>) : grid_for(s, k_stream_primary<false>);
-        if (!s->gs_sparse[fi]) s->gs_sparse[fi] = m.fast ? grid_for(s, k_stream_primary_sparse<true>) : grid_for(s, k_stream_primary_sparse<false>);
-        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>) : grid_for(s, k_stream_level<false>);
+        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>, STREAM_THREADS) : grid_for(s, k_stream_primary<false>, STREAM_THREADS);
+        if (!s->gs_sparse[fi]) s->gs_sparse[fi] = m.fast ? grid_for(s, k_stream_primary_sparse<true>, STREAM_THREADS) : grid_for(s, k_stream_primary_sparse<false>, STREAM_THREADS);
+        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>, STREAM_THREADS) : grid_for(s, k_stream_level<false>, STREAM_THREADS);
         if (!s->gs_shadow[fi * 2 + tr])
-            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>) : grid_for(s, k_stream_shadow<true, false>))
-                                           : (m.fast ? grid_for(s, k_stream_shadow<false, true>) : grid_for(s, k_stream_shadow<false, false>));
+            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>, STREAM_THREADS) : grid_for(s, k_stream_shadow<true, false>, STREAM_THREADS))
+                                           : (m.fast ? grid_for(s, k_stream_shadow<false, true>, STREAM_THREADS) : grid_for(s, k_stream_shadow<false, false>, STREAM_THREADS));
     } else {
         if (!s->g_primary[mi]) s->g_primary[mi] = m.fast ? grid_for(s, k_primary<true, false>) : grid_for(s, k_primary<false, false>);
         if (!s->g_trace[mi]) s->g_trace[mi] = m.fast ? grid_for(s, k_trace_level<true, false>) : grid_for(s, k_trace_level<false, false>);
@@ -534,11 +534,11 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     launch(TC_PRIMARY, [&] {
         if (fp.sparse0) {
             const uint32_t* tiles = cull_tiles ? s->tiles0.p : nullptr;
-            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
-            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
+            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
+            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
         } else if (m.ordered) {
-            if (m.fast) launch_k(k_stream_primary<true>, s->gs_primary[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-            else launch_k(k_stream_primary<false>, s->gs_primary[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            if (m.fast) launch_k(k_stream_primary<true>, s->gs_primary[1], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            else launch_k(k_stream_primary<false>, s->gs_primary[0], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
         } else if (m.fast) launch_k(k_primary<true, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
         else launch_k(k_primary<false, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
     });
@@ -547,8 +547,8 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         if (lvl > 0) {
             launch(TC_SECONDARY, [&] {
                 if (m.ordered) {
-                    if (m.fast) launch_k(k_stream_level<true>, s->gs_level[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                    else launch_k(k_stream_level<false>, s->gs_level[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    if (m.fast) launch_k(k_stream_level<true>, s->gs_level[1], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    else launch_k(k_stream_level<false>, s->gs_level[0], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
                 } else if (m.fast) launch_k(k_trace_level<true, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
                 else launch_k(k_trace_level<false, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
             });
@@ -564,10 +564,10 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         launch(TC_SHADOW, [&] {
             if (m.ordered) {
                 const int g = s->gs_shadow[fi * 2 + tr];
-                if (tr) { if (m.fast) launch_k(k_stream_shadow<true, true>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
-                          else launch_k(k_stream_shadow<true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
-                else { if (m.fast) launch_k(k_stream_shadow<false, true>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
-                       else launch_k(k_stream_shadow<false, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
+                if (tr) { if (m.fast) launch_k(k_stream_shadow<true, true>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot);
+                          else launch_k(k_stream_shadow<true, false>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot); }
+                else { if (m.fast) launch_k(k_stream_shadow<false, true>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot);
+                       else launch_k(k_stream_shadow<false, false>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot); }
             } else {
                 const int g = s->g_shadow[mi * 2 + tr];
                 if (tr) { if (m.fast) launch_k(k_shadow<true, true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);

@@ -26,9 +26,13 @@ namespace rtb {
 #ifndef RT_STREAM_LEAF_FRAC
 #define RT_STREAM_LEAF_FRAC 3
 #endif
+#ifndef RT_STREAM_THREADS
+#define RT_STREAM_THREADS 256
+#endif
 #ifndef RT_STREAM_MIN_BLOCKS
 #define RT_STREAM_MIN_BLOCKS 3
 #endif
+constexpr int STREAM_THREADS = RT_STREAM_THREADS;            // threads per block of the stream kernels (registers per thread follow from it)
 constexpr int STREAM_BURST = RT_STREAM_BURST;                // rounds (node steps + one leaf phase) between completion phases
 constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
 constexpr int STREAM_LEAF_MIN = RT_STREAM_LEAF_MIN;          // run the leaf phase when this many lanes are parked ...
@@ -200,7 +204,7 @@ struct PrimaryPolicy {
 };
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                         PassState* __restrict__ ps, int work_slot) {
     pdl_wait();
     PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                                uint32_t* __restrict__ mask0, float* __restrict__ fb, int divide,
                                                                PassState* __restrict__ ps, int work_slot, const uint32_t* __restrict__ tile_list) {
     pdl_wait();
@@ -370,7 +374,7 @@ struct LevelPolicy {
 };
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                       PassState* __restrict__ ps, int level, int work_slot) {
     pdl_wait();
     const uint32_t begin = ps->lv[level];
@@ -430,7 +434,7 @@ struct ShadowPolicy {
 };
 
 template <bool TRANSMISSIVE, bool FAST>
-__global__ void __launch_bounds__(256, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
+__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                        int work_slot) {
     pdl_wait();
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
