@@ -23,10 +23,14 @@
 // F = float only: the device path is FP32 like the reference's shipped configuration (src/main.cpp:36).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <initializer_list>
 #include <memory>
 #include <optional>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -203,6 +207,58 @@ image<F> render_frame(const b200_accel<F>& accel, const scheduling_type /* tiles
     const int st = rt_render_frame(accel.handle.get(), &p, rgb.data());
     if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame: ") + rt_status_string(st) + ": " + rt_last_error());
     return b200_image_from_rgb<F>(rgb.data(), h, w);
+}
+
+// ---- image output --------------------------------------------------------------------------------
+// The reference quantises while it writes: write_ppm (io/image/ppm.hpp:7-25) turns every float channel into
+// uint8(255.999 * clamp(c, 0, 1)) and prints ASCII P3 - at 4K that is 100 MB of text through operator<<.  Here the frame is
+// quantised on the device by the same expression (rt_render_frame_rgb8: a quarter of the bytes over PCIe) and the file is
+// written from the bytes: b200_write_ppm produces the reference's file byte for byte, b200_write_ppm_binary the P6 form.
+template <typename F>
+std::vector<std::uint8_t> b200_render_frame_rgb8(const b200_accel<F>& accel, const rt_params& p = b200_config_params()) {
+    const std::size_t h = accel.scene_ptr->config.image_height, w = accel.scene_ptr->config.image_width;
+    std::vector<std::uint8_t> rgb8(h * w * 3);
+    const int st = rt_render_frame_rgb8(accel.handle.get(), &p, rgb8.data());
+    if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame_rgb8: ") + rt_status_string(st) + ": " + rt_last_error());
+    return rgb8;
+}
+// the bytes write_ppm would print for this image (host-side restatement of ppm.hpp:17-19, for callers that hold an image<F>)
+template <typename F>
+std::vector<std::uint8_t> b200_quantise(const image<F>& img) {
+    std::vector<std::uint8_t> rgb8(img.get_height() * img.get_width() * 3);
+    std::size_t k = 0;
+    for (std::size_t y = 0; y < img.get_height(); ++y)
+        for (std::size_t x = 0; x < img.get_width(); ++x) {
+            const auto c = img.get_pixel(y, x);
+            for (const F ch : {c.red, c.green, c.blue})
+                rgb8[k++] = static_cast<std::uint8_t>(255.999 * std::clamp(ch, static_cast<F>(0.), static_cast<F>(1.)));
+        }
+    return rgb8;
+}
+// ASCII P3, identical to write_ppm's output for the same bytes: "r g b\t" per pixel, one line per row (ppm.hpp:8-24)
+inline void b200_write_ppm(const std::uint8_t* rgb8, std::size_t width, std::size_t height, std::ostream& out) {
+    char dec[256][4];
+    std::uint8_t len[256];
+    for (int v = 0; v < 256; ++v) len[v] = static_cast<std::uint8_t>(std::snprintf(dec[v], sizeof dec[v], "%d", v));
+    out << "P3\n" << width << " " << height << "\n255\n";
+    std::string line;
+    line.reserve(width * 12 + 1);
+    for (std::size_t y = 0; y < height; ++y) {
+        line.clear();
+        const std::uint8_t* px = rgb8 + y * width * 3;
+        for (std::size_t x = 0; x < width; ++x, px += 3) {
+            line.append(dec[px[0]], len[px[0]]); line.push_back(' ');
+            line.append(dec[px[1]], len[px[1]]); line.push_back(' ');
+            line.append(dec[px[2]], len[px[2]]); line.push_back('\t');
+        }
+        line.push_back('\n');
+        out.write(line.data(), static_cast<std::streamsize>(line.size()));
+    }
+}
+// binary P6: the same pixels in 3 bytes each
+inline void b200_write_ppm_binary(const std::uint8_t* rgb8, std::size_t width, std::size_t height, std::ostream& out) {
+    out << "P6\n" << width << " " << height << "\n255\n";
+    out.write(reinterpret_cast<const char*>(rgb8), static_cast<std::streamsize>(width * height * 3));
 }
 
 // A caller that renders frame after frame (src/main.cpp:13-25 in a loop - the reference's animation outputs) keeps two

@@ -14,7 +14,9 @@ REF = "/root/reference/include"
 
 SRC = r'''
 #include <cstdio>
+#include <sstream>
 #include <raytracer/render/render.hpp>
+#include <raytracer/io/image/ppm.hpp>
 #include <b200_accel.hpp>
 extern "C" unsigned char* stbi_load(const char*, int*, int*, int*, int) { return nullptr; }
 extern "C" void stbi_image_free(void*) {}
@@ -43,6 +45,25 @@ int main() {
     catch (const std::exception& e) { std::printf("render_frame: %s\n", e.what()); }
     try { b200_frame_sequence<float> seq(a); seq.submit(); seq.submit(); auto img = seq.next(); std::printf("sequence: %zu rows\n", img.get_height()); }
     catch (const std::exception& e) { std::printf("sequence: %s\n", e.what()); }
+    try { auto px = b200_render_frame_rgb8(a); std::printf("rgb8: %zu bytes\n", px.size()); }
+    catch (const std::exception& e) { std::printf("rgb8: %s\n", e.what()); }
+    // image output (SURVEY section 8 row f3): the file written from quantised bytes is the reference's file, byte for byte
+    {
+        const std::size_t H = 37, W = 53;
+        std::vector<std::vector<color<float>>> px(H, std::vector<color<float>>(W));
+        unsigned r = 12345u;
+        auto next = [&] { r = r * 1664525u + 1013904223u; return float(r >> 8) / float(1u << 24); };
+        for (auto& row : px) for (auto& c : row) c = color<float>{next() * 1.5f - 0.25f, next(), next() * 4.0f - 2.0f};
+        px[0][0] = color<float>{1.0f, 0.0f, 0.99999994f};
+        px[0][1] = color<float>{0.003906f, 0.0039062f, 0.00390626f};
+        image<float> img(H, W, std::move(px));
+        std::ostringstream ref, mine, bin;
+        write_ppm(img, ref);
+        const auto bytes = b200_quantise(img);
+        b200_write_ppm(bytes.data(), W, H, mine);
+        b200_write_ppm_binary(bytes.data(), W, H, bin);
+        std::printf("ppm identical: %d (%zu bytes), p6 %zu bytes\n", int(ref.str() == mine.str()), ref.str().size(), bin.str().size());
+    }
     return 0;
 }
 '''
@@ -60,10 +81,12 @@ def test_adapter_compiles_against_reference_and_dispatches(rt, tmp_path):
                            f"-Wl,-rpath,{libdir}"])
     out = subprocess.check_output([str(exe)], text=True)
     assert "scene_ptr ok: 1" in out
+    assert "ppm identical: 1" in out and f"p6 {len('P6\n53 37\n255\n') + 53 * 37 * 3} bytes" in out
     import torch
     if not torch.cuda.is_available():
         assert "ctor: b200_accel: no usable sm_100 CUDA device" in out
         assert "intersect without device: nullopt" in out
         # the device overload was chosen (the generic CPU render_frame would have returned 4 rows)
         assert "render_frame: b200 render_frame: no usable sm_100 CUDA device" in out
-        assert "sequence: b200" in out and "rows" not in out.split("sequence:")[1]
+        assert "sequence: b200" in out and "rows" not in out.split("sequence:")[1].split("rgb8:")[0]
+        assert "rgb8: b200 render_frame_rgb8: no usable sm_100 CUDA device" in out
