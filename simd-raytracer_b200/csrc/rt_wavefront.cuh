@@ -67,6 +67,38 @@ __device__ __forceinline__ uint32_t claim32(uint32_t* counter) {
 // kernels latency-bound at a third of the HBM rate).  The trace kernels keep the dynamic counter: their cost per ray varies.
 __device__ __forceinline__ uint32_t first_chunk() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; }
 __device__ __forceinline__ uint32_t chunk_stride() { return gridDim.x * (blockDim.x >> 5) * 32u; }
+// The 32-entry chunks of a level for one warp of a streaming kernel.  Dense: grid-stride order, every entry live.  Sparse
+// level 0 (mask = one word per chunk, bit = the entry exists): the warp reads the words of its next 32 chunks with ONE load
+// and visits the non-empty ones; a dependent load in front of every chunk, most of them empty, kept the level-0 kernels
+// waiting for a third of their time.  Every lane of the warp has to call next() (it shuffles).
+struct ChunkIter {
+    const uint32_t* mask;
+    uint32_t n_chunks, c0, cbase, nz, words, nw, lane;
+    __device__ __forceinline__ ChunkIter(uint32_t n_entries, const uint32_t* mask_or_null)
+        : mask(mask_or_null), n_chunks((n_entries + 31u) >> 5), c0(first_chunk() >> 5), cbase(0), nz(0), words(0),
+          nw(chunk_stride() >> 5), lane(threadIdx.x & 31u) {}
+    // base: first entry of the chunk (relative to the level); word: which of its 32 entries exist
+    __device__ __forceinline__ bool next(uint32_t& base, uint32_t& word) {
+        __syncwarp();
+        if (!mask) {
+            if (c0 >= n_chunks) return false;
+            base = c0 << 5; word = 0xFFFFFFFFu; c0 += nw;
+            return true;
+        }
+        while (!nz) {
+            if (c0 >= n_chunks) return false;
+            const uint32_t c = c0 + lane * nw;
+            words = c < n_chunks ? mask[c] : 0u;
+            nz = __ballot_sync(0xFFFFFFFFu, words != 0u);
+            cbase = c0; c0 += nw << 5;
+        }
+        const int l = __ffs(nz) - 1;
+        nz &= nz - 1u;
+        word = __shfl_sync(0xFFFFFFFFu, words, l);
+        base = (cbase + uint32_t(l) * nw) << 5;
+        return true;
+    }
+};
 // warp-aggregated append: every lane asks for n slots, returns its first slot
 __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, uint32_t n) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -312,14 +344,11 @@ __global__ void __launch_bounds__(256) k_shade(DScene sc, FrameParams fp, Ray* _
     const float PI = 3.14159265358979323846f;
     const bool sparse = level == 0 && fp.sparse0 != 0u;           // level 0 starts at entry 0: chunk c is tile c, mask0[c] its hits
     (void)work_slot;
-    for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
+    ChunkIter chunks(end - begin, sparse ? mask0 : nullptr);
+    uint32_t base, word;
+    while (chunks.next(base, word)) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
-        bool live = i < end;
-        if (sparse) {
-            const uint32_t word = __ldg(mask0 + (base >> 5));
-            if (word == 0u) continue;                                                                    // warp-uniform: a tile without a hit
-            live = live && ((word >> (threadIdx.x & 31u)) & 1u);
-        }
+        const bool live = i < end && ((word >> (threadIdx.x & 31u)) & 1u);
 
         uint32_t kind = REC_DONE, n_child = 0, n_shadow = 0;
         float fresnel = 0.0f;
@@ -479,16 +508,12 @@ __global__ void __launch_bounds__(256) k_resolve(DScene sc, FrameParams fp, Rec*
     (void)work_slot;
     bool discard = false;
     if (ACC) discard = ps->overflow != 0u || (launched < total && ps->pool_count > ps->lv[launched]);
-    for (uint32_t base = first_chunk(); base < end - begin; base += chunk_stride()) {
+    ChunkIter chunks(end - begin, sparse ? mask0 : nullptr);
+    uint32_t base, word;
+    while (chunks.next(base, word)) {
         const uint32_t i = begin + base + (threadIdx.x & 31u);
-        if (sparse) {
-            const uint32_t word = mask0[base >> 5];
-            if (word == 0u) continue;                                                                    // warp-uniform
-            __syncwarp();
-            if (ACC && (threadIdx.x & 31u) == 0u) mask0[base >> 5] = 0u;       // multi-sample pass: k_accumulate reads it last
-            if (!((word >> (threadIdx.x & 31u)) & 1u)) continue;
-        }
-        if (i >= end) continue;
+        if (sparse && ACC && (threadIdx.x & 31u) == 0u) mask0[base >> 5] = 0u;   // multi-sample pass: k_accumulate reads it last
+        if (i >= end || !((word >> (threadIdx.x & 31u)) & 1u)) continue;
         float4* p = reinterpret_cast<float4*>(recs + i);
         const float4 a = p[0];
         const uint32_t kind = __float_as_uint(a.x), fc = __float_as_uint(a.y), fs = __float_as_uint(a.z);
