@@ -512,10 +512,12 @@ template <class Launch>
 void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_flags, cudaStream_t st, Launch&& launch) {
     FrameParams fp = P.fp;
     const Mode m = P.m;
-    // only the HITS of the camera rays become level-0 entries (rt_stream.cuh): in a one-sample pass that overwrites the
-    // framebuffer the misses write their pixels at once, in a multi-sample pass k_accumulate adds them
-    fp.sparse0 = (m.ordered && (fp.n_samples > 1 || P.first_pass)) ? 1u : 0u;
-    float* const miss_fb = fp.n_samples == 1 ? d_rgb : nullptr;
+    // accelerated mode: only the HITS of the camera rays become level-0 entries (rt_stream.cuh).  In a one-sample pass that
+    // overwrites the framebuffer the misses write their pixels at once and level 0 resolves straight into the framebuffer
+    // (fuse_acc); in every other pass k_accumulate adds the samples of a pixel in order, misses included
+    fp.sparse0 = m.ordered ? 1u : 0u;
+    const bool fuse_acc = fp.n_samples == 1 && (P.first_pass || !m.ordered);
+    float* const miss_fb = fuse_acc ? d_rgb : nullptr;
     const int mi = (m.fast ? 1 : 0) | (m.ordered ? 2 : 0), fi = m.fast ? 1 : 0;
     const bool tr = s->d.has_transmissive != 0, has_gi = P.has_gi;
     const uint32_t launched = P.launched, levels = P.levels;
@@ -578,7 +580,6 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         });
         ++slot;
     }
-    const bool fuse_acc = fp.n_samples == 1;          // one sample in the pass: level 0 resolves straight into the framebuffer
     for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
         launch(TC_RESOLVE, [&] {
             if (lvl == 0 && fuse_acc)

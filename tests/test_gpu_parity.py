@@ -265,6 +265,19 @@ def test_sparse_level0_equals_dense_frames(rt):
             assert np.array_equal(want.view(np.uint32), tiled.view(np.uint32)), (name, kw, "tiles")
 
 
+def test_sparse_level0_in_later_one_sample_passes(rt):
+    """a frame whose samples do not fit one pass: 1920x1080 at 5 spp renders a 4-sample pass and then a ONE-sample pass that
+    adds to the framebuffer (sparse level 0 through k_accumulate, not the fused first-pass path)"""
+    s, _ = gpu_scene(rt, "hw09_scene5")
+    want = s.render_frame(rt.default_params(samples_per_pixel=5))
+    cw = s.counters()
+    got = s.render_frame(rt.default_params(samples_per_pixel=5, flags=rt.FLAG_ORDERED))
+    cg = s.counters()
+    assert cg.passes == 2
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert (cw.primary, cw.primary_hits, cw.shadow, cw.secondary) == (cg.primary, cg.primary_hits, cg.shadow, cg.secondary)
+
+
 def test_tile_culling_is_conservative(rt):
     """k_tile_cull finishes 8x4 pixel tiles whose camera rays cannot reach the scene's root box.  A small constant-colour
     quad seen by rotated / sheared cameras from many positions (box in a corner of the frame, partly off-screen, behind the
