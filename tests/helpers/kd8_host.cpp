@@ -52,3 +52,17 @@ extern "C" void bvh_trace_batch(const float* nodes16, const float* tris, const f
         if (tie) tie[i] = (h.tri == rtb::KD_RERUN || (h.tri >= 0 && h.tie_t == h.t)) ? 1 : 0;
     }
 }
+
+// per-ray node-visit and triangle-test counts of the BVH traversal (developer sweeps: scripts/bvh_ray_lengths_cpu.py)
+extern "C" void bvh_trace_batch_counts(const float* nodes16, const float* tris, const float* root6, const float* rays6, uint64_t n,
+                                       int cull, float eps, const float* t_far, int any_hit, uint32_t* node_visits, uint32_t* tri_tests) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* q = rays6 + 6 * i;
+        const float far = t_far ? t_far[i] : FLT_MAX;
+        const uint64_t n0 = g_kd8_nodes, t0 = g_kd8_tris;
+        if (cull) rtb::bvh_trace<true, false>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        else rtb::bvh_trace<false, false>(nodes16, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        node_visits[i] = uint32_t(g_kd8_nodes - n0);
+        tri_tests[i] = uint32_t(g_kd8_tris - t0);
+    }
+}
