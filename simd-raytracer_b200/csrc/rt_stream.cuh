@@ -7,6 +7,7 @@
 #pragma once
 
 #include "rt_wavefront.cuh"
+#include "rt_tilecull.cuh"
 
 namespace rtb {
 
@@ -269,45 +270,19 @@ __device__ __forceinline__ V3 first_pass_miss_colour(const DScene& sc, const Fra
 }
 
 // ---- tile culling in front of the sparse primary kernel -----------------------------------------------------------------------
-// The camera rays of an 8x4 pixel tile (any sample position inside the pixels) lie in the pyramid spanned by the directions
-// through the tile's four corners: the un-normalised direction is affine in the raster position (render.hpp:47-60).  If the
-// scene's root box lies outside one of the pyramid's four side planes, no ray of the tile can enter it, and every such ray is a
-// miss in the reference too (its first act is the slab test of the root box, kd_tree_simd.hpp:200-203).  The test is
-// conservative by a margin of 1e-3 of the camera-to-box distance - about half a pixel at 1080p, a thousand times the rounding
-// of the reference's slab test and of this plane arithmetic - so tiles that graze the box are traced as before.  A NaN
-// anywhere keeps the tile.  Culled tiles get their miss colour here; the tiles that remain are listed for the stream kernel.
-__device__ __forceinline__ V3 tile_corner_dir(const DScene& sc, float tan_half_fov, float x, float y) {
-    const float aspect = float(sc.width) / float(sc.height);
-    const float sx = ((2.0f * (x / float(sc.width))) - 1.0f) * aspect * tan_half_fov;
-    const float sy = (1.0f - (2.0f * (y / float(sc.height)))) * tan_half_fov;
-    const float* m = sc.cam_m;
-    return mk(m[0] * sx + m[3] * sy - m[6], m[1] * sx + m[4] * sy - m[7], m[2] * sx + m[5] * sy - m[8]);
-}
-__device__ __forceinline__ bool tile_misses_box(const DScene& sc, const FrameParams& fp, float x0, float y0, float x1, float y1) {
-    const float th = float(fp.tan_half_fov);
-    const V3 c[4] = {tile_corner_dir(sc, th, x0, y0), tile_corner_dir(sc, th, x1, y0), tile_corner_dir(sc, th, x1, y1),
-                     tile_corner_dir(sc, th, x0, y1)};
-    const V3 centre = (c[0] + c[1]) + (c[2] + c[3]);
-    const V3 o = mk(sc.cam_pos[0], sc.cam_pos[1], sc.cam_pos[2]);
-    const V3 lo = mk(sc.root_min[0], sc.root_min[1], sc.root_min[2]) - o, hi = mk(sc.root_max[0], sc.root_max[1], sc.root_max[2]) - o;
-    const float reach = fmaxf(fabsf(lo.x), fabsf(hi.x)) + fmaxf(fabsf(lo.y), fabsf(hi.y)) + fmaxf(fabsf(lo.z), fabsf(hi.z));
-    bool outside = false;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        V3 n = cross(c[e], c[(e + 1) & 3]);
-        if (dot(n, centre) > 0.0f) n = -n;                                       // the pyramid is the side n . p <= 0
-        // the box corner that is deepest on the pyramid's side of the plane
-        const float d = n.x * (n.x > 0.0f ? lo.x : hi.x) + n.y * (n.y > 0.0f ? lo.y : hi.y) + n.z * (n.z > 0.0f ? lo.z : hi.z);
-        outside = outside || (d > 1e-3f * reach * __fsqrt_rn(len2(n)));
-    }
-    return outside;
-}
-
+// rt_tilecull.cuh: all camera rays of an 8x4 pixel tile lie in the pyramid through the tile's four corners; if the scene's root
+// box is outside one of its side planes (by a margin far above any rounding), every ray of the tile is a miss in the reference
+// too - its first act is the slab test of the root box (kd_tree_simd.hpp:200-203).  Culled tiles get their miss colour here (or
+// nothing, in a pass that k_accumulate finishes); the tiles that remain are listed for the stream kernel.
 __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, float* __restrict__ fb, int divide, PassState* __restrict__ ps,
                                                    uint32_t* __restrict__ tile_list) {
     pdl_wait();
     const uint32_t n_tiles = fp.plane >> 5, lane = threadIdx.x & 31u, FULL = 0xFFFFFFFFu;
     const V3 miss = first_pass_miss_colour(sc, fp, divide);
+    TileCamera cam;
+    for (int k = 0; k < 9; ++k) cam.m[k] = sc.cam_m[k];
+    for (int k = 0; k < 3; ++k) cam.pos[k] = sc.cam_pos[k];
+    cam.width = float(sc.width); cam.height = float(sc.height); cam.tan_half_fov = float(fp.tan_half_fov);
     uint32_t n_culled = 0;
     for (uint32_t base = first_chunk(); base < n_tiles; base += chunk_stride()) {                        // 32 tiles per warp and round
         const uint32_t t = base + lane;
@@ -316,7 +291,7 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
         if (t < n_tiles) {
             lx0 = (t % fp.tiles_x) * 8u; ly0 = (t / fp.tiles_x) * 4u;
             w = min(8u, fp.tw - lx0); h = min(4u, fp.th - ly0);
-            cull = tile_misses_box(sc, fp, float(fp.x0 + lx0), float(fp.y0 + ly0), float(fp.x0 + lx0 + w), float(fp.y0 + ly0 + h));
+            cull = tile_misses_box(cam, sc.root_min, sc.root_max, float(fp.x0 + lx0), float(fp.y0 + ly0), float(fp.x0 + lx0 + w), float(fp.y0 + ly0 + h));
         }
         const uint32_t keep = __ballot_sync(FULL, t < n_tiles && !cull);
         uint32_t slot = 0;

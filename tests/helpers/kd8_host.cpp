@@ -66,3 +66,14 @@ extern "C" void bvh_trace_batch_counts(const float* nodes16, const float* tris, 
         tri_tests[i] = uint32_t(g_kd8_tris - t0);
     }
 }
+
+// the tile-culling predicate of k_tile_cull (csrc/rt_tilecull.cuh), one raster rectangle per call
+#include "../../simd-raytracer_b200/csrc/rt_tilecull.cuh"
+extern "C" int tile_misses_box_host(const float* m9, const float* pos3, float width, float height, float tan_half_fov, const float* lo3,
+                                    const float* hi3, float x0, float y0, float x1, float y1) {
+    rtb::TileCamera c;
+    for (int k = 0; k < 9; ++k) c.m[k] = m9[k];
+    for (int k = 0; k < 3; ++k) c.pos[k] = pos3[k];
+    c.width = width; c.height = height; c.tan_half_fov = tan_half_fov;
+    return rtb::tile_misses_box(c, lo3, hi3, x0, y0, x1, y1) ? 1 : 0;
+}

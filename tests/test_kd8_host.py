@@ -182,3 +182,68 @@ def test_rays_from_walls_edges_and_triangles(rt, oracle_mod, kd8):
                 assert np.array_equal(tuv[h].view(np.uint32), want_tuv[h].view(np.uint32))
                 if org is on_tris:
                     assert rerun.mean() < 2e-2
+
+
+# ---- tile culling (csrc/rt_tilecull.cuh) --------------------------------------------------------------------------------------
+def _camera_dirs(m, W, H, tan_half, xs, ys):
+    """un-normalised camera-ray directions of render/render.hpp:47-60 in float64 for raster positions xs x ys"""
+    X, Y = np.meshgrid(xs, ys)
+    sx = (2.0 * (X / W) - 1.0) * (W / H) * tan_half
+    sy = (1.0 - 2.0 * (Y / H)) * tan_half
+    m = m.reshape(3, 3)
+    v = np.stack([sx, sy, -np.ones_like(sx)], axis=-1)
+    return v @ m                                           # transpose(M) * v  ==  v (row) * M
+
+
+def _hits_box(o, d, lo, hi):
+    """exact (float64) slab test, t >= 0, of rays o + t d against the closed box"""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1, t2 = (lo - o) / d, (hi - o) / d
+    tn, tf = np.minimum(t1, t2), np.maximum(t1, t2)
+    par = d == 0                                            # parallel to a slab: inside it or never
+    inside = (o >= lo) & (o <= hi)
+    tn = np.where(par, np.where(inside, -np.inf, np.inf), tn)
+    tf = np.where(par, np.where(inside, np.inf, -np.inf), tf)
+    return np.maximum(tn.max(-1), 0.0) <= tf.min(-1)
+
+
+def test_tile_culling_predicate_is_conservative_and_effective(tmp_path):
+    """k_tile_cull's predicate on the CPU: whenever it says "no ray of this 8x4 tile reaches the box", an exact float64 slab
+    test of a 9x9 grid of raster positions in the tile (corners and edges included) agrees for every one of them; and it is
+    not vacuous - over cameras that see the box in a part of the frame most of the empty tiles are culled."""
+    out = tmp_path / "libkd8_host.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                           os.path.join(REPO, "tests", "helpers", "kd8_host.cpp"), "-o", str(out)])
+    lib = C.CDLL(str(out))
+    lib.tile_misses_box_host.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p] + [C.c_float] * 4
+    rng = np.random.default_rng(11)
+    W, H = 192, 120
+    culled = empty = wrong = 0
+    for k in range(40):
+        ang = rng.uniform(-np.pi, np.pi, 3)
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        R = (np.asarray([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]) @ np.asarray([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+             np.asarray([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]))
+        if k % 4 == 3:
+            R = R @ np.asarray([[1.0, 0.4, 0.0], [0.0, 0.7, 0.1], [0.2, 0.0, 1.3]])
+        m = np.ascontiguousarray(R.reshape(-1), np.float32)
+        lo = rng.uniform(-1, 0.5, 3).astype(np.float32)
+        hi = (lo + rng.uniform(0.05, 1.5, 3)).astype(np.float32)
+        if k % 5 == 0:
+            hi[k % 3] = lo[k % 3]                            # a flat box (the floor of a scene)
+        pos = rng.uniform(-3, 3, 3).astype(np.float32)
+        if np.all((lo <= pos) & (pos <= hi)):
+            pos[0] = hi[0] + 1.0                             # the host only culls with the camera outside the box
+        tan_half = np.float32(np.tan(np.radians(rng.choice([30.0, 90.0, 150.0])) / 2))
+        m64, pos64, lo64, hi64 = m.astype(np.float64), pos.astype(np.float64), lo.astype(np.float64), hi.astype(np.float64)
+        for ty in range(0, H, 4):
+            for tx in range(0, W, 8):
+                x1, y1 = min(tx + 8, W), min(ty + 4, H)
+                d = _camera_dirs(m64, W, H, float(tan_half), np.linspace(tx, x1, 9), np.linspace(ty, y1, 9)).reshape(-1, 3)
+                hit = _hits_box(pos64, d, lo64, hi64)
+                says_miss = lib.tile_misses_box_host(m.ctypes.data, pos.ctypes.data, W, H, tan_half, lo.ctypes.data, hi.ctypes.data, tx, ty, x1, y1)
+                empty += int(not hit.any())
+                culled += int(says_miss)
+                wrong += int(says_miss and hit.any())
+    assert wrong == 0
+    assert culled >= 0.8 * empty, (culled, empty)            # sub-pixel margin: nearly every empty tile is culled
