@@ -242,6 +242,7 @@ RT_API int rt_resolve_sum_device(rt_scene* s, const float* d_sum, uint32_t spp_t
 #define RT_PEER_MAX_RANKS 16
 #define RT_PEER_OUT_RGB 1u          /* float result in rank 0's rt_peer_result_rgb()  */
 #define RT_PEER_OUT_RGB8 2u         /* 8-bit result in rank 0's rt_peer_result_rgb8() */
+#define RT_PEER_OUT_HOST_RGB 4u     /* float result in the shared HOST frame (rt_peer_host_result_attach) */
 typedef struct rt_peer_group rt_peer_group;
 RT_API int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t width, uint32_t height, rt_peer_group** out,
                                 uint8_t* handle /* RT_PEER_HANDLE_BYTES, may be null */);
@@ -267,6 +268,13 @@ RT_API int rt_peer_wait_done(rt_peer_group* g, void* stream);
  * rt_peer_download_result only queues the copies on `stream`; rt_peer_read_result also synchronises `stream`.              */
 RT_API int rt_peer_download_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream);
 RT_API int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream);
+/* Shared host result (one process per GPU): every rank maps and pins the SAME host frame - the POSIX shared-memory object
+ * `shm_name` ("/name"; rank 0 passes create = 1 first, the others attach after a barrier, then rank 0 may shm_unlink it) - and
+ * rt_peer_reduce_resolve(..., RT_PEER_OUT_HOST_RGB) makes every rank copy ITS slice of the combined float frame into it with
+ * its own copy engine over its own PCIe link: N links carry the frame instead of rank 0's one.  *host_rgb = this process's
+ * mapping: two frames of height*width*3 floats; frame e (the e-th rt_peer_signal_ready) is in slot (e - 1) & 1 and is complete,
+ * on any rank, once that rank's rt_peer_wait_done for the frame has completed (render/render.hpp:18-108 returns this image). */
+RT_API int rt_peer_host_result_attach(rt_peer_group* g, const char* shm_name, int create, float** host_rgb);
 RT_API void rt_peer_group_destroy(rt_peer_group* g);
 
 #ifdef __cplusplus

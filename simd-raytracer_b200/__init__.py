@@ -40,7 +40,7 @@ ABI_SYMBOLS = (
     "rt_resolve_sum_device",
     "rt_peer_group_create", "rt_peer_group_connect", "rt_peer_group_connect_local", "rt_peer_framebuffer", "rt_peer_result_rgb",
     "rt_peer_result_rgb8", "rt_peer_combine", "rt_peer_signal_ready", "rt_peer_reduce_resolve", "rt_peer_wait_done",
-    "rt_peer_download_result", "rt_peer_read_result", "rt_peer_group_destroy",
+    "rt_peer_download_result", "rt_peer_read_result", "rt_peer_group_destroy", "rt_peer_host_result_attach",
 )
 
 
@@ -166,6 +166,7 @@ def _load():
     L.rt_peer_wait_done.argtypes = [vp, vp]
     L.rt_peer_read_result.argtypes = [vp, vp, vp, vp]
     L.rt_peer_download_result.argtypes = [vp, vp, vp, vp]
+    L.rt_peer_host_result_attach.argtypes = [vp, C.c_char_p, i32, C.POINTER(vp)]
     L.rt_peer_group_destroy.argtypes = [vp]
     L.rt_peer_group_destroy.restype = None
     return L
@@ -424,7 +425,7 @@ class Scene:
 
 
 PEER_HANDLE_BYTES = 64
-PEER_OUT_RGB, PEER_OUT_RGB8 = 1, 2
+PEER_OUT_RGB, PEER_OUT_RGB8, PEER_OUT_HOST_RGB = 1, 2, 4
 
 
 class PeerGroup:
@@ -488,6 +489,14 @@ class PeerGroup:
         """rank 0: queue the copy of the combined float frame (of the frame signalled last) into pinned `rgb`; no sync"""
         assert rgb.dtype == np.float32 and rgb.size == self.height * self.width * 3 and rgb.flags["C_CONTIGUOUS"]
         _check(lib.rt_peer_download_result(self.h, rgb.ctypes.data, None, _stream(stream)))
+
+    def attach_host_result(self, shm_name: str, create: bool) -> np.ndarray:
+        """map and pin the shared host frame (two slots of (H, W, 3) float32); frame e lands in slot (e - 1) & 1 when
+        reduce_resolve is called with PEER_OUT_HOST_RGB.  The array is a view of the mapping: drop it before close()."""
+        p = C.c_void_p()
+        _check(lib.rt_peer_host_result_attach(self.h, shm_name.encode(), int(create), C.byref(p)))
+        n = 2 * self.height * self.width * 3
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).reshape(2, self.height, self.width, 3)
 
     def close(self) -> None:
         if self.h:

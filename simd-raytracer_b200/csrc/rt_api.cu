@@ -17,6 +17,11 @@
 #include <string>
 #include <vector>
 
+#include <cerrno>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include "../../include/rt_b200.h"
 #include "../host/kd_build.hpp"
 #include "../host/scene.hpp"
@@ -1192,6 +1197,11 @@ struct rt_peer_group {
     bool connected = false;
     uint32_t epoch = 0;                     // frames signalled so far; frame e lives in slot (e - 1) & 1
     PeerTable table{};
+    // shared host result: a POSIX shared-memory object every rank's process maps and pins; two frame slots like the device's
+    float* host_map = nullptr;              // this process's mapping (2 x n floats)
+    float* host_dev = nullptr;              // the same memory as this device addresses it
+    size_t host_bytes = 0;
+    uint32_t host_epoch = 0;                // last frame that was sent to the shared host frame
     size_t next_slot() const { return size_t(epoch & 1u) * slot_bytes; }           // where the NEXT frame is rendered
     size_t last_slot() const { return size_t((epoch - 1u) & 1u) * slot_bytes; }    // the frame signalled last
 };
@@ -1311,6 +1321,7 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
     return guarded([&] {
         if (!g || !g->connected || spp_total == 0) throw rt_error(RT_ERR_BAD_ARG, "bad argument");
         if (g->epoch == 0) throw rt_error(RT_ERR_BAD_ARG, "rt_peer_signal_ready has not been called for this frame");
+        if ((outputs & RT_PEER_OUT_HOST_RGB) && !g->host_dev) throw rt_error(RT_ERR_BAD_ARG, "RT_PEER_OUT_HOST_RGB without rt_peer_host_result_attach");
         CK(cudaSetDevice(g->device));
         const uint64_t n4 = g->n / 4;
         const uint64_t g0 = n4 * g->rank / g->world, g1 = n4 * (g->rank + 1) / g->world;
@@ -1322,7 +1333,18 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
         k_peer_reduce_resolve<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             g->table, uint64_t(g->last_slot() / 4), int(g->world), int(g->rank), g0, g1, float(spp_total),
             (outputs & 1u) ? reinterpret_cast<float*>(root + g->off_rgb) : nullptr, (outputs & 2u) ? root + g->off_rgb8 : nullptr,
-            g->epoch, n4 * 4, g->n);
+            g->epoch, n4 * 4, g->n, (outputs & RT_PEER_OUT_HOST_RGB) ? reinterpret_cast<float*>(g->block + g->last_slot() + g->off_rgb) : nullptr);
+        CK(cudaGetLastError());
+        if (outputs & RT_PEER_OUT_HOST_RGB) {
+            // this rank's slice: its own copy engine, its own PCIe link; then tell every rank (the consumer waits in rt_peer_wait_done)
+            const uint64_t f0 = g0 * 4, f1 = (g->rank + 1 == g->world) ? g->n : g1 * 4;
+            CK(cudaMemcpyAsync(g->host_map + size_t((g->epoch - 1u) & 1u) * g->n + f0,
+                               reinterpret_cast<const float*>(g->block + g->last_slot() + g->off_rgb) + f0, (f1 - f0) * sizeof(float),
+                               cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+            k_peer_signal_host<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table, int(g->world), int(g->rank), g->epoch);
+            g->host_epoch = g->epoch;
+        }
+
         CK(cudaGetLastError());
         return int(RT_OK);
     });
@@ -1334,6 +1356,10 @@ int rt_peer_wait_done(rt_peer_group* g, void* stream) {
         CK(cudaSetDevice(g->device));
         k_peer_wait_done<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch);
         CK(cudaGetLastError());
+        if (g->host_epoch == g->epoch) {          // this frame also goes to the shared host frame: every rank's slice has landed
+            k_peer_wait_host<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch);
+            CK(cudaGetLastError());
+        }
         return int(RT_OK);
     });
 }
@@ -1365,10 +1391,34 @@ int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* strea
     });
 }
 
+int rt_peer_host_result_attach(rt_peer_group* g, const char* shm_name, int create, float** host_rgb) {
+    return guarded([&] {
+        if (!g || !shm_name || shm_name[0] != '/' || !host_rgb) throw rt_error(RT_ERR_BAD_ARG, "bad argument (the name must start with '/')");
+        if (g->host_map) throw rt_error(RT_ERR_BAD_ARG, "a host result is already attached");
+        CK(cudaSetDevice(g->device));
+        const size_t bytes = (2 * g->n * sizeof(float) + 4095) & ~size_t(4095);
+        const int fd = shm_open(shm_name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+        if (fd < 0) throw rt_error(RT_ERR_IO, std::string("shm_open ") + shm_name + ": " + std::strerror(errno));
+        if (create && ftruncate(fd, off_t(bytes)) != 0) { const int e = errno; close(fd); throw rt_error(RT_ERR_IO, std::string("ftruncate: ") + std::strerror(e)); }
+        void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        const int e = errno;
+        close(fd);
+        if (p == MAP_FAILED) throw rt_error(RT_ERR_IO, std::string("mmap: ") + std::strerror(e));
+        const cudaError_t ce = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+        if (ce != cudaSuccess) { munmap(p, bytes); throw cuda_error{ce, "cudaHostRegister"}; }
+        void* d = nullptr;
+        CK(cudaHostGetDevicePointer(&d, p, 0));
+        g->host_map = static_cast<float*>(p); g->host_dev = static_cast<float*>(d); g->host_bytes = bytes;
+        *host_rgb = g->host_map;
+        return int(RT_OK);
+    });
+}
+
 void rt_peer_group_destroy(rt_peer_group* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     cudaDeviceSynchronize();
+    if (g->host_map) { cudaHostUnregister(g->host_map); munmap(g->host_map, g->host_bytes); }
     for (uint32_t r = 0; r < g->world; ++r)
         if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
     if (g->block) cudaFree(g->block);

@@ -7,7 +7,10 @@
 // of every peer's framebuffer straight through NVLink (P2P loads on cudaIpc-mapped pointers), adds them in rank order - rank
 // r holds sample slice r, so this is the reference's sample order and the result is bit-identical to the single-GPU frame
 // when every rank renders one sample - divides, quantises, and stores the float and 8-bit slices into the root's result
-// buffers (P2P stores).  The last block publishes "rank r done with frame e" to every peer; k_peer_wait_done then orders the
+// buffers (P2P stores).  With a shared host result attached (rt_peer_host_result_attach) the slice is also kept in the rank's
+// OWN result buffer, from where the rank's copy engine moves it into the frame in HOST memory that every rank's process maps:
+// N PCIe links carry the frame instead of rank 0's one (k_peer_signal_host / k_peer_wait_host order the consumer behind the
+// copies; storing into host memory from the kernel itself was measured at a third of the copy engine's rate).  The last block publishes "rank r done with frame e" to every peer; k_peer_wait_done then orders the
 // next frame behind everybody's reads.  No host round trip, no staging copy, one NVLink crossing per byte.
 //
 // Flags live in each rank's own block and are written remotely by peers with system-scope release stores.  Epochs only
@@ -22,7 +25,8 @@ namespace rtb {
 constexpr int PEER_MAX = 16;
 constexpr int PEER_FLAG_READY = 0;            // flags[PEER_FLAG_READY + r] = last frame rank r has rendered
 constexpr int PEER_FLAG_DONE = PEER_MAX;      // flags[PEER_FLAG_DONE + r]  = last frame rank r has finished reducing
-constexpr int PEER_FLAG_COUNT = 2 * PEER_MAX + 2;   // [2*PEER_MAX] = block counter of the local reduce kernel
+constexpr int PEER_FLAG_HOST = 2 * PEER_MAX + 2;    // flags[PEER_FLAG_HOST + r]  = last frame whose slice rank r has copied into the shared host frame
+constexpr int PEER_FLAG_COUNT = 3 * PEER_MAX + 2;   // [2*PEER_MAX] = block counter of the local reduce kernel
 
 struct PeerTable {
     const float* fb[PEER_MAX];                // every rank's raw sample sums (height*width*3 floats), frame slot 0
@@ -46,6 +50,17 @@ __global__ void k_peer_signal_ready(PeerTable t, int world, int rank, uint32_t e
     if (i < world) st_release_sys(t.flags[i] + PEER_FLAG_READY + rank, epoch);
 }
 
+// "my slice of frame `epoch` is in the shared host frame": one remote store per peer, behind the copy in stream order
+__global__ void k_peer_signal_host(PeerTable t, int world, int rank, uint32_t epoch) {
+    const int i = threadIdx.x;
+    if (i < world) { __threadfence_system(); st_release_sys(t.flags[i] + PEER_FLAG_HOST + rank, epoch); }
+}
+__global__ void k_peer_wait_host(const uint32_t* my_flags, int world, uint32_t epoch) {
+    const int i = threadIdx.x;
+    if (i < world)
+        while (ld_acquire_sys(my_flags + PEER_FLAG_HOST + i) < epoch) __nanosleep(64);
+}
+
 __global__ void k_peer_wait_done(const uint32_t* my_flags, int world, uint32_t epoch) {
     const int i = threadIdx.x;
     if (i < world)
@@ -60,7 +75,7 @@ __device__ __forceinline__ uint8_t peer_quantise(float c) {          // io/image
 // n4 = number of float4 groups of the whole frame; this rank owns groups [g0, g1)
 __global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, uint64_t slot_floats, int world, int rank, uint64_t g0, uint64_t g1, float div,
                                                              float* __restrict__ root_rgb, uint8_t* __restrict__ root_rgb8,
-                                                             uint32_t epoch, uint64_t n_tail_begin, uint64_t n_total) {
+                                                             uint32_t epoch, uint64_t n_tail_begin, uint64_t n_total, float* __restrict__ own_rgb) {
     // ---- wait until every peer has rendered frame `epoch` (flags are in MY memory, peers store into them) ----
     if (threadIdx.x < world)
         while (ld_acquire_sys(t.flags[rank] + PEER_FLAG_READY + threadIdx.x) < epoch) __nanosleep(32);
@@ -83,6 +98,7 @@ __global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, uint64
         }
         s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);   // :74
         if (root_rgb) reinterpret_cast<float4*>(root_rgb)[g] = s;
+        if (own_rgb) reinterpret_cast<float4*>(own_rgb)[g] = s;            // this rank's slice in its OWN memory: copied to the shared host frame next
         if (root_rgb8)
             reinterpret_cast<uchar4*>(root_rgb8)[g] = make_uchar4(peer_quantise(s.x), peer_quantise(s.y), peer_quantise(s.z), peer_quantise(s.w));
     }
@@ -93,6 +109,7 @@ __global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, uint64
             for (int r = 1; r < world; ++r) s = s + __ldcg(t.fb[r] + slot_floats + i);
             s = __fdiv_rn(s, div);
             if (root_rgb) root_rgb[i] = s;
+            if (own_rgb) own_rgb[i] = s;
             if (root_rgb8) root_rgb8[i] = peer_quantise(s);
         }
     }

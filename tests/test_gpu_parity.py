@@ -458,6 +458,46 @@ def test_peer_combine_equals_single_gpu_frame(rt, size):
         g.close()
 
 
+def test_peer_combine_into_the_shared_host_frame(rt):
+    """rt_peer_host_result_attach: every rank maps and pins the same POSIX shared-memory frame and stores ITS slice of the
+    combined frame straight into it (RT_PEER_OUT_HOST_RGB), so N PCIe links carry the frame and nobody downloads it.  Emulated
+    ranks in one process (each with its own mapping of the object); three frames alternate the two host slots."""
+    import os
+    import torch
+    size = (322, 181)
+    s, _ = gpu_scene(rt, "hw11_scene8", size=size)
+    world = 4
+    st = torch.cuda.current_stream().cuda_stream
+    groups = [rt.PeerGroup(world, r, 0, size[0], size[1]) for r in range(world)]
+    rt.PeerGroup.connect_local(groups)
+    name = f"/rt_b200_test_{os.getpid()}"
+    views = [g.attach_host_result(name, create=(r == 0)) for r, g in enumerate(groups)]
+    os.unlink("/dev/shm" + name)                                  # the mappings keep the object alive
+    with pytest.raises(rt.RtError):
+        groups[0].attach_host_result(name, create=False)          # already attached
+    for frame, depth in enumerate((3, 1, 2)):
+        kw = dict(max_ray_depth=depth)
+        want = s.render_frame(rt.default_params(samples_per_pixel=world, **kw))
+        for r, g in enumerate(groups):
+            first, count = rt.spp_slice(world, r, world)
+            s.render_frame_device(rt.default_params(samples_per_pixel=count, sample_offset=first, spp_total=world,
+                                                    flags=rt.FLAG_RAW_SUM, **kw), g.framebuffer, stream=st)
+        for g in groups:
+            g.signal_ready(st)
+        for g in groups:
+            g.reduce_resolve(world, rt.PEER_OUT_HOST_RGB | rt.PEER_OUT_RGB, stream=st)
+        for g in groups:
+            g.wait_done(st)
+        torch.cuda.synchronize()
+        for v in views:                                           # every process-side mapping sees the whole frame
+            assert np.array_equal(v[frame & 1].view(np.uint32), want.view(np.uint32)), frame
+        rgb, _ = groups[0].read_result(st)
+        assert np.array_equal(rgb.view(np.uint32), want.view(np.uint32))
+    del views, v
+    for g in groups:
+        g.close()
+
+
 def test_peer_combine_pipelined_over_two_frame_slots(rt):
     """The pipelined use of the peer combine (bench.py --gpus N): frame i is queued on each rank's render stream
     (rt_render_frame_device_begin, no host sync) while frame i-1 is reduced on a second stream; every rank owns two frame
