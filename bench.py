@@ -271,16 +271,29 @@ def main() -> None:
         dist.barrier()
         # the end-to-end frames land in ONE host frame that every rank's process maps and pins (POSIX shared memory): every
         # rank stores its slice of the combined frame over its own PCIe link, nobody downloads it (rt_peer_host_result_attach)
+        # (falls back to downloading the frame from rank 0 when the shared-memory object cannot be created, e.g. a small /dev/shm)
+        host_frames = None
         shm = [f"/rt_b200_bench_{os.getpid()}" if rank == 0 else None]
+        if rank == 0:
+            try:
+                host_frames = peer.attach_host_result(shm[0], create=True)
+            except rt.RtError as e:
+                print(f"bench: no shared host frame ({e}); rank 0 downloads the combined frame instead", file=sys.stderr)
+                shm[0] = None
         dist.broadcast_object_list(shm, src=0)
-        if rank == 0:
-            host_frames = peer.attach_host_result(shm[0], create=True)
-        dist.barrier()
-        if rank != 0:
-            host_frames = peer.attach_host_result(shm[0], create=False)
-        dist.barrier()
-        if rank == 0:
-            os.unlink("/dev/shm" + shm[0])
+        if rank != 0 and shm[0]:
+            try:
+                host_frames = peer.attach_host_result(shm[0], create=False)
+            except rt.RtError as e:
+                print(f"bench: rank {rank} cannot attach the shared host frame ({e})", file=sys.stderr)
+        ok = torch.tensor([1 if host_frames is not None else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)             # all ranks or none
+        all_attached = int(ok.item()) == 1                    # .item() waits for the collective: every rank has tried by now
+        if rank == 0 and shm[0]:
+            os.unlink("/dev/shm" + shm[0])                    # the mappings keep the object alive
+        if not all_attached:
+            host_frames = None
+    shared_host = peer is not None and host_frames is not None
     # N > 1, peer combine: one step = the render of frame i (main stream) and, concurrently on a second stream, the fused
     # wait+reduce+resolve of frame i-1 (rt_peer_* keeps two frame slots per rank).  The combine is released by the step's
     # start event, so every timed step [a, b] contains exactly one render and one combine; nothing runs during the L2 flush.
@@ -436,13 +449,19 @@ def main() -> None:
             scene.frame_wait(prev)
             return 0
         redo = 0
+        ev_dl = torch.cuda.Event()
         for i in range(k + 1):
             e = torch.cuda.Event()
             e.record(stream)
-            if i > 0:
-                # frame i-1: every rank reduces its slice and stores it into the shared HOST frame (side stream); complete when
-                # rank 0 has seen every rank's DONE flag (rt_peer_wait_done inside combine_pending)
+            if i > 0 and shared_host:
+                # frame i-1: every rank reduces its slice and copies it into the shared HOST frame (side stream); complete when
+                # this rank has seen every rank's flags (rt_peer_wait_done inside combine_pending)
                 combine_pending(e, rt.PEER_OUT_HOST_RGB)
+            elif i > 0:
+                combine_pending(e)                                # frame i-1: reduce + resolve into rank 0, side stream
+                if rank == 0:
+                    peer.download_result(host2_np if (i - 1) & 1 else host_np, stream=side.cuda_stream)
+                    ev_dl.record(side)
             t = None
             if i < k:
                 t = scene.render_frame_device_begin(params, peer.framebuffer, stream=stream.cuda_stream)
@@ -450,7 +469,7 @@ def main() -> None:
                 if i > 0:
                     stream.wait_event(ev_done)
             if i > 0:
-                ev_done.synchronize()                             # frame i-1 is in host memory (all slices, all ranks)
+                (ev_dl if (rank == 0 and not shared_host) else ev_done).synchronize()   # frame i-1 is in host memory
             if t is not None:
                 redo += bool(scene.frame_wait(t))
         return redo
@@ -494,7 +513,7 @@ def main() -> None:
                 verify = {"combined_frame_finite": bool(np.isfinite(got).all()), "rgb8_nonzero": int((got8 != 0).sum())}
         barrier()
 
-    if peer and rank == 0 and verify is not None and "combined_frame_equals_single_gpu_spp_N_frame" in verify:
+    if shared_host and rank == 0 and verify is not None and "combined_frame_equals_single_gpu_spp_N_frame" in verify:
         # both host slots hold the frame of the last two sequence steps (same parameters every step)
         verify["host_frames_equal_single_gpu_spp_N_frame"] = bool(np.array_equal(host_frames[0].view(np.uint32), want.view(np.uint32)) and
                                                                   np.array_equal(host_frames[1].view(np.uint32), want.view(np.uint32)))
@@ -550,9 +569,12 @@ def main() -> None:
                     "api": ("rt_render_frame_begin + rt_frame_wait (frame sequence: params in, float frame out to pinned host memory "
                             "every step; frame i's download overlaps frame i+1's render)" if world == 1 else
                             ("rt_render_frame_device_begin per rank, rt_peer_* combine on a second stream (overlaps frame i+1's render) "
-                             "with RT_PEER_OUT_HOST_RGB: every rank stores its slice of the combined float frame into the shared pinned "
+                             "with RT_PEER_OUT_HOST_RGB: every rank copies its slice of the combined float frame into the shared pinned "
                              "host frame over its own PCIe link (rt_peer_host_result_attach); d2h_bytes_per_step is the sum over ranks"
-                             if peer else
+                             if shared_host else
+                             "rt_render_frame_device_begin per rank, rt_peer_* combine + rt_peer_download_result on a second stream "
+                             "(frame i's combine and download overlap frame i+1's render), float frame in pinned host memory on rank 0 "
+                             "every step" if peer else
                              "rt_render_frame_device per rank + ncclReduce + resolve + float frame to pinned host memory on rank 0")),
                     "one_call_per_frame": ({"value": rays_all * K / t_e2e_sync / 1e6, "ms_per_frame": 1e3 * t_e2e_sync / K,
                                             "api": ("rt_render_frame (synchronous: render, download, return)" if world == 1 else

@@ -1399,7 +1399,11 @@ int rt_peer_host_result_attach(rt_peer_group* g, const char* shm_name, int creat
         const size_t bytes = (2 * g->n * sizeof(float) + 4095) & ~size_t(4095);
         const int fd = shm_open(shm_name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
         if (fd < 0) throw rt_error(RT_ERR_IO, std::string("shm_open ") + shm_name + ": " + std::strerror(errno));
-        if (create && ftruncate(fd, off_t(bytes)) != 0) { const int e = errno; close(fd); throw rt_error(RT_ERR_IO, std::string("ftruncate: ") + std::strerror(e)); }
+        // posix_fallocate, not ftruncate: a /dev/shm that is too small must fail here (RT_ERR_IO), not with SIGBUS at the first store
+        if (create) {
+            const int fe = posix_fallocate(fd, 0, off_t(bytes));
+            if (fe != 0) { close(fd); shm_unlink(shm_name); throw rt_error(RT_ERR_IO, std::string("posix_fallocate (is /dev/shm large enough?): ") + std::strerror(fe)); }
+        }
         void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
         const int e = errno;
         close(fd);
