@@ -9,6 +9,7 @@ from tests.conftest import resized
 so = os.path.join(tempfile.mkdtemp(), "libkd8_host.so")
 subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", os.path.join(REPO, "tests/helpers/kd8_host.cpp"), "-o", so])
 lib = C.CDLL(so)
+lib.bvh4_node_count.restype = C.c_uint64
 rt = importlib.import_module("simd-raytracer_b200")
 scene = sys.argv[1] if len(sys.argv) > 1 else "hw09_scene5"
 W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (480, 270)
@@ -38,3 +39,12 @@ for kind, m, cu, far, ah in (("primary", cull, 1, None, 0), ("secondary", (~cull
     big = work > 4 * max(work.mean(), 1)
     print(f"  {kind:9s} n {n:7d}: node visits mean {work.mean():6.1f} p50 {q[0]:.0f} p90 {q[1]:.0f} p99 {q[2]:.0f} p99.9 {q[3]:.0f} max {q[4]:.0f}; "
           f"tri tests mean {tt.mean():5.1f} max {tt.max()}; queries over 4x the mean: {big.sum()} ({100*big.mean():.2f} %) holding {100*work[big].sum()/max(work.sum(),1):.1f} % of the visits")
+    # the same queries over the four-wide hierarchy (csrc/rt_bvh4.cuh, collapsed from the two-wide nodes)
+    nv4 = np.zeros(n, np.uint32); tuv = np.zeros((n, 3), np.float32); tri = np.zeros(n, np.int32)
+    lib.kd8_counters(None, None, 1)
+    lib.bvh4_trace_batch(C.c_void_p(nodes.ctypes.data), C.c_uint64(int(s.info.bvh_n_nodes)), C.c_void_p(tris.ctypes.data), C.c_void_p(root.ctypes.data),
+                         C.c_void_p(r.ctypes.data), C.c_uint64(n), cu, 0, C.c_float(1e-6), None if f is None else C.c_void_p(f.ctypes.data), ah,
+                         C.c_void_p(tuv.ctypes.data), C.c_void_p(tri.ctypes.data), None, C.c_void_p(nv4.ctypes.data))
+    a, b = C.c_uint64(0), C.c_uint64(0); lib.kd8_counters(C.byref(a), C.byref(b), 1)
+    w4 = nv4.astype(np.int64); q4 = np.percentile(w4, [50, 90, 99, 99.9, 100])
+    print(f"  {'':9s} four-wide : node visits mean {w4.mean():6.1f} p50 {q4[0]:.0f} p90 {q4[1]:.0f} p99 {q4[2]:.0f} p99.9 {q4[3]:.0f} max {q4[4]:.0f}; tri tests mean {b.value/max(n,1):5.1f}")

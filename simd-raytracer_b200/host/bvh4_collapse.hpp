@@ -1,0 +1,82 @@
+// host/bvh4_collapse.hpp - the four-wide hierarchy of csrc/rt_bvh4.cuh from the flattened two-wide one (BvhLayout::nodes,
+// host/bvh_build.cpp): a node's child list starts as its two children; while it holds fewer than four entries, the inner child
+// with the largest surface area is replaced by its own two children.  The child boxes are taken over unchanged (they carry the
+// builder's padding), leaves keep pointing into the same triangle records, nodes are emitted in DFS pre-order.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace rtb {
+
+struct Bvh4Child { float lo[3], hi[3]; uint32_t ref, cnt; };
+
+inline void bvh2_children(const uint32_t* nodes16, uint32_t node, Bvh4Child out[2]) {
+    float f[12];
+    std::memcpy(f, nodes16 + size_t(node) * 16, sizeof f);
+    const uint32_t* w = nodes16 + size_t(node) * 16 + 12;
+    out[0] = Bvh4Child{{f[0], f[1], f[2]}, {f[3], f[4], f[5]}, w[0], w[2]};
+    out[1] = Bvh4Child{{f[6], f[7], f[8]}, {f[9], f[10], f[11]}, w[1], w[3]};
+}
+
+inline float bvh4_area(const Bvh4Child& c) {
+    const float x = c.hi[0] - c.lo[0], y = c.hi[1] - c.lo[1], z = c.hi[2] - c.lo[2];
+    return x * y + y * z + z * x;
+}
+
+// nodes16: the two-wide nodes (16 words each), node 0 the root; returns the four-wide nodes (32 words each), node 0 the root
+inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_nodes2) {
+    constexpr uint32_t NO_CHILD = 0xFFFFFFFFu;
+    std::vector<uint32_t> out;
+    if (!n_nodes2) return out;
+    struct Todo { uint32_t node2, slot; };            // two-wide subtree root -> where its four-wide node index has to be written
+    std::vector<Todo> todo{{0u, NO_CHILD}};
+    while (!todo.empty()) {
+        const Todo t = todo.back();
+        todo.pop_back();
+        const uint32_t me = uint32_t(out.size() / 32);
+        if (t.slot != NO_CHILD) out[t.slot] = me;
+        Bvh4Child c[4];
+        int n = 2;
+        bvh2_children(nodes16, t.node2, c);
+        // a missing child of the two-wide node is dropped from the list
+        for (int k = 0; k < n;) { if (c[k].cnt == NO_CHILD) { c[k] = c[n - 1]; --n; } else ++k; }
+        while (n < 4) {
+            int best = -1;
+            for (int k = 0; k < n; ++k)
+                if (c[k].cnt == 0 && (best < 0 || bvh4_area(c[k]) > bvh4_area(c[best]))) best = k;
+            if (best < 0) break;
+            Bvh4Child g[2];
+            bvh2_children(nodes16, c[best].ref, g);
+            int m = 0;
+            Bvh4Child keep[2];
+            for (int k = 0; k < 2; ++k) if (g[k].cnt != NO_CHILD) keep[m++] = g[k];
+            if (m == 0) { c[best] = c[n - 1]; --n; continue; }
+            c[best] = keep[0];
+            if (m == 2) c[n++] = keep[1];
+        }
+        const size_t base = out.size();
+        out.resize(base + 32, 0u);
+        float f[24];
+        uint32_t ref[4], cnt[4];
+        for (int k = 0; k < 4; ++k) {
+            const bool have = k < n;
+            for (int a = 0; a < 3; ++a) {
+                f[a * 4 + k] = have ? c[k].lo[a] : 0.0f;
+                f[12 + a * 4 + k] = have ? c[k].hi[a] : 0.0f;
+            }
+            ref[k] = have ? c[k].ref : 0u;
+            cnt[k] = have ? c[k].cnt : NO_CHILD;
+        }
+        std::memcpy(out.data() + base, f, sizeof f);
+        std::memcpy(out.data() + base + 24, ref, sizeof ref);
+        std::memcpy(out.data() + base + 28, cnt, sizeof cnt);
+        // inner children: their four-wide index is patched in when they are emitted; pushed in reverse so that child 0 comes next
+        for (int k = n - 1; k >= 0; --k)
+            if (c[k].cnt == 0) todo.push_back({c[k].ref, uint32_t(base + 24 + k)});
+    }
+    return out;
+}
+
+}  // namespace rtb

@@ -77,3 +77,37 @@ extern "C" int tile_misses_box_host(const float* m9, const float* pos3, float wi
     c.width = width; c.height = height; c.tan_half_fov = tan_half_fov;
     return rtb::tile_misses_box(c, lo3, hi3, x0, y0, x1, y1) ? 1 : 0;
 }
+
+// ---- four-wide hierarchy (csrc/rt_bvh4.cuh), collapsed on the fly from the two-wide nodes the scene exports ----------------
+#include <map>
+#include <vector>
+#include "../../simd-raytracer_b200/csrc/rt_bvh4.cuh"
+#include "../../simd-raytracer_b200/host/bvh4_collapse.hpp"
+static const std::vector<uint32_t>& bvh4_of(const float* nodes16, uint64_t n_nodes2) {
+    static std::map<std::pair<const float*, uint64_t>, std::vector<uint32_t>> cache;
+    auto it = cache.find({nodes16, n_nodes2});
+    if (it == cache.end()) it = cache.emplace(std::make_pair(nodes16, n_nodes2), rtb::bvh4_collapse(reinterpret_cast<const uint32_t*>(nodes16), n_nodes2)).first;
+    return it->second;
+}
+extern "C" uint64_t bvh4_node_count(const float* nodes16, uint64_t n_nodes2) { return bvh4_of(nodes16, n_nodes2).size() / 32; }
+extern "C" void bvh4_trace_batch(const float* nodes16, uint64_t n_nodes2, const float* tris, const float* root6, const float* rays6, uint64_t n,
+                                 int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie,
+                                 uint32_t* node_visits) {
+    // a fresh collapse per batch unless the caller keeps the node array alive and unchanged (the cache is keyed by its address)
+    const std::vector<uint32_t> nodes4v = rtb::bvh4_collapse(reinterpret_cast<const uint32_t*>(nodes16), n_nodes2);
+    const float* nodes4 = reinterpret_cast<const float*>(nodes4v.data());
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* q = rays6 + 6 * i;
+        const float far = t_far ? t_far[i] : FLT_MAX;
+        const uint64_t n0 = g_kd8_nodes;
+        rtb::KdHit h;
+        if (cull) h = fast ? rtb::bvh4_trace<true, true>(nodes4, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
+                           : rtb::bvh4_trace<true, false>(nodes4, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        else h = fast ? rtb::bvh4_trace<false, true>(nodes4, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
+                      : rtb::bvh4_trace<false, false>(nodes4, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
+        tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
+        tri[i] = h.tri;
+        if (tie) tie[i] = (h.tri == rtb::KD_RERUN || (h.tri >= 0 && h.tie_t == h.t)) ? 1 : 0;
+        if (node_visits) node_visits[i] = uint32_t(g_kd8_nodes - n0);
+    }
+}

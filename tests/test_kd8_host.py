@@ -15,7 +15,7 @@ from .conftest import REPO, SCENES, resized, scene_bytes
 from .helpers import crtscene
 
 
-@pytest.fixture(scope="module", params=["bvh", "kd"])
+@pytest.fixture(scope="module", params=["bvh", "kd", "bvh4"])
 def kd8(tmp_path_factory, request):
     structure = request.param
     out = tmp_path_factory.mktemp("kd8") / "libkd8_host.so"
@@ -25,15 +25,23 @@ def kd8(tmp_path_factory, request):
     for fn in (lib.kd8_trace_batch, lib.bvh_trace_batch):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bvh4_trace_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     batch = lib.bvh_trace_batch if structure == "bvh" else lib.kd8_trace_batch
 
     def trace(scene, rays, cull, fast=False, t_far=None, any_hit=False, eps=np.float32(1e-6)):
-        nodes8, packets, root = scene.bvh_layout() if structure == "bvh" else scene.accel_layout()
+        nodes8, packets, root = scene.bvh_layout() if structure in ("bvh", "bvh4") else scene.accel_layout()
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         tuv = np.zeros((len(rays), 3), np.float32)
         tri = np.zeros(len(rays), np.int32)
         tie = np.zeros(len(rays), np.uint8)
         far = None if t_far is None else np.ascontiguousarray(t_far, np.float32)
+        if structure == "bvh4":
+            # the four-wide hierarchy (csrc/rt_bvh4.cuh), collapsed from the scene's two-wide nodes (host/bvh4_collapse.hpp)
+            lib.bvh4_trace_batch(nodes8.ctypes.data, int(scene.info.bvh_n_nodes), packets.ctypes.data, root.ctypes.data, rays.ctypes.data, len(rays),
+                                 int(cull), int(fast), C.c_float(eps), None if far is None else far.ctypes.data, int(any_hit),
+                                 tuv.ctypes.data, tri.ctypes.data, tie.ctypes.data, None)
+            return tuv, tri, tie.astype(bool)
         batch(nodes8.ctypes.data, packets.ctypes.data, root.ctypes.data, rays.ctypes.data, len(rays), int(cull), int(fast),
                             C.c_float(eps), None if far is None else far.ctypes.data, int(any_hit), tuv.ctypes.data, tri.ctypes.data, tie.ctypes.data)
         return tuv, tri, tie.astype(bool)
