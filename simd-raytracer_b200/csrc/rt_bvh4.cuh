@@ -24,8 +24,17 @@ namespace rtb {
 constexpr int BVH4_STACK = 64;
 constexpr uint32_t BVH4_NODE_FLOATS = 32;
 
+// compare-and-swap of two (entry distance, ref, cnt) triples: predicate selects only, nothing indexed at run time
+RT_HD void bvh4_order(float& ta, uint32_t& ra, uint32_t& ca, float& tb, uint32_t& rb, uint32_t& cb) {
+    const bool sw = tb < ta;
+    const float t = sw ? tb : ta; tb = sw ? ta : tb; ta = t;
+    const uint32_t r = sw ? rb : ra; rb = sw ? ra : rb; ra = r;
+    const uint32_t c = sw ? cb : ca; cb = sw ? ca : cb; ca = c;
+}
+
 // One inner-node visit (phase WALK): test the four children's boxes, go to the nearest one, push the others so that the
-// nearer one is popped first.
+// nearer one is popped first.  Children the ray does not touch get the key +inf; a five-comparator network sorts the four
+// keys; everything lives in scalars (registers on the device).
 RT_HD void bvh4_node_step(BvhState& s, BvhStackEntry* stack, const float* __restrict__ nodes) {
     const float lim = kd_min(s.best.t, s.t_far);
     bool pop = s.ref == BVH_SKIP;                                            // still dropping stack entries (bvh_pop)
@@ -37,25 +46,32 @@ RT_HD void bvh4_node_step(BvhState& s, BvhStackEntry* stack, const float* __rest
         const KdRow rr = kd_load_row(p + 24), cc = kd_load_row(p + 28);
         const float ix = kd_rcp_estimate(s.dx), iy = kd_rcp_estimate(s.dy), iz = kd_rcp_estimate(s.dz);
         const float cx = -(s.ox * ix), cy = -(s.oy * iy), cz = -(s.oz * iz);
-        const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
-        const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
-        const uint32_t ref[4] = {uint32_t(kd_as_int(rr.x)), uint32_t(kd_as_int(rr.y)), uint32_t(kd_as_int(rr.z)), uint32_t(kd_as_int(rr.w))};
-        const uint32_t cnt[4] = {uint32_t(kd_as_int(cc.x)), uint32_t(kd_as_int(cc.y)), uint32_t(kd_as_int(cc.z)), uint32_t(kd_as_int(cc.w))};
-        // the children the ray touches, ordered by entry distance (insertion into a list of at most four)
-        float et[4];
-        uint32_t er[4], ec[4];
-        int n = 0;
-        for (int k = 0; k < 4; ++k) {
-            float t_in, t_out;
-            bvh_slab(ix, iy, iz, cx, cy, cz, lx[k], ly[k], lz[k], hx[k], hy[k], hz[k], t_in, t_out);
-            if (!((cnt[k] != BVH_NO_CHILD) & (t_in <= t_out) & (t_in <= lim))) continue;
-            int j = n++;
-            while (j > 0 && et[j - 1] > t_in) { et[j] = et[j - 1]; er[j] = er[j - 1]; ec[j] = ec[j - 1]; --j; }
-            et[j] = t_in; er[j] = ref[k]; ec[j] = cnt[k];
-        }
-        for (int j = n - 1; j >= 1; --j) { bvh_stack_put(stack + s.sp, er[j], ec[j], et[j]); ++s.sp; }    // farthest first
-        pop = n == 0;
-        if (n) { s.ref = er[0]; s.cnt = ec[0]; s.phase = s.cnt ? KD8_LEAF : KD8_WALK; }
+        uint32_t r0 = uint32_t(kd_as_int(rr.x)), r1 = uint32_t(kd_as_int(rr.y)), r2 = uint32_t(kd_as_int(rr.z)), r3 = uint32_t(kd_as_int(rr.w));
+        uint32_t c0 = uint32_t(kd_as_int(cc.x)), c1 = uint32_t(kd_as_int(cc.y)), c2 = uint32_t(kd_as_int(cc.z)), c3 = uint32_t(kd_as_int(cc.w));
+        const float MISS = FLT_MAX;             // entry distances are <= lim <= FLT_MAX; a touched child at exactly FLT_MAX cannot be closer than a hit
+        float in, out, t0, t1, t2, t3;
+        bvh_slab(ix, iy, iz, cx, cy, cz, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, in, out);
+        const bool h0 = (c0 != BVH_NO_CHILD) & (in <= out) & (in <= lim); t0 = h0 ? in : MISS;
+        bvh_slab(ix, iy, iz, cx, cy, cz, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, in, out);
+        const bool h1 = (c1 != BVH_NO_CHILD) & (in <= out) & (in <= lim); t1 = h1 ? in : MISS;
+        bvh_slab(ix, iy, iz, cx, cy, cz, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, in, out);
+        const bool h2 = (c2 != BVH_NO_CHILD) & (in <= out) & (in <= lim); t2 = h2 ? in : MISS;
+        bvh_slab(ix, iy, iz, cx, cy, cz, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, in, out);
+        const bool h3 = (c3 != BVH_NO_CHILD) & (in <= out) & (in <= lim); t3 = h3 ? in : MISS;
+        // untouched children: the key alone would tie with a touched child at FLT_MAX, so they also lose their identity
+        c0 = h0 ? c0 : BVH_NO_CHILD; c1 = h1 ? c1 : BVH_NO_CHILD; c2 = h2 ? c2 : BVH_NO_CHILD; c3 = h3 ? c3 : BVH_NO_CHILD;
+        bvh4_order(t0, r0, c0, t1, r1, c1); bvh4_order(t2, r2, c2, t3, r3, c3);
+        bvh4_order(t0, r0, c0, t2, r2, c2); bvh4_order(t1, r1, c1, t3, r3, c3);
+        bvh4_order(t1, r1, c1, t2, r2, c2);
+        // an untouched child (cnt == NO_CHILD) may sort in front of a touched one only when both keys are FLT_MAX: skip by identity
+        if (c3 != BVH_NO_CHILD) { bvh_stack_put(stack + s.sp, r3, c3, t3); ++s.sp; }                     // farthest first
+        if (c2 != BVH_NO_CHILD) { bvh_stack_put(stack + s.sp, r2, c2, t2); ++s.sp; }
+        if (c0 != BVH_NO_CHILD) {
+            if (c1 != BVH_NO_CHILD) { bvh_stack_put(stack + s.sp, r1, c1, t1); ++s.sp; }
+            s.ref = r0; s.cnt = c0;
+        } else { s.ref = r1; s.cnt = c1; }       // only reachable when every touched key is FLT_MAX
+        pop = (c0 == BVH_NO_CHILD) & (c1 == BVH_NO_CHILD);
+        if (!pop) s.phase = s.cnt ? KD8_LEAF : KD8_WALK;
     }
     if (pop) bvh_pop(s, stack, lim);
 }
