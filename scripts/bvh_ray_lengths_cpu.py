@@ -48,3 +48,9 @@ for kind, m, cu, far, ah in (("primary", cull, 1, None, 0), ("secondary", (~cull
     a, b = C.c_uint64(0), C.c_uint64(0); lib.kd8_counters(C.byref(a), C.byref(b), 1)
     w4 = nv4.astype(np.int64); q4 = np.percentile(w4, [50, 90, 99, 99.9, 100])
     print(f"  {'':9s} four-wide : node visits mean {w4.mean():6.1f} p50 {q4[0]:.0f} p90 {q4[1]:.0f} p99 {q4[2]:.0f} p99.9 {q4[3]:.0f} max {q4[4]:.0f}; tri tests mean {b.value/max(n,1):5.1f}")
+    for width in (8, 16):      # statistics only: how many dependent node visits would wider nodes need?
+        nvw = np.zeros(n, np.uint32)
+        lib.bvh_wide_visit_counts(C.c_void_p(nodes.ctypes.data), C.c_uint64(int(s.info.bvh_n_nodes)), width, C.c_void_p(tris.ctypes.data), C.c_void_p(root.ctypes.data),
+                                  C.c_void_p(r.ctypes.data), C.c_uint64(n), cu, C.c_float(1e-6), None if f is None else C.c_void_p(f.ctypes.data), ah, C.c_void_p(nvw.ctypes.data))
+        ww = nvw.astype(np.int64); qw = np.percentile(ww, [50, 90, 99, 99.9, 100])
+        print(f"  {'':9s} {width:2d}-wide   : node visits mean {ww.mean():6.1f} p50 {qw[0]:.0f} p90 {qw[1]:.0f} p99 {qw[2]:.0f} p99.9 {qw[3]:.0f} max {qw[4]:.0f}")

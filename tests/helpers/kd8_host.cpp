@@ -111,3 +111,78 @@ extern "C" void bvh4_trace_batch(const float* nodes16, uint64_t n_nodes2, const 
         if (node_visits) node_visits[i] = uint32_t(g_kd8_nodes - n0);
     }
 }
+
+// ---- developer statistics: node visits of a W-wide hierarchy (W = 2..16) collapsed from the two-wide nodes the same way --------
+// (scripts/bvh_ray_lengths_cpu.py; a plain recursive-list traversal with the two-wide traversal's box test, root test and leaf
+// test - it answers "how many dependent node visits would a query need", nothing more)
+namespace {
+struct WideNode { int n; rtb::Bvh4Child c[16]; };
+std::vector<WideNode> collapse_wide(const uint32_t* nodes16, uint64_t n_nodes2, int width) {
+    constexpr uint32_t NO_CHILD = 0xFFFFFFFFu;
+    std::vector<WideNode> out;
+    if (!n_nodes2) return out;
+    struct Todo { uint32_t node2; int parent, slot; };
+    std::vector<Todo> todo{{0u, -1, -1}};
+    while (!todo.empty()) {
+        const Todo t = todo.back(); todo.pop_back();
+        const int me = int(out.size());
+        if (t.parent >= 0) out[size_t(t.parent)].c[t.slot].ref = uint32_t(me);
+        WideNode w; w.n = 2;
+        rtb::bvh2_children(nodes16, t.node2, w.c);
+        for (int k = 0; k < w.n;) { if (w.c[k].cnt == NO_CHILD) { w.c[k] = w.c[w.n - 1]; --w.n; } else ++k; }
+        while (w.n < width) {
+            int best = -1;
+            for (int k = 0; k < w.n; ++k) if (w.c[k].cnt == 0 && (best < 0 || rtb::bvh4_area(w.c[k]) > rtb::bvh4_area(w.c[best]))) best = k;
+            if (best < 0) break;
+            rtb::Bvh4Child g[2]; rtb::bvh2_children(nodes16, w.c[best].ref, g);
+            int m = 0; rtb::Bvh4Child keep[2];
+            for (int k = 0; k < 2; ++k) if (g[k].cnt != NO_CHILD) keep[m++] = g[k];
+            if (m == 0) { w.c[best] = w.c[w.n - 1]; --w.n; continue; }
+            w.c[best] = keep[0];
+            if (m == 2) w.c[w.n++] = keep[1];
+        }
+        out.push_back(w);
+        for (int k = w.n - 1; k >= 0; --k) if (w.c[k].cnt == 0) todo.push_back({w.c[k].ref, me, k});
+    }
+    return out;
+}
+}  // namespace
+extern "C" void bvh_wide_visit_counts(const float* nodes16, uint64_t n_nodes2, int width, const float* tris, const float* root6, const float* rays6,
+                                      uint64_t n, int cull, float eps, const float* t_far, int any_hit, uint32_t* node_visits) {
+    const std::vector<WideNode> nodes = collapse_wide(reinterpret_cast<const uint32_t*>(nodes16), n_nodes2, width < 2 ? 2 : (width > 16 ? 16 : width));
+    struct Entry { uint32_t ref, cnt; float t0; };
+    std::vector<Entry> stack;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* q = rays6 + 6 * i;
+        rtb::BvhState s;
+        node_visits[i] = 0;
+        if (!rtb::bvh_init(s, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], t_far ? t_far[i] : FLT_MAX, any_hit != 0) || s.phase == rtb::KD8_DONE) continue;
+        stack.clear();
+        stack.push_back({0u, 0u, 0.0f});
+        const float ix = rtb::kd_rcp_estimate(s.dx), iy = rtb::kd_rcp_estimate(s.dy), iz = rtb::kd_rcp_estimate(s.dz);
+        const float cx = -(s.ox * ix), cy = -(s.oy * iy), cz = -(s.oz * iz);
+        while (!stack.empty()) {
+            const Entry e = stack.back(); stack.pop_back();
+            const float lim = rtb::kd_min(s.best.t, s.t_far);
+            if (e.t0 > lim) continue;
+            if (e.cnt) {
+                if (cull) rtb::kd_test_leaf<true, false>(tris + size_t(e.ref) * rtb::KD8_TRI_FLOATS, e.cnt, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
+                else rtb::kd_test_leaf<false, false>(tris + size_t(e.ref) * rtb::KD8_TRI_FLOATS, e.cnt, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, eps, s.best);
+                if (s.any_hit && s.best.t <= s.t_far) break;
+                continue;
+            }
+            ++node_visits[i];
+            const WideNode& w = nodes[e.ref];
+            Entry hit[16]; int m = 0;
+            for (int k = 0; k < w.n; ++k) {
+                float t_in, t_out;
+                rtb::bvh_slab(ix, iy, iz, cx, cy, cz, w.c[k].lo[0], w.c[k].lo[1], w.c[k].lo[2], w.c[k].hi[0], w.c[k].hi[1], w.c[k].hi[2], t_in, t_out);
+                if (!((t_in <= t_out) & (t_in <= lim))) continue;
+                int j = m++;
+                while (j > 0 && hit[j - 1].t0 < t_in) { hit[j] = hit[j - 1]; --j; }       // descending: the nearest is pushed last
+                hit[j] = Entry{w.c[k].ref, w.c[k].cnt, t_in};
+            }
+            for (int j = 0; j < m; ++j) stack.push_back(hit[j]);
+        }
+    }
+}
