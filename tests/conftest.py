@@ -39,6 +39,17 @@ def psnr8(a: np.ndarray, b: np.ndarray) -> float:
     return 99.0 if mse == 0 else 10.0 * np.log10(255.0 * 255.0 / mse)
 
 
+def check_textures_png(got8: np.ndarray, published8: np.ndarray) -> None:
+    """an 8-bit config-4 frame (hw12/scene4, spp 1) against the decoded outputs/textures.png: the albedo, edges and checker
+    quadrants exactly; the bitmap quadrant (bottom right) to +-2/255 on <= 0.1 % of the frame (JPEG decoder)"""
+    assert got8.shape == published8.shape == (1080, 1920, 3)
+    diff = np.abs(got8.astype(np.int32) - published8.astype(np.int32)).max(axis=2)
+    exact = np.ones(diff.shape, bool)
+    exact[540:, 960:] = False
+    assert int(diff[exact].max()) == 0, "albedo / edges / checker quadrants differ from outputs/textures.png"
+    assert int(diff.max()) <= 2 and int((diff > 0).sum()) <= diff.size // 1000
+
+
 @pytest.fixture(scope="session")
 def golden() -> dict:
     with open(os.path.join(HERE, "golden", "golden.json")) as fh:
