@@ -200,13 +200,13 @@ def data_desc(w: dict) -> str:
     return "synthetic camera rays over the reference's own scene file (fixture copy)"
 
 
-def workload_config(w: dict, args, world: int) -> dict:
+def workload_config(w: dict, args, world: int, accel: str | None = None) -> dict:
     kd = w.get("kd", [8, 64])
     src = (f"{w['scene']} (tests/helpers/crtscene.synthetic_scene)" if w.get("synthetic") else
            f"scenes/{w['scene'].replace('_', '/', 1)}.crtscene")
     return {"workload": f"{w['key']}: {src} {w['width']}x{w['height']}, "
                         f"spp {w['spp']} per GPU, max_ray_depth {w['max_ray_depth']}, gi_rays {w['gi_rays']}, kd<{kd[0]},{kd[1]}>",
-            "rays_per_frame_per_gpu": w.get("rays"), "mode": args.mode, "sharding": "replicated scene, 1 sample slice per GPU" if world > 1 else "none",
+            "rays_per_frame_per_gpu": w.get("rays"), "mode": args.mode, "accel": accel, "sharding": "replicated scene, 1 sample slice per GPU" if world > 1 else "none",
             "l2": "flushed between timed frames (256 MiB write, outside the CUDA events)"}
 
 
@@ -537,6 +537,9 @@ def main() -> None:
         # dominant kernel = the trace kernel class with the largest share of the frame; algorithmic bytes = the REFERENCE
         # algorithm's node + triangle fetches for that ray kind (tests/golden/workloads.json)
         accel = args.mode.endswith("ordered")
+        # the structure the timed trace kernels walk: the reference's own kd<depth,leaf> tree in reference order (exact / fast), or
+        # the backend's bounding-volume hierarchy, two- or four-wide (ordered modes; rt_build_opts.accel_width)
+        accel_name = f"bvh{int(scene.info.accel_width)}" if accel else f"reference kd<{kd[0]},{kd[1]}>"
         dom_kernel = ({"primary": "k_stream_primary", "secondary": "k_stream_level", "shadow": "k_stream_shadow"} if accel else
                       {"primary": "k_primary", "secondary": "k_trace_level", "shadow": "k_shadow"})[dom]
         n_dom_launch = {"primary": 1, "secondary": max(1, w["max_ray_depth"]), "shadow": 1}[dom]
@@ -554,7 +557,7 @@ def main() -> None:
             "metric": "Mrays/s", "value": rays_all * K / (ms_dev * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": data_desc(w),
-            "config": workload_config(w, args, world),
+            "config": workload_config(w, args, world, accel_name),
             "rays": {"primary_per_frame": int(c0.primary), "shadow_per_frame": int(c0.shadow), "secondary_per_frame": int(c0.secondary),
                      "primary_mrays_s": c0.primary / cls["primary"] / 1e3 if cls["primary"] else None,
                      "shadow_mrays_s": c0.shadow / cls["shadow"] / 1e3 if cls["shadow"] else None,

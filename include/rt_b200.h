@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RT_API __attribute__((visibility("default")))
@@ -93,7 +93,12 @@ typedef struct rt_build_opts {
      * 0 = automatic: depth min(30, 8 + 1.3 log2(n_triangles)); the heuristic decides where leaves end (leaf size is a floor) */
     uint32_t accel_max_depth;
     uint32_t accel_max_leaf_size;
+    /* width of the bounding-volume hierarchy the accelerated mode walks: 2 = 64-byte two-child nodes (csrc/rt_bvh.cuh), 4 = their
+     * four-wide collapse, 128-byte nodes (csrc/rt_bvh4.cuh; the reference author's own TODO, README.md:118-124); 0 = the default
+     * (RT_DEFAULT_ACCEL_WIDTH).  Frames, hits and ray counts do not depend on it. */
+    uint32_t accel_width;
 } rt_build_opts;
+#define RT_DEFAULT_ACCEL_WIDTH 4
 #define RT_DEVICE_HOST_ONLY (-1)
 
 /* config.hpp:6-17 as run-time parameters, plus the tile / sample slice used for multi-GPU sharding. */
@@ -133,6 +138,8 @@ typedef struct rt_scene_info {
     uint32_t accel_max_depth, accel_max_leaf_size;       /* parameters the accelerated tree was built with */
     uint64_t accel_n_nodes, accel_n_leaf_refs, accel_n_leaves, accel_tree_depth;
     uint64_t bvh_n_nodes, bvh_n_refs, bvh_n_leaves, bvh_depth;   /* the bounding-volume hierarchy (64-byte two-child nodes) */
+    uint32_t accel_width, reserved0;                             /* 2 or 4: what the accelerated mode walks */
+    uint64_t bvh4_n_nodes, bvh4_stack_need;                      /* four-wide collapse: nodes, worst-case traversal stack entries */
 } rt_scene_info;
 
 typedef struct rt_counters {         /* of the last rt_render_frame* call */

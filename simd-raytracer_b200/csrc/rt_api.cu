@@ -25,6 +25,7 @@
 #include "../../include/rt_b200.h"
 #include "../host/kd_build.hpp"
 #include "../host/scene.hpp"
+#include "../host/bvh4_collapse.hpp"
 #include "rt_stream.cuh"
 #include "rt_peer.cuh"
 
@@ -104,6 +105,8 @@ struct rt_scene {
     KdTree accel_tree;               // the backend's own deeper tree (RT_FLAG_ORDERED)
     AccelLayout accel_layout;
     BvhLayout bvh_layout;            // the bounding-volume hierarchy (RT_FLAG_ORDERED, csrc/rt_bvh.cuh)
+    std::vector<uint32_t> bvh4_nodes; // its four-wide collapse (csrc/rt_bvh4.cuh, host/bvh4_collapse.hpp); empty when accel_width == 2
+    bool wide = false;               // the accelerated mode walks the four-wide nodes
     rt_build_opts accel_opts{};
     bool accel_built = false;
     rt_scene_info info{};
@@ -160,7 +163,7 @@ struct rt_scene {
 
     std::mutex mtx;
     int g_primary[4] = {0, 0, 0, 0}, g_trace[4] = {0, 0, 0, 0}, g_shadow[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g_shade[2] = {0, 0}, g_resolve = 0;
-    int gs_primary[2] = {0, 0}, gs_sparse[2] = {0, 0}, gs_level[2] = {0, 0}, gs_shadow[4] = {0, 0, 0, 0};   // stream kernels (accelerated mode)
+    int gs_primary[2] = {0, 0}, gs_sparse[2] = {0, 0}, gs_level[2] = {0, 0}, gs_shadow[4] = {0, 0, 0, 0};   // stream kernels (accelerated mode, the scene's width)
 
     ~rt_scene() {
         if (device >= 0) {
@@ -229,7 +232,9 @@ void upload_scene(rt_scene* s) {
     d.a_nodes8 = nullptr; d.a_tris = nullptr;
     d.b_nodes = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.nodes.data(), s->bvh_layout.nodes.size() / 4, bytes)));
     d.b_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.tris.data(), s->bvh_layout.tris.size() / 4, bytes)));
+    d.w_nodes = s->wide ? reinterpret_cast<const float*>(keep(upload<float4>(s->bvh4_nodes.data(), s->bvh4_nodes.size() / 4, bytes))) : nullptr;
 #else
+    d.w_nodes = nullptr;
     d.b_nodes = nullptr; d.b_tris = nullptr;
     d.a_nodes8 = keep(upload<uint32_t>(s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size(), bytes));
     d.a_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->accel_layout.tris.data(), s->accel_layout.tris.size() / 4, bytes)));
@@ -319,6 +324,20 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         s->bvh_layout = flatten_bvh(s->geom, bvh);
         s->info.bvh_n_nodes = s->bvh_layout.n_nodes; s->info.bvh_n_refs = s->bvh_layout.n_refs;
         s->info.bvh_n_leaves = bvh.n_leaves; s->info.bvh_depth = bvh.depth;
+        // the four-wide form of the same hierarchy (rt_build_opts.accel_width; RT_B200_ACCEL_WIDTH overrides the default for sweeps)
+        uint32_t width = o.accel_width;
+        if (!width) { width = RT_DEFAULT_ACCEL_WIDTH; if (const char* e = std::getenv("RT_B200_ACCEL_WIDTH")) std::sscanf(e, "%u", &width); }
+        if (width != 2 && width != 4) throw rt_error(RT_ERR_BAD_ARG, "accel_width must be 0 (default), 2 or 4");
+        if (width == 4 && leaf > BVH4_MAX_LEAF) throw rt_error(RT_ERR_BAD_ARG, "accel_width 4 holds at most 7 triangles per leaf");
+        s->wide = width == 4;
+        s->info.accel_width = width;
+        if (s->wide) {
+            try { s->bvh4_nodes = bvh4_collapse(s->bvh_layout.nodes.data(), s->bvh_layout.n_nodes); }
+            catch (const std::length_error& e) { throw rt_error(RT_ERR_UNSUPPORTED, e.what()); }
+            s->info.bvh4_n_nodes = s->bvh4_nodes.size() / 32;
+            s->info.bvh4_stack_need = bvh4_stack_need(s->bvh4_nodes);
+            if (s->info.bvh4_stack_need > uint64_t(BVH4_STACK)) throw rt_error(RT_ERR_UNSUPPORTED, "four-wide hierarchy needs a deeper traversal stack than BVH4_STACK");
+        }
         if (std::getenv("RT_B200_VERBOSE")) std::fprintf(stderr, "[rt_b200] bvh build + flatten %.3f s\n", now_s() - t3);
     }
     s->info.flatten_seconds = now_s() - t0;
@@ -467,12 +486,15 @@ void ensure_grids(rt_scene* s, Mode m, bool has_gi) {
     if (!s->g_resolve) s->g_resolve = grid_for(s, k_resolve<false>);
     if (!s->g_shade[has_gi]) s->g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
     if (m.ordered) {
-        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? grid_for(s, k_stream_primary<true>, STREAM_THREADS) : grid_for(s, k_stream_primary<false>, STREAM_THREADS);
-        if (!s->gs_sparse[fi]) s->gs_sparse[fi] = m.fast ? grid_for(s, k_stream_primary_sparse<true>, STREAM_THREADS) : grid_for(s, k_stream_primary_sparse<false>, STREAM_THREADS);
-        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? grid_for(s, k_stream_level<true>, STREAM_THREADS) : grid_for(s, k_stream_level<false>, STREAM_THREADS);
+        // the stream kernels exist per hierarchy width; a scene only ever launches those of its own
+#define STREAM_GRID(K2, K4) (s->wide ? grid_for(s, K4, STREAM_THREADS) : grid_for(s, K2, STREAM_THREADS))
+        if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? STREAM_GRID((k_stream_primary<true, 2>), (k_stream_primary<true, 4>)) : STREAM_GRID((k_stream_primary<false, 2>), (k_stream_primary<false, 4>));
+        if (!s->gs_sparse[fi]) s->gs_sparse[fi] = m.fast ? STREAM_GRID((k_stream_primary_sparse<true, 2>), (k_stream_primary_sparse<true, 4>)) : STREAM_GRID((k_stream_primary_sparse<false, 2>), (k_stream_primary_sparse<false, 4>));
+        if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? STREAM_GRID((k_stream_level<true, 2>), (k_stream_level<true, 4>)) : STREAM_GRID((k_stream_level<false, 2>), (k_stream_level<false, 4>));
         if (!s->gs_shadow[fi * 2 + tr])
-            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? grid_for(s, k_stream_shadow<true, true>, STREAM_THREADS) : grid_for(s, k_stream_shadow<true, false>, STREAM_THREADS))
-                                           : (m.fast ? grid_for(s, k_stream_shadow<false, true>, STREAM_THREADS) : grid_for(s, k_stream_shadow<false, false>, STREAM_THREADS));
+            s->gs_shadow[fi * 2 + tr] = tr ? (m.fast ? STREAM_GRID((k_stream_shadow<true, true, 2>), (k_stream_shadow<true, true, 4>)) : STREAM_GRID((k_stream_shadow<true, false, 2>), (k_stream_shadow<true, false, 4>)))
+                                           : (m.fast ? STREAM_GRID((k_stream_shadow<false, true, 2>), (k_stream_shadow<false, true, 4>)) : STREAM_GRID((k_stream_shadow<false, false, 2>), (k_stream_shadow<false, false, 4>)));
+#undef STREAM_GRID
     } else {
         if (!s->g_primary[mi]) s->g_primary[mi] = m.fast ? grid_for(s, k_primary<true, false>) : grid_for(s, k_primary<false, false>);
         if (!s->g_trace[mi]) s->g_trace[mi] = m.fast ? grid_for(s, k_trace_level<true, false>) : grid_for(s, k_trace_level<false, false>);
@@ -513,6 +535,22 @@ void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStrea
     CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
+// a stream kernel of the scene's hierarchy width, exact or fast arithmetic
+#define STREAM_LAUNCH(K, GRID, ...)                                                                       \
+    do {                                                                                                  \
+        if (s->wide) { if (m.fast) launch_k(K<true, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__);           \
+                       else launch_k(K<false, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__); }               \
+        else { if (m.fast) launch_k(K<true, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__);                   \
+               else launch_k(K<false, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__); }                       \
+    } while (0)
+#define STREAM_LAUNCH_T(K, T, GRID, ...)                                                                  \
+    do {                                                                                                  \
+        if (s->wide) { if (m.fast) launch_k(K<T, true, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__);        \
+                       else launch_k(K<T, false, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__); }            \
+        else { if (m.fast) launch_k(K<T, true, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__);                \
+               else launch_k(K<T, false, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__); }                    \
+    } while (0)
+
 template <class Launch>
 void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_flags, cudaStream_t st, Launch&& launch) {
     FrameParams fp = P.fp;
@@ -541,11 +579,9 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     launch(TC_PRIMARY, [&] {
         if (fp.sparse0) {
             const uint32_t* tiles = cull_tiles ? s->tiles0.p : nullptr;
-            if (m.fast) launch_k(k_stream_primary_sparse<true>, s->gs_sparse[1], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
-            else launch_k(k_stream_primary_sparse<false>, s->gs_sparse[0], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
+            STREAM_LAUNCH(k_stream_primary_sparse, s->gs_sparse[fi], s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
         } else if (m.ordered) {
-            if (m.fast) launch_k(k_stream_primary<true>, s->gs_primary[1], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-            else launch_k(k_stream_primary<false>, s->gs_primary[0], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            STREAM_LAUNCH(k_stream_primary, s->gs_primary[fi], s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
         } else if (m.fast) launch_k(k_primary<true, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
         else launch_k(k_primary<false, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
     });
@@ -554,8 +590,7 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         if (lvl > 0) {
             launch(TC_SECONDARY, [&] {
                 if (m.ordered) {
-                    if (m.fast) launch_k(k_stream_level<true>, s->gs_level[1], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                    else launch_k(k_stream_level<false>, s->gs_level[0], STREAM_THREADS, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    STREAM_LAUNCH(k_stream_level, s->gs_level[fi], s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
                 } else if (m.fast) launch_k(k_trace_level<true, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
                 else launch_k(k_trace_level<false, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
             });
@@ -571,10 +606,8 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         launch(TC_SHADOW, [&] {
             if (m.ordered) {
                 const int g = s->gs_shadow[fi * 2 + tr];
-                if (tr) { if (m.fast) launch_k(k_stream_shadow<true, true>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot);
-                          else launch_k(k_stream_shadow<true, false>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot); }
-                else { if (m.fast) launch_k(k_stream_shadow<false, true>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot);
-                       else launch_k(k_stream_shadow<false, false>, g, STREAM_THREADS, st, s->d, fp, s->jobs.p, s->ps, slot); }
+                if (tr) { STREAM_LAUNCH_T(k_stream_shadow, true, g, s->d, fp, s->jobs.p, s->ps, slot); }
+                else { STREAM_LAUNCH_T(k_stream_shadow, false, g, s->d, fp, s->jobs.p, s->ps, slot); }
             } else {
                 const int g = s->g_shadow[mi * 2 + tr];
                 if (tr) { if (m.fast) launch_k(k_shadow<true, true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
@@ -866,7 +899,7 @@ const char* rt_last_error(void) { return g_last_error.c_str(); }
 
 void rt_default_build_opts(rt_build_opts* o) {
     if (!o) return;
-    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_max_depth = 0; o->accel_max_leaf_size = 0;
+    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_max_depth = 0; o->accel_max_leaf_size = 0; o->accel_width = 0;
 }
 
 void rt_default_params(rt_params* p) {

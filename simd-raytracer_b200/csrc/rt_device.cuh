@@ -13,7 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "rt_bvh.cuh"
+#include "rt_bvh4.cuh"
 
 namespace rtb {
 
@@ -38,6 +38,7 @@ struct DScene {
     const float* __restrict__ a_tris;       //                   and its 48-byte leaf triangle records
     const float* __restrict__ b_nodes;      // accelerated mode, BVH variant (default): 64-byte two-child nodes (rt_bvh.cuh)
     const float* __restrict__ b_tris;       //                   and its 48-byte triangle records (one per triangle)
+    const float* __restrict__ w_nodes;      // accelerated mode, four-wide variant (rt_bvh4.cuh): 128-byte nodes over the same records; null = two-wide
     const float4* __restrict__ nodes32;     // 2 x float4 per node: box + the same two words (reference-order traversal)
     const float4* __restrict__ packets;     // 10 x float4 per 4-triangle SoA packet
     const uint4* __restrict__ tri_index;    // vi0, vi1, vi2, material
@@ -97,9 +98,12 @@ template <bool CULL, bool FAST>
 __device__ __forceinline__ void accel_leaf_step(AccelState& st, const AccelStackEntry* stack, const DScene& sc, float eps) {
     bvh_leaf_step<CULL, FAST>(st, stack, sc.b_tris, eps);
 }
+// the one-ray-per-thread query of the batch entry points (rt_trace_closest / rt_trace_occluded / rt_trace_primary) walks the
+// hierarchy the scene was built with; the stream kernels of the frame path pick theirs at compile time (rt_stream.cuh)
 template <bool CULL, bool FAST>
 __device__ __forceinline__ KdHit accel_trace(const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
                                              float t_far, bool any_hit) {
+    if (sc.w_nodes) return bvh4_trace<CULL, FAST>(sc.w_nodes, sc.b_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
     return bvh_trace<CULL, FAST>(sc.b_nodes, sc.b_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
 }
 #else

@@ -33,6 +33,10 @@ namespace rtb {
 #ifndef RT_STREAM_MIN_BLOCKS
 #define RT_STREAM_MIN_BLOCKS 3
 #endif
+#ifndef RT_STREAM_SSTACK
+#define RT_STREAM_SSTACK 12
+#endif
+constexpr int STREAM_SSTACK = RT_STREAM_SSTACK;              // four-wide traversal: stack entries per lane that live in shared memory
 constexpr int STREAM_THREADS = RT_STREAM_THREADS;            // threads per block of the stream kernels (registers per thread follow from it)
 constexpr int STREAM_BURST = RT_STREAM_BURST;                // rounds (node steps + one leaf phase) between completion phases
 constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
@@ -63,16 +67,52 @@ __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox
     if (active) *out = e;
 }
 
+// ---- the traversal stack of a lane, by hierarchy width -------------------------------------------------------------------------
+// Two-wide (rt_bvh.cuh): 16-byte entries in thread-local memory, as in round 1.
+// Four-wide (rt_bvh4.cuh): 8-byte entries; the first STREAM_SSTACK of a lane live in shared memory (one column per thread:
+// consecutive lanes are consecutive 8-byte words, so a warp's access is two conflict-free wavefronts whatever the lanes'
+// depths), deeper ones - rare - in a thread-local tail.  No stack traffic reaches L1, which the node fetches need.
+template <int WIDE> struct StreamStack;
+template <> struct StreamStack<2> {
+    AccelStackEntry e[ACCEL_STACK];
+    __device__ __forceinline__ void bind(uint2*) {}
+};
+template <> struct StreamStack<4> {
+    uint2* col;                                  // this thread's column of the block's shared stack
+    uint2 tail[BVH4_STACK - STREAM_SSTACK];
+    __device__ __forceinline__ void bind(uint2* shared_rows) { col = shared_rows + threadIdx.x; }
+    __device__ __forceinline__ void put(int pos, float t0, uint32_t child) {
+        const uint2 v = make_uint2(__float_as_uint(t0), child);
+        if (pos < STREAM_SSTACK) col[pos * STREAM_THREADS] = v; else tail[pos - STREAM_SSTACK] = v;
+    }
+    __device__ __forceinline__ void get(int pos, float& t0, uint32_t& child) const {
+        const uint2 v = pos < STREAM_SSTACK ? col[pos * STREAM_THREADS] : tail[pos - STREAM_SSTACK];
+        t0 = __uint_as_float(v.x); child = v.y;
+    }
+};
+template <int WIDE>
+__device__ __forceinline__ void stream_node_step(AccelState& st, StreamStack<WIDE>& stack, const DScene& sc) {
+    if constexpr (WIDE == 4) bvh4_node_step(st, stack, sc.w_nodes);
+    else accel_node_step(st, stack.e, sc);
+}
+template <bool CULL, bool FAST, int WIDE>
+__device__ __forceinline__ void stream_leaf_step(AccelState& st, StreamStack<WIDE>& stack, const DScene& sc, float eps) {
+    if constexpr (WIDE == 4) bvh4_leaf_step<CULL, FAST>(st, stack, sc.b_tris, eps);
+    else accel_leaf_step<CULL, FAST>(st, stack.e, sc, eps);
+}
+
 // Policy concept:
 //   bool load(const DScene&, uint32_t& idx, V3& o, V3& d, float& t_far, bool& any_hit)  false: entry needs no query; may remap idx
 //   void entered(uint32_t idx, V3 o, V3 d)                                                  the query touches the scene box and will be traced
 //   bool finish(const DScene&, uint32_t idx, const Hit& h, AccelState& st)                  true: lane re-armed (st re-initialised)
-template <bool CULL, bool FAST, class Policy>
+template <bool CULL, bool FAST, int WIDE, class Policy>
 __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     AccelState st;
-    AccelStackEntry stack[ACCEL_STACK];
+    __shared__ uint2 shared_stack[WIDE == 4 ? STREAM_SSTACK * STREAM_THREADS : 1];
+    StreamStack<WIDE> stack;
+    stack.bind(shared_stack);
     st.sp = 0; st.phase = KD8_DONE; st.any_hit = false; st.best.tri = -1; st.best.t = FLT_MAX; st.best.tie_t = -1.0f; st.t_far = FLT_MAX;
     st.ox = st.oy = st.oz = st.dx = st.dy = st.dz = 0.0f;
     bool busy = false, exhausted = false;
@@ -132,7 +172,7 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
                     stats[4] += __popc(__ballot_sync(FULL, !busy));
                 }
 #endif
-                if (busy && st.phase == KD8_WALK) accel_node_step(st, stack, sc);
+                if (busy && st.phase == KD8_WALK) stream_node_step<WIDE>(st, stack, sc);
             }
             const uint32_t parked = __ballot_sync(FULL, busy && st.phase == KD8_LEAF);
             const uint32_t walking = __ballot_sync(FULL, busy && st.phase == KD8_WALK);
@@ -140,7 +180,7 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
             // tail of a launch a warp holds a handful of queries, and a parked one must not wait for eight
             if (parked && (__popc(parked) >= STREAM_LEAF_MIN || __popc(parked) * STREAM_LEAF_FRAC >= __popc(walking))) {
                 STREAM_STAT(5, 1); STREAM_STAT(6, __popc(parked));
-                if (busy && st.phase == KD8_LEAF) accel_leaf_step<CULL, FAST>(st, stack, sc, eps);
+                if (busy && st.phase == KD8_LEAF) stream_leaf_step<CULL, FAST, WIDE>(st, stack, sc, eps);
             }
             const int running = __popc(__ballot_sync(FULL, busy && st.phase != KD8_DONE));
             if (running == 0 || (!exhausted && running < STREAM_REFILL_BELOW)) break;
@@ -204,12 +244,12 @@ struct PrimaryPolicy {
     }
 };
 
-template <bool FAST>
+template <bool FAST, int WIDE>
 __global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                         PassState* __restrict__ ps, int work_slot) {
     pdl_wait();
     PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
-    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
+    stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 
@@ -317,7 +357,7 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, n_culled, 0u);
 }
 
-template <bool FAST>
+template <bool FAST, int WIDE>
 __global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                                uint32_t* __restrict__ mask0, float* __restrict__ fb, int divide,
                                                                PassState* __restrict__ ps, int work_slot, const uint32_t* __restrict__ tile_list) {
@@ -325,7 +365,7 @@ __global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_str
     SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb; p.tile_list = tile_list;
     p.per_sample = tile_list ? ps->n_tiles0 * 32u : fp.plane;
     p.miss_rgb = first_pass_miss_colour(sc, fp, divide);
-    stream_loop<true, FAST>(sc, p, &ps->work[work_slot], p.per_sample * fp.n_samples, fp.eps);             // render.hpp:64, culling ON
+    stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], p.per_sample * fp.n_samples, fp.eps);             // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 
@@ -348,7 +388,7 @@ struct LevelPolicy {
     }
 };
 
-template <bool FAST>
+template <bool FAST, int WIDE>
 __global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                       PassState* __restrict__ ps, int level, int work_slot) {
     pdl_wait();
@@ -356,7 +396,7 @@ __global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_str
     const uint32_t end = min(ps->pool_count, fp.pool_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) ps->lv[level + 1] = end;
     LevelPolicy p; p.rays = rays; p.hits = hits; p.begin = begin;
-    stream_loop<false, FAST>(sc, p, &ps->work[work_slot], end - begin, fp.eps);
+    stream_loop<false, FAST, WIDE>(sc, p, &ps->work[work_slot], end - begin, fp.eps);
     warp_sum_to(&ps->pc.secondary, &ps->pc.secondary_hits, p.n_rays, p.n_hits);
 }
 
@@ -408,14 +448,14 @@ struct ShadowPolicy {
     }
 };
 
-template <bool TRANSMISSIVE, bool FAST>
+template <bool TRANSMISSIVE, bool FAST, int WIDE>
 __global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                        int work_slot) {
     pdl_wait();
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
     ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.shadow_bias = fp.shadow_bias;
     p.n_lights = sc.n_lights; p.n_jobs = end;
-    stream_loop<false, FAST>(sc, p, &ps->work[work_slot], end, fp.eps);
+    stream_loop<false, FAST, WIDE>(sc, p, &ps->work[work_slot], end, fp.eps);
     warp_sum_to(&ps->pc.shadow, &ps->pc.shadow_hits, p.n_q, p.n_h);
 }
 

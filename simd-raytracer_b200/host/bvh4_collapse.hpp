@@ -4,8 +4,10 @@
 // builder's padding), leaves keep pointing into the same triangle records, nodes are emitted in DFS pre-order.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 
 namespace rtb {
@@ -25,9 +27,10 @@ inline float bvh4_area(const Bvh4Child& c) {
     return x * y + y * z + z * x;
 }
 
-// nodes16: the two-wide nodes (16 words each), node 0 the root; returns the four-wide nodes (32 words each), node 0 the root
+// nodes16: the two-wide nodes (16 words each), node 0 the root; returns the four-wide nodes (32 words each), node 0 the root.
+// Throws std::length_error when a leaf or an index does not fit the packed child word (ref << 3 | cnt).
 inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_nodes2) {
-    constexpr uint32_t NO_CHILD = 0xFFFFFFFFu;
+    constexpr uint32_t NO_CHILD = 0xFFFFFFFFu, MAX_LEAF = 7u, MAX_REF = 0x1FFFFFFDu;       // csrc/rt_bvh4.cuh
     std::vector<uint32_t> out;
     if (!n_nodes2) return out;
     struct Todo { uint32_t node2, slot; };            // two-wide subtree root -> where its four-wide node index has to be written
@@ -36,7 +39,8 @@ inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_n
         const Todo t = todo.back();
         todo.pop_back();
         const uint32_t me = uint32_t(out.size() / 32);
-        if (t.slot != NO_CHILD) out[t.slot] = me;
+        if (me > MAX_REF) throw std::length_error("bvh4: more than 2^29 nodes");
+        if (t.slot != NO_CHILD) out[t.slot] = me << 3;
         Bvh4Child c[4];
         int n = 2;
         bvh2_children(nodes16, t.node2, c);
@@ -59,24 +63,44 @@ inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_n
         const size_t base = out.size();
         out.resize(base + 32, 0u);
         float f[24];
-        uint32_t ref[4], cnt[4];
+        uint32_t child[4];
         for (int k = 0; k < 4; ++k) {
             const bool have = k < n;
             for (int a = 0; a < 3; ++a) {
                 f[a * 4 + k] = have ? c[k].lo[a] : 0.0f;
                 f[12 + a * 4 + k] = have ? c[k].hi[a] : 0.0f;
             }
-            ref[k] = have ? c[k].ref : 0u;
-            cnt[k] = have ? c[k].cnt : NO_CHILD;
+            if (have && (c[k].cnt > MAX_LEAF || c[k].ref > MAX_REF)) throw std::length_error("bvh4: leaf larger than 7 triangles or index beyond 2^29");
+            child[k] = have ? ((c[k].ref << 3) | c[k].cnt) : NO_CHILD;          // an inner child's index is patched in when it is emitted
         }
         std::memcpy(out.data() + base, f, sizeof f);
-        std::memcpy(out.data() + base + 24, ref, sizeof ref);
-        std::memcpy(out.data() + base + 28, cnt, sizeof cnt);
-        // inner children: their four-wide index is patched in when they are emitted; pushed in reverse so that child 0 comes next
+        std::memcpy(out.data() + base + 24, child, sizeof child);
+        // inner children: pushed in reverse so that child 0 comes next
         for (int k = n - 1; k >= 0; --k)
             if (c[k].cnt == 0) todo.push_back({c[k].ref, uint32_t(base + 24 + k)});
     }
     return out;
+}
+
+// Stack entries the traversal of csrc/rt_bvh4.cuh can need on this tree, whatever the ray: a visit of a node with n children
+// leaves n - 1 entries below the child it descends into, and any child may be the one visited first.
+inline uint32_t bvh4_stack_need(const std::vector<uint32_t>& nodes4) {
+    if (nodes4.empty()) return 0;
+    struct Item { uint32_t node, sp; };
+    std::vector<Item> todo{{0u, 0u}};
+    uint32_t need = 0;
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        const uint32_t* child = nodes4.data() + size_t(it.node) * 32 + 24;
+        uint32_t n = 0;
+        for (int k = 0; k < 4; ++k) n += child[k] != 0xFFFFFFFFu;
+        const uint32_t below = it.sp + (n ? n - 1 : 0);
+        need = std::max(need, below);
+        for (int k = 0; k < 4; ++k)
+            if (child[k] != 0xFFFFFFFFu && (child[k] & 7u) == 0u) todo.push_back({child[k] >> 3, below});
+    }
+    return need;
 }
 
 }  // namespace rtb

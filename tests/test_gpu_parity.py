@@ -28,14 +28,18 @@ CONFIGS = [(n, "s1d5g0", 5) for n in SCENES] + [("hw11_scene8", "s1d10g0", 10)]
 _open: dict = {}
 
 
-def gpu_scene(rt, name: str, size=None, kd=(8, 64)):
-    key = (name, size, kd)
+def gpu_scene(rt, name: str, size=None, kd=(8, 64), width=0):
+    """width: rt_build_opts.accel_width - the hierarchy the accelerated mode walks (0 = the default, four-wide; 2 = two-wide)"""
+    key = (name, size, kd, width)
     if key not in _open:
         data = scene_bytes(name)
         if size:
             data = resized(data, *size)
-        _open[key] = (rt.Scene.from_rtsc(data, kd_max_depth=kd[0], kd_max_leaf_size=kd[1]), data)
+        _open[key] = (rt.Scene.from_rtsc(data, kd_max_depth=kd[0], kd_max_leaf_size=kd[1], accel_width=width), data)
     return _open[key]
+
+
+WIDTHS = [4, 2]          # both hierarchies of the accelerated mode (csrc/rt_bvh4.cuh, csrc/rt_bvh.cuh) are held to the same bar
 
 
 def assert_hits_equal(hits, tuv, tri):
@@ -378,13 +382,15 @@ def test_fast_mode_within_north_star_tolerance(rt, oracle_mod, name):
     assert psnr8(img, oi) >= 50.0
 
 
+@pytest.mark.parametrize("width", WIDTHS)
 @pytest.mark.parametrize("name", SCENES)
-def test_accelerated_mode_same_hits(rt, oracle_mod, name):
+def test_accelerated_mode_same_hits(rt, oracle_mod, name, width):
     """RT_FLAG_ORDERED: the backend's own deeper tree, front-to-back (rt_kd8.cuh).  Same arithmetic per triangle, so t/u/v are
     the reference's bits; exact-t ties between different triangles are re-run in reference order -> identical output"""
-    s, data = gpu_scene(rt, name)
+    s, data = gpu_scene(rt, name, width=width)
     o = oracle_mod.Oracle(data)
     assert s.info.bvh_n_refs == s.info.n_triangles and s.info.bvh_n_nodes >= 1
+    assert s.info.accel_width == width and (s.info.bvh4_n_nodes >= 1) == (width == 4)
     hits = s.trace_primary(rt.default_params(flags=rt.FLAG_ORDERED)).reshape(-1)
     assert_hits_equal(hits, *o.trace(o.primary_rays(), True))
     rays = random_rays(200_000, 23)
@@ -394,12 +400,13 @@ def test_accelerated_mode_same_hits(rt, oracle_mod, name):
         assert_hits_equal(s.trace_closest(rays, cull, flags=rt.FLAG_ORDERED), *o.trace(rays, cull))
 
 
+@pytest.mark.parametrize("width", WIDTHS)
 @pytest.mark.parametrize("name,key,depth", CONFIGS)
-def test_accelerated_mode_frames_bit_exact(rt, golden, name, key, depth):
+def test_accelerated_mode_frames_bit_exact(rt, golden, name, key, depth, width):
     """the accelerated mode renders the same float frame, bit for bit, and issues the same queries; only the shadow-hit
     STATISTIC differs (it does not look for hits beyond the light)"""
     g = golden["scenes"][name]["configs"][key]
-    s, _ = gpu_scene(rt, name)
+    s, _ = gpu_scene(rt, name, width=width)
     img = s.render_frame(rt.default_params(max_ray_depth=depth, flags=rt.FLAG_ORDERED))
     assert sha(img) == g["sha256_f32"]
     c = s.counters()
@@ -408,9 +415,10 @@ def test_accelerated_mode_frames_bit_exact(rt, golden, name, key, depth):
     assert c.shadow_hits + c.secondary_hits <= g["counts"]["nocull_hit"]
 
 
-def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod):
+@pytest.mark.parametrize("width", WIDTHS)
+def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod, width):
     data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=60_000, seed=5, width=320, height=200))
-    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64)
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64, accel_width=width)
     o = oracle_mod.Oracle(data, 24, 64)
     assert_hits_equal(s.trace_primary(rt.default_params(flags=rt.FLAG_ORDERED)).reshape(-1), *o.trace(o.primary_rays(), True))
     rays = random_rays(100_000, 3, -1.4, 1.4)
@@ -423,7 +431,7 @@ def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod):
     assert np.array_equal(img.view(np.uint32), oi.view(np.uint32))
     s.close()
     for name in ("hw15_scene2", "hw11_scene8"):                 # refractive pass-through in the shadow loop
-        s, data = gpu_scene(rt, name)
+        s, data = gpu_scene(rt, name, width=width)
         o = oracle_mod.Oracle(data)
         n5, bx, _ = s.tree()
         rays = random_rays(100_000, 31)
@@ -433,13 +441,14 @@ def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod):
         assert np.array_equal(s.trace_occluded(rays, max_t, flags=rt.FLAG_ORDERED), want)
 
 
-def test_config5_shape_synthetic_gi_frame(rt, oracle_mod):
+@pytest.mark.parametrize("width", WIDTHS)
+def test_config5_shape_synthetic_gi_frame(rt, oracle_mod, width):
     """BASELINE.json configs[4] in miniature: a 300 K-triangle random mesh in the diffuse box, kd<24,64>, GI 1, depth 5.
     Size-independent properties at a size the full-resolution job shares: the two query modes render the SAME float frame
     (bit for bit - the GI rays are Philox-keyed, so both modes trace identical rays) with the same query counts; a crop is
     checked against the oracle's Philox render (cos/sin last-bit differences only); 1-spp deterministic part is bit-exact."""
     data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=300_000, seed=1234, width=480, height=270))
-    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64)
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64, accel_width=width)
     o = oracle_mod.Oracle(data, 24, 64)
     kw = dict(samples_per_pixel=1, diffuse_reflection_ray_count=1, max_ray_depth=5)
     a = s.render_frame(rt.default_params(**kw))
