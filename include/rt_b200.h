@@ -218,6 +218,9 @@ RT_API int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8);
  * stay valid until waited for.  Frames complete in ticket order.                                                   */
 RT_API int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t* ticket);
 RT_API int rt_frame_wait(rt_scene* s, uint64_t ticket);
+/* The same sequence with the PPM writer's quantisation (io/image/ppm.hpp:17-19) fused on the device: the frame that crosses PCIe
+ * is height*width*3 BYTES - what write_ppm consumes (src/main.cpp:23) - a quarter of the float frame.                          */
+RT_API int rt_render_frame_rgb8_begin(rt_scene* s, const rt_params* p, uint8_t* rgb8, uint64_t* ticket);
 /* page-locked host memory for the frames of a sequence, for hosts that do not link the CUDA runtime themselves */
 RT_API void* rt_alloc_pinned(uint64_t bytes);           /* null on failure */
 RT_API void rt_free_pinned(void* p);

@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_build_kd_accel", "rt_scene_get_bvh_layout",
     "rt_scene_get_geometry",
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
-    "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_begin", "rt_frame_wait", "rt_alloc_pinned", "rt_free_pinned", "rt_render_frame_device_begin", "rt_render_frame_device", "rt_trace_primary",
+    "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_begin", "rt_render_frame_rgb8_begin", "rt_frame_wait", "rt_alloc_pinned", "rt_free_pinned", "rt_render_frame_device_begin", "rt_render_frame_device", "rt_trace_primary",
     "rt_get_counters",
     "rt_resolve_sum_device",
     "rt_peer_group_create", "rt_peer_group_connect", "rt_peer_group_connect_local", "rt_peer_framebuffer", "rt_peer_result_rgb",
@@ -146,6 +146,7 @@ def _load():
     L.rt_render_frame_rgb8.argtypes = [vp, C.POINTER(Params), vp]
     L.rt_render_frame_device.argtypes = [vp, C.POINTER(Params), vp, vp]
     L.rt_render_frame_begin.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(u64)]
+    L.rt_render_frame_rgb8_begin.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(u64)]
     L.rt_frame_wait.argtypes = [vp, u64]
     L.rt_alloc_pinned.argtypes = [u64]
     L.rt_alloc_pinned.restype = vp
@@ -400,6 +401,13 @@ class Scene:
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.height, self.width, 3)
         t = C.c_uint64(0)
         _check(lib.rt_render_frame_begin(self.h, C.byref(params), out.ctypes.data, C.byref(t)))
+        return int(t.value)
+
+    def render_frame_rgb8_begin(self, params: Params, out: np.ndarray) -> int:
+        """rt_render_frame_rgb8_begin: the frame sequence with the 8-bit frame (io/image/ppm.hpp:17-19 on the device) downloaded"""
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (self.height, self.width, 3)
+        t = C.c_uint64(0)
+        _check(lib.rt_render_frame_rgb8_begin(self.h, C.byref(params), out.ctypes.data, C.byref(t)))
         return int(t.value)
 
     def frame_wait(self, ticket: int) -> bool:

@@ -123,7 +123,8 @@ struct rt_scene {
     DBuf<uint32_t> mask0;            // sparse level 0: one word per 8x4 pixel tile, bit = the camera ray hit something; zero between passes
     PassState* ps = nullptr;
     FrameCounters* fc = nullptr;
-    uint32_t* h_flags = nullptr;     // pinned: pool_count, shadow_count, overflow of the last pass
+    uint32_t* h_flags = nullptr;     // pinned: 4 words per pass of the frame being rendered (k_pass_commit): pool_count, shadow_count, overflow, levels
+    size_t h_flags_passes = 0;
     FrameCounters* h_fc = nullptr;   // pinned
     double pool_factor = 2.0, shadow_factor = 1.0;
     DBuf<float> fb; DBuf<uint8_t> fb8;
@@ -132,8 +133,12 @@ struct rt_scene {
     // pinned completion words and counters; downloads run on their own stream
     struct SeqSlot {
         DBuf<float> fb;
+        DBuf<uint8_t> fb8;               // rt_render_frame_rgb8_begin: the quantised frame the copy engine downloads
+        uint8_t* host_rgb8 = nullptr;
         cudaEvent_t rendered = nullptr, copied = nullptr, a = nullptr, b = nullptr;
-        uint32_t* h_flags = nullptr;     // pinned: what k_pass_commit published for this frame
+        uint32_t* h_flags = nullptr;     // pinned: what k_pass_commit published for every pass of this frame (4 words each)
+        size_t h_flags_passes = 0;
+        uint32_t n_passes = 0, per_pass = 0;
         FrameCounters* h_fc = nullptr;   // pinned
         bool in_flight = false, deferred = false, used = false;
         rt_params params{}, key{};
@@ -175,7 +180,7 @@ struct rt_scene {
                 for (cudaEvent_t e : {q.rendered, q.copied, q.a, q.b}) if (e) cudaEventDestroy(e);
                 if (q.h_flags) cudaFreeHost(q.h_flags);
                 if (q.h_fc) cudaFreeHost(q.h_fc);
-                q.fb.release();
+                q.fb.release(); q.fb8.release();
             }
             rays.release(); hits.release(); recs.release(); jobs.release(); mask0.release(); tiles0.release(); fb.release(); fb8.release();
             q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
@@ -266,6 +271,7 @@ void upload_scene(rt_scene* s) {
     CK(cudaMalloc(&s->ps, sizeof(PassState)));
     CK(cudaMalloc(&s->fc, sizeof(FrameCounters)));
     CK(cudaMallocHost(&s->h_flags, 4 * sizeof(uint32_t)));
+    s->h_flags_passes = 1;
     CK(cudaMallocHost(&s->h_fc, sizeof(FrameCounters)));
     CK(cudaEventCreate(&s->frame_a));
     CK(cudaEventCreate(&s->frame_b));
@@ -376,11 +382,14 @@ struct Mode { bool fast, ordered; };
 Mode mode_of(uint32_t flags) { return Mode{(flags & RT_FLAG_FAST_MATH) != 0, (flags & RT_FLAG_ORDERED) != 0}; }
 
 template <class K>
-int grid_for(rt_scene* s, K kernel, int threads = 256) {
+int grid_for(rt_scene* s, K kernel, int threads = 256, size_t dyn_smem = 0) {
+    if (dyn_smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
     return s->n_sm * std::max(per_sm, 1);
 }
+// the four-wide stream kernels keep every lane's traversal stack in shared memory: worst case of the scene's hierarchy + 1 rows
+size_t wide_stack_bytes(const rt_scene* s) { return s->wide ? (size_t(s->info.bvh4_stack_need) + 1) * StreamCfg<4>::THREADS * sizeof(uint2) : 0; }
 
 #define DISPATCH_MODE(m, CALL)                                      \
     do {                                                            \
@@ -414,25 +423,33 @@ void launch_occluded_batch(rt_scene* s, const float* d_rays, const float* d_maxt
     CK(cudaGetLastError());
 }
 
-__global__ void k_pass_init(PassState* ps, uint32_t n0) {
+// first_of_frame: a new frame starts here; otherwise a pass behind a discarded pass of the same frame is skipped (PassState::carry)
+__global__ void k_pass_init(PassState* ps, uint32_t n0, int first_of_frame) {
     pdl_wait();
+    const uint32_t skip = first_of_frame ? 0u : ps->carry;
+    __syncthreads();
     uint32_t* w = reinterpret_cast<uint32_t*>(ps);
     for (uint32_t i = threadIdx.x; i < sizeof(PassState) / 4; i += blockDim.x) w[i] = 0u;
     __syncthreads();
-    if (threadIdx.x == 0) { ps->pool_count = n0; ps->lv[0] = 0u; ps->lv[1] = n0; }
+    if (threadIdx.x == 0) {
+        ps->skipped = skip; ps->carry = skip;
+        if (!skip) { ps->pool_count = n0; ps->lv[1] = n0; }          // a skipped pass has no entries at any level and no shadow jobs
+    }
 }
 // end of a pass: publish the pool usage to pinned host memory and, if the pass is kept, fold its ray counts
 // `launched` of the `total` levels the frame can reach were traced and shaded (the host skips levels the previous pass of the
 // same frame parameters left empty); if the last launched level spawned children after all, the pass is marked truncated
 // (overflow bit 4) and the host renders it again with every level.  out[3] = levels that held entries.
+// A pass skipped behind a discarded one reports overflow bit 8 and nothing else.
 __global__ void k_pass_commit(PassState* ps, FrameCounters* fc, uint32_t* out, uint32_t launched, uint32_t total) {
     pdl_wait();
+    if (ps->skipped) { out[0] = 0u; out[1] = 0u; out[2] = 8u; out[3] = 0u; return; }
     uint32_t used = 0;
     for (uint32_t d = 0; d < launched; ++d)
         if (ps->lv[d + 1] > ps->lv[d]) used = d + 1;
     if (launched < total && ps->pool_count > ps->lv[launched]) ps->overflow |= 4u;
     out[0] = ps->pool_count; out[1] = ps->shadow_count; out[2] = ps->overflow; out[3] = used;
-    if (ps->overflow) return;
+    if (ps->overflow) { ps->carry = 1u; return; }
     fc->primary += ps->pc.primary; fc->primary_hits += ps->pc.primary_hits;
     fc->shadow += ps->pc.shadow; fc->shadow_hits += ps->pc.shadow_hits;
     fc->secondary += ps->pc.secondary; fc->secondary_hits += ps->pc.secondary_hits;
@@ -477,7 +494,25 @@ uint32_t level_count(const rt_scene* s, const rt_params& p) {
     return spawns ? p.max_ray_depth + 1 : 1;
 }
 
-constexpr uint64_t PRIMARY_BUDGET = 1ull << 23;     // level-0 entries per pass
+// level-0 entries per pass.  A pass costs 80 B per entry and level (ray, hit, record) plus 32 B per shadow job - 2^25 entries are
+// 5-8 GB of the 180 GB - and the more samples a pass holds, the smaller the share of its kernels' tails.
+// RT_B200_PASS_ENTRIES overrides (tests force small passes with it).
+uint64_t primary_budget() {
+    static const uint64_t v = [] {
+        unsigned long long e = 0;
+        if (const char* t = std::getenv("RT_B200_PASS_ENTRIES")) std::sscanf(t, "%llu", &e);
+        return e ? uint64_t(e) : (1ull << 25);
+    }();
+    return v;
+}
+
+void reserve_flags(uint32_t** flags, size_t* have, size_t passes) {
+    if (passes <= *have) return;
+    if (*flags) CK(cudaFreeHost(*flags));
+    *flags = nullptr; *have = 0;
+    CK(cudaMallocHost(flags, passes * 4 * sizeof(uint32_t)));
+    *have = passes;
+}
 
 // persistent grid sizes of the kernels a frame in this mode launches (occupancy queries, once per scene)
 void ensure_grids(rt_scene* s, Mode m, bool has_gi) {
@@ -487,7 +522,7 @@ void ensure_grids(rt_scene* s, Mode m, bool has_gi) {
     if (!s->g_shade[has_gi]) s->g_shade[has_gi] = has_gi ? grid_for(s, k_shade<true>) : grid_for(s, k_shade<false>);
     if (m.ordered) {
         // the stream kernels exist per hierarchy width; a scene only ever launches those of its own
-#define STREAM_GRID(K2, K4) (s->wide ? grid_for(s, K4, STREAM_THREADS) : grid_for(s, K2, STREAM_THREADS))
+#define STREAM_GRID(K2, K4) (s->wide ? grid_for(s, K4, StreamCfg<4>::THREADS, wide_stack_bytes(s)) : grid_for(s, K2, StreamCfg<2>::THREADS))
         if (!s->gs_primary[fi]) s->gs_primary[fi] = m.fast ? STREAM_GRID((k_stream_primary<true, 2>), (k_stream_primary<true, 4>)) : STREAM_GRID((k_stream_primary<false, 2>), (k_stream_primary<false, 4>));
         if (!s->gs_sparse[fi]) s->gs_sparse[fi] = m.fast ? STREAM_GRID((k_stream_primary_sparse<true, 2>), (k_stream_primary_sparse<true, 4>)) : STREAM_GRID((k_stream_primary_sparse<false, 2>), (k_stream_primary_sparse<false, 4>));
         if (!s->gs_level[fi]) s->gs_level[fi] = m.fast ? STREAM_GRID((k_stream_level<true, 2>), (k_stream_level<true, 4>)) : STREAM_GRID((k_stream_level<false, 2>), (k_stream_level<false, 4>));
@@ -511,6 +546,7 @@ struct PassLaunch {
     uint32_t levels, launched;        // levels the frame can reach / levels traced and shaded in this pass
     bool has_gi;
     int first_pass, divide;           // framebuffer: overwrite instead of add / divide by spp_total after adding
+    int first_of_frame;               // first pass queued for this frame (or for its resumption): clears PassState::carry
 };
 
 // Queues the kernels of one pass on `st` (nothing here waits for the device).  launch(class, f) issues f() - the synchronous
@@ -525,30 +561,34 @@ bool pdl_enabled() {
     return on;
 }
 template <class... KArgs, class... Args>
-void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args&&... args) {
+void launch_ks(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t dyn_smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
+template <class... KArgs, class... Args>
+void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args&&... args) {
+    launch_ks(kernel, grid, block, 0, st, std::forward<Args>(args)...);
+}
 
 // a stream kernel of the scene's hierarchy width, exact or fast arithmetic
 #define STREAM_LAUNCH(K, GRID, ...)                                                                       \
     do {                                                                                                  \
-        if (s->wide) { if (m.fast) launch_k(K<true, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__);           \
-                       else launch_k(K<false, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__); }               \
-        else { if (m.fast) launch_k(K<true, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__);                   \
-               else launch_k(K<false, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__); }                       \
+        if (s->wide) { if (m.fast) launch_ks(K<true, 4>, GRID, StreamCfg<4>::THREADS, wide_stack_bytes(s), st, __VA_ARGS__);   \
+                       else launch_ks(K<false, 4>, GRID, StreamCfg<4>::THREADS, wide_stack_bytes(s), st, __VA_ARGS__); }       \
+        else { if (m.fast) launch_k(K<true, 2>, GRID, StreamCfg<2>::THREADS, st, __VA_ARGS__);            \
+               else launch_k(K<false, 2>, GRID, StreamCfg<2>::THREADS, st, __VA_ARGS__); }                \
     } while (0)
 #define STREAM_LAUNCH_T(K, T, GRID, ...)                                                                  \
     do {                                                                                                  \
-        if (s->wide) { if (m.fast) launch_k(K<T, true, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__);        \
-                       else launch_k(K<T, false, 4>, GRID, STREAM_THREADS, st, __VA_ARGS__); }            \
-        else { if (m.fast) launch_k(K<T, true, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__);                \
-               else launch_k(K<T, false, 2>, GRID, STREAM_THREADS, st, __VA_ARGS__); }                    \
+        if (s->wide) { if (m.fast) launch_ks(K<T, true, 4>, GRID, StreamCfg<4>::THREADS, wide_stack_bytes(s), st, __VA_ARGS__);   \
+                       else launch_ks(K<T, false, 4>, GRID, StreamCfg<4>::THREADS, wide_stack_bytes(s), st, __VA_ARGS__); }       \
+        else { if (m.fast) launch_k(K<T, true, 2>, GRID, StreamCfg<2>::THREADS, st, __VA_ARGS__);         \
+               else launch_k(K<T, false, 2>, GRID, StreamCfg<2>::THREADS, st, __VA_ARGS__); }             \
     } while (0)
 
 template <class Launch>
@@ -566,7 +606,7 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     const uint32_t launched = P.launched, levels = P.levels;
     const uint32_t n0 = fp.plane * fp.n_samples;
     int slot = 0;
-    launch_k(k_pass_init, 1, 256, st, s->ps, n0);
+    launch_k(k_pass_init, 1, 256, st, s->ps, n0, P.first_of_frame);
     CK(cudaGetLastError());
     // a camera outside the scene's root box: tiles whose rays cannot reach the box are finished by k_tile_cull (rt_stream.cuh)
     bool cull_tiles = false;
@@ -642,6 +682,9 @@ void reserve_pools(rt_scene* s, FrameParams& fp, uint64_t n0, uint32_t levels) {
     const uint64_t pool_cap = std::max<uint64_t>(uint64_t(double(n0) * (levels > 1 ? s->pool_factor : 1.0)) + 1024, n0);
     const uint64_t shadow_cap = uint64_t(double(n0) * s->shadow_factor * std::max<size_t>(s->host.lights.size(), 1)) + 1024;
     if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
+    // a pool that has to grow is freed and allocated again: frames still in flight (a queued frame of a sequence) use the old
+    // one, so wait for them explicitly instead of leaning on cudaFree's implicit device synchronisation
+    if (pool_cap > s->rays.cap || shadow_cap > s->jobs.cap || n0 / 32 + 1 > s->tiles0.cap || n0 / 32 + 1 > s->mask0.cap) CK(cudaDeviceSynchronize());
     s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
     s->tiles0.reserve(n0 / 32 + 1);
     if (s->mask0.cap < n0 / 32 + 1) {
@@ -707,8 +750,13 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     CK(cudaEventRecord(s->frame_a, st));
 
     const uint32_t spp = p.samples_per_pixel;
-    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp, PRIMARY_BUDGET / fp.plane)));
+    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp, primary_budget() / fp.plane)));
+    const uint32_t n_passes = (spp + per_pass - 1) / per_pass;
+    // per-launch timing events only where they can be read back as a per-class split of ONE pass structure; a long multi-pass
+    // frame is queued bare (the events would also switch programmatic dependent launch off between its kernels)
+    const bool with_spans = n_passes <= 8;
     auto timed = [&](int cls, auto&& launch) {
+        if (!with_spans) { launch(); CK(cudaGetLastError()); ++s->launches; return; }
         rt_scene::Span sp{s->next_event(), s->next_event(), cls};
         CK(cudaEventRecord(sp.a, st));
         launch();
@@ -725,29 +773,37 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     if (std::memcmp(&key, &s->hint_params, sizeof key) != 0) { s->levels_hint = 0; s->hint_params = key; }
     uint32_t levels_seen = 0;
 
-    uint32_t done = 0;
-    while (done < spp) {
-        const uint32_t ns = std::min(per_pass, spp - done);
-        fp.n_samples = ns;
-        fp.sample_first = p.sample_offset + done;
-        const uint64_t n0 = uint64_t(fp.plane) * ns;
-        for (int attempt = 0;; ++attempt) {
-            reserve_pools(s, fp, n0, levels);
+    // All passes of the frame are queued back to back; the host waits ONCE, at the end, and reads what every pass's
+    // k_pass_commit published.  A pass that outgrew its pools was discarded on the device and the passes behind it skipped
+    // themselves (PassState::carry), so the framebuffer holds exactly the passes in front of it: grow the pools, resume there.
+    reserve_flags(&s->h_flags, &s->h_flags_passes, n_passes);
+    uint32_t first = 0;                               // first pass that is not in the framebuffer yet
+    for (int attempt = 0; first < n_passes; ++attempt) {
+        if (attempt > 24) throw rt_error(RT_ERR_OOM, "wavefront pools keep overflowing");
+        fp.n_samples = std::min(per_pass, spp);
+        reserve_pools(s, fp, uint64_t(fp.plane) * fp.n_samples, levels);           // the largest pass; may grow (and synchronise) here only
+        for (uint32_t k = first; k < n_passes; ++k) {
+            const uint32_t done = k * per_pass, ns = std::min(per_pass, spp - done);
+            fp.n_samples = ns;
+            fp.sample_first = p.sample_offset + done;
             PassLaunch P{fp, m, levels, s->levels_hint ? std::min(levels, s->levels_hint) : levels, has_gi,
-                         done == 0 ? 1 : 0, (!raw && done + ns == spp) ? 1 : 0};
-            enqueue_pass(s, P, d_rgb, s->h_flags, st, timed);
-            CK(cudaStreamSynchronize(st));
-            if (s->h_flags[2] == 0) {
-                s->pool_hwm = std::max<uint64_t>(s->pool_hwm, s->h_flags[0]);
-                s->shadow_hwm = std::max<uint64_t>(s->shadow_hwm, s->h_flags[1]);
-                levels_seen = std::max(levels_seen, s->h_flags[3]);
-                break;
-            }
-            if (attempt >= 24) throw rt_error(RT_ERR_OOM, "wavefront pools keep overflowing");
-            grow_pools_after_overflow(s, s->h_flags, n0);
+                         done == 0 ? 1 : 0, (!raw && done + ns == spp) ? 1 : 0, k == first ? 1 : 0};
+            enqueue_pass(s, P, d_rgb, s->h_flags + 4 * size_t(k), st, timed);
         }
-        done += ns;
-        ++s->passes;
+        CK(cudaStreamSynchronize(st));
+        uint32_t k = first;
+        for (; k < n_passes && s->h_flags[4 * size_t(k) + 2] == 0; ++k) {
+            const uint32_t* f = s->h_flags + 4 * size_t(k);
+            s->pool_hwm = std::max<uint64_t>(s->pool_hwm, f[0]);
+            s->shadow_hwm = std::max<uint64_t>(s->shadow_hwm, f[1]);
+            levels_seen = std::max(levels_seen, f[3]);
+            ++s->passes;
+        }
+        if (k < n_passes) {
+            const uint32_t done = k * per_pass;
+            grow_pools_after_overflow(s, s->h_flags + 4 * size_t(k), uint64_t(fp.plane) * std::min(per_pass, spp - done));
+        }
+        first = k;
     }
     if (s->levels_hint == 0 || levels_seen > s->levels_hint) s->levels_hint = std::max<uint32_t>(levels_seen, 1);
     CK(cudaEventRecord(s->frame_b, st));
@@ -772,30 +828,57 @@ void copy_rect_to_host(rt_scene* s, const Rect& r, const float* d_rgb, float* rg
                          r.y1 - r.y0, cudaMemcpyDeviceToHost, st));
 }
 
+void copy_rect8_to_host(rt_scene* s, const Rect& r, const uint8_t* d_rgb8, uint8_t* rgb8, cudaStream_t st) {
+    const size_t at = (size_t(r.y0) * s->host.width + r.x0) * 3;
+    if (r.x0 == 0 && r.x1 == s->host.width) {
+        CK(cudaMemcpyAsync(rgb8 + at, d_rgb8 + at, size_t(s->host.width) * 3 * (r.y1 - r.y0), cudaMemcpyDeviceToHost, st));
+        return;
+    }
+    CK(cudaMemcpy2DAsync(rgb8 + at, size_t(s->host.width) * 3, d_rgb8 + at, size_t(s->host.width) * 3, size_t(r.x1 - r.x0) * 3,
+                         r.y1 - r.y0, cudaMemcpyDeviceToHost, st));
+}
+// io/image/ppm.hpp:17-19 on the rows of the tile rectangle, on the render stream
+void quantise_rows(rt_scene* s, const Rect& r, const float* d_rgb, uint8_t* d_rgb8, cudaStream_t st) {
+    const size_t first = size_t(r.y0) * s->host.width * 3, count = size_t(r.y1 - r.y0) * s->host.width * 3;
+    k_quantise<<<unsigned((count + 255) / 256), 256, 0, st>>>(d_rgb + first, d_rgb8 + first, count);
+    CK(cudaGetLastError());
+}
+
 void finalize_slot(rt_scene* s, int k) {
     rt_scene::SeqSlot& q = s->seq[k];
     if (!q.in_flight) return;
     CK(cudaEventSynchronize(q.copied));
     q.in_flight = false;
     if (!q.deferred) return;                                   // rendered by the synchronous path: nothing left to check
-    if (q.h_flags[2] != 0) {
-        grow_pools_after_overflow(s, q.h_flags, q.n0);
+    uint32_t bad = 0, levels_used = 0;
+    uint64_t pool_hwm = 0, shadow_hwm = 0;
+    for (; bad < q.n_passes && q.h_flags[4 * size_t(bad) + 2] == 0; ++bad) {
+        pool_hwm = std::max<uint64_t>(pool_hwm, q.h_flags[4 * size_t(bad)]);
+        shadow_hwm = std::max<uint64_t>(shadow_hwm, q.h_flags[4 * size_t(bad) + 1]);
+        levels_used = std::max(levels_used, q.h_flags[4 * size_t(bad) + 3]);
+    }
+    if (bad < q.n_passes) {
+        grow_pools_after_overflow(s, q.h_flags + 4 * size_t(bad), q.n0);
         CK(cudaStreamSynchronize(q.stream));                   // the other frame in flight uses the pools that are about to grow
         render_device(s, q.params, q.target, q.stream, false);
         if (q.host_rgb) copy_rect_to_host(s, rect_of(s, q.params), q.target, q.host_rgb, q.stream);
+        if (q.host_rgb8) {
+            quantise_rows(s, rect_of(s, q.params), q.target, q.fb8.p, q.stream);
+            copy_rect8_to_host(s, rect_of(s, q.params), q.fb8.p, q.host_rgb8, q.stream);
+        }
         CK(cudaStreamSynchronize(q.stream));
         q.rerendered = true;
         return;
     }
-    s->pool_hwm = q.h_flags[0]; s->shadow_hwm = q.h_flags[1];
-    if (std::memcmp(&q.key, &s->hint_params, sizeof q.key) == 0 && (s->levels_hint == 0 || q.h_flags[3] > s->levels_hint))
-        s->levels_hint = std::max<uint32_t>(q.h_flags[3], 1);
+    s->pool_hwm = pool_hwm; s->shadow_hwm = shadow_hwm;
+    if (std::memcmp(&q.key, &s->hint_params, sizeof q.key) == 0 && (s->levels_hint == 0 || levels_used > s->levels_hint))
+        s->levels_hint = std::max<uint32_t>(levels_used, 1);
     rt_counters c{};
     c.primary = q.h_fc->primary; c.primary_hits = q.h_fc->primary_hits;
     c.shadow = q.h_fc->shadow; c.shadow_hits = q.h_fc->shadow_hits;
     c.secondary = q.h_fc->secondary; c.secondary_hits = q.h_fc->secondary_hits;
     c.nodes_pool = s->pool_hwm; c.shadow_pool = s->shadow_hwm;
-    c.kernel_launches = q.launches; c.passes = 1;
+    c.kernel_launches = q.launches; c.passes = q.n_passes;
     CK(cudaEventElapsedTime(&c.ms_total, q.a, q.b));           // no per-class events inside a queued frame
     s->counters = c;
     s->counters_pending = false;
@@ -808,10 +891,14 @@ void drain_sequence(rt_scene* s) {
     finalize_slot(s, older ^ 1);
 }
 
-// rgb: host frame to download into (frame sequences) or null; d_ext: the caller's device frame or null (then the slot's own)
-void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cudaStream_t st, uint64_t* ticket) {
+// rgb / rgb8: host frame to download into (frame sequences) or null; d_ext: the caller's device frame or null (then the slot's own)
+void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cudaStream_t st, uint64_t* ticket, uint8_t* rgb8 = nullptr) {
     check_params(p);
     const Rect rect = rect_of(s, p);
+    // every queued frame of a scene shares its wavefront pools, pass state and counters: two frames in flight on DIFFERENT
+    // streams would race on them
+    for (const rt_scene::SeqSlot& o : s->seq)
+        if (o.in_flight && o.stream != st) throw rt_error(RT_ERR_BAD_ARG, "all queued frames of a scene must use the same stream");
     if (!s->copy_stream) {
         CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
         for (rt_scene::SeqSlot& q : s->seq) {
@@ -820,6 +907,7 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
             CK(cudaEventCreate(&q.a));
             CK(cudaEventCreate(&q.b));
             CK(cudaMallocHost(&q.h_flags, 4 * sizeof(uint32_t)));
+            q.h_flags_passes = 1;
             CK(cudaMallocHost(&q.h_fc, sizeof(FrameCounters)));
         }
     }
@@ -827,17 +915,15 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
     rt_scene::SeqSlot& q = s->seq[k];
     finalize_slot(s, k);                                       // the frame two tickets back (normally long complete)
     if (!d_ext) q.fb.reserve(size_t(s->host.width) * s->host.height * 3);
+    if (rgb8) q.fb8.reserve(size_t(s->host.width) * s->host.height * 3);
     float* const target = d_ext ? d_ext : q.fb.p;
     q.rerendered = false;
 
     FrameParams fp = frame_params(s, p, rect);
     const uint32_t spp = p.samples_per_pixel;
-    const bool one_pass = uint64_t(spp) * fp.plane <= PRIMARY_BUDGET;
-    if (!one_pass) {
-        // several passes re-use the pools and need the pass-by-pass overflow check: synchronous render, overlapped download
-        render_device(s, p, target, st);
-        q.deferred = false;
-    } else {
+    {
+        // every pass of the frame is queued (render_device explains the device-side overflow protocol); what the passes
+        // published is read at wait time, and a frame with a discarded pass is rendered again there
         fetch_counters(s);
         const Mode m = mode_of(p.flags);
         const bool has_gi = fp.gi_rays > 0;
@@ -846,30 +932,39 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
         rt_params key = p;
         key.sample_offset = 0; key.samples_per_pixel = 0;
         if (std::memcmp(&key, &s->hint_params, sizeof key) != 0) { s->levels_hint = 0; s->hint_params = key; }
-        fp.n_samples = spp;
-        fp.sample_first = p.sample_offset;
-        const uint64_t n0 = uint64_t(fp.plane) * spp;
+        const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp, primary_budget() / fp.plane)));
+        const uint32_t n_passes = (spp + per_pass - 1) / per_pass;
+        reserve_flags(&q.h_flags, &q.h_flags_passes, n_passes);
+        fp.n_samples = std::min(per_pass, spp);
+        const uint64_t n0 = uint64_t(fp.plane) * fp.n_samples;
         reserve_pools(s, fp, n0, levels);
-        PassLaunch P{fp, m, levels, s->levels_hint ? std::min(levels, s->levels_hint) : levels, has_gi, 1,
-                     (p.flags & RT_FLAG_RAW_SUM) ? 0 : 1};
         uint32_t launches = 0;
         if (q.used) CK(cudaStreamWaitEvent(st, q.copied, 0));   // the device frame of this slot has been downloaded
         CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
         CK(cudaEventRecord(q.a, st));
-        enqueue_pass(s, P, target, q.h_flags, st, [&](int, auto&& launch) { launch(); CK(cudaGetLastError()); ++launches; });
+        for (uint32_t k = 0; k < n_passes; ++k) {
+            const uint32_t done = k * per_pass, ns = std::min(per_pass, spp - done);
+            fp.n_samples = ns;
+            fp.sample_first = p.sample_offset + done;
+            PassLaunch P{fp, m, levels, s->levels_hint ? std::min(levels, s->levels_hint) : levels, has_gi, done == 0 ? 1 : 0,
+                         (!(p.flags & RT_FLAG_RAW_SUM) && done + ns == spp) ? 1 : 0, k == 0 ? 1 : 0};
+            enqueue_pass(s, P, target, q.h_flags + 4 * size_t(k), st, [&](int, auto&& launch) { launch(); CK(cudaGetLastError()); ++launches; });
+        }
         CK(cudaEventRecord(q.b, st));
         CK(cudaMemcpyAsync(q.h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
-        q.deferred = true; q.params = p; q.key = key; q.n0 = n0; q.launches = launches;
+        q.deferred = true; q.params = p; q.key = key; q.n0 = n0; q.launches = launches; q.n_passes = n_passes; q.per_pass = per_pass;
     }
-    if (rgb) {
+    if (rgb8) quantise_rows(s, rect, target, q.fb8.p, st);     // 6.2 MB instead of 24.9 MB over PCIe for a 1080p frame
+    if (rgb || rgb8) {
         CK(cudaEventRecord(q.rendered, st));
         CK(cudaStreamWaitEvent(s->copy_stream, q.rendered, 0));
-        copy_rect_to_host(s, rect, target, rgb, s->copy_stream);
+        if (rgb) copy_rect_to_host(s, rect, target, rgb, s->copy_stream);
+        if (rgb8) copy_rect8_to_host(s, rect, q.fb8.p, rgb8, s->copy_stream);
         CK(cudaEventRecord(q.copied, s->copy_stream));
     } else {
         CK(cudaEventRecord(q.copied, st));                     // "complete" = rendered
     }
-    q.host_rgb = rgb; q.target = target; q.stream = st; q.in_flight = true; q.used = true;
+    q.host_rgb = rgb; q.host_rgb8 = rgb8; q.target = target; q.stream = st; q.in_flight = true; q.used = true;
     *ticket = s->seq_issued++;
 }
 
@@ -1115,6 +1210,18 @@ int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t*
     });
 }
 
+int rt_render_frame_rgb8_begin(rt_scene* s, const rt_params* p, uint8_t* rgb8, uint64_t* ticket) {
+    return guarded([&] {
+        require_device(s);
+        if (!p || !rgb8 || !ticket) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        if (p->flags & RT_FLAG_RAW_SUM) throw rt_error(RT_ERR_BAD_ARG, "RT_FLAG_RAW_SUM cannot be quantised");
+        std::lock_guard<std::mutex> lock(s->mtx);
+        CK(cudaSetDevice(s->device));
+        begin_frame(s, *p, nullptr, nullptr, s->stream, ticket, rgb8);
+        return int(RT_OK);
+    });
+}
+
 #ifdef RT_STREAM_STATS
 // developer builds only (not declared in include/rt_b200.h): lane-occupancy counters of the stream kernels since the last reset
 extern "C" __attribute__((visibility("default"))) int rt_debug_stream_stats(unsigned long long* out16, int reset) {
@@ -1161,7 +1268,7 @@ int rt_frame_wait(rt_scene* s, uint64_t ticket) {
         else return int(RT_OK);
         const rt_scene::SeqSlot& q = s->seq[ticket & 1];
         // a caller-owned device frame may already have been consumed (e.g. combined with other ranks) before the re-render
-        return (q.rerendered && !q.host_rgb) ? int(RT_FRAME_RERENDERED) : int(RT_OK);
+        return (q.rerendered && !q.host_rgb && !q.host_rgb8) ? int(RT_FRAME_RERENDERED) : int(RT_OK);
     });
 }
 

@@ -43,6 +43,7 @@ RT_HD uint32_t bvh4_child(uint32_t ref, uint32_t cnt) { return (ref << 3) | cnt;
 struct Bvh4ArrayStack {
     struct Entry { float t0; uint32_t child; } e[BVH4_STACK];
     RT_HD void put(int pos, float t0, uint32_t child) { e[pos].t0 = t0; e[pos].child = child; }
+    RT_HD void put_if(bool on, int pos, float t0, uint32_t child) { if (on) put(pos, t0, child); }
     RT_HD void get(int pos, float& t0, uint32_t& child) const { t0 = e[pos].t0; child = e[pos].child; }
 };
 
@@ -100,11 +101,13 @@ RT_HD void bvh4_node_step(BvhState& s, Stack& stack, const float* __restrict__ n
             const int r2 = (2 - n20 - n21) + n32;
             const int r3 = 3 - n30 - n31 - n32;
             const int top = s.sp + touched - 1;                             // rank r >= 1 goes to top - r: rank 1 is popped first
-            uint32_t cur = c0;
-            if (h0 & (r0 != 0)) stack.put(top - r0, t0, c0);
-            if (h1) { if (r1 == 0) cur = c1; else stack.put(top - r1, t1, c1); }
-            if (h2) { if (r2 == 0) cur = c2; else stack.put(top - r2, t2, c2); }
-            if (h3) { if (r3 == 0) cur = c3; else stack.put(top - r3, t3, c3); }
+            // exactly one touched child has rank 0 (an untouched one ranks behind every touched one): it becomes the current node;
+            // the others store themselves, no branch between them
+            stack.put_if(h0 & (r0 != 0), top - r0, t0, c0);
+            stack.put_if(h1 & (r1 != 0), top - r1, t1, c1);
+            stack.put_if(h2 & (r2 != 0), top - r2, t2, c2);
+            stack.put_if(h3 & (r3 != 0), top - r3, t3, c3);
+            const uint32_t cur = (r0 == 0) ? c0 : (r1 == 0) ? c1 : (r2 == 0) ? c2 : c3;
             s.sp = top;
             s.ref = cur >> 3; s.cnt = cur & 7u;
             s.phase = s.cnt ? KD8_LEAF : KD8_WALK;

@@ -33,11 +33,16 @@ namespace rtb {
 #ifndef RT_STREAM_MIN_BLOCKS
 #define RT_STREAM_MIN_BLOCKS 3
 #endif
-#ifndef RT_STREAM_SSTACK
-#define RT_STREAM_SSTACK 12
+#ifndef RT_STREAM4_THREADS
+#define RT_STREAM4_THREADS 128
 #endif
-constexpr int STREAM_SSTACK = RT_STREAM_SSTACK;              // four-wide traversal: stack entries per lane that live in shared memory
-constexpr int STREAM_THREADS = RT_STREAM_THREADS;            // threads per block of the stream kernels (registers per thread follow from it)
+#ifndef RT_STREAM4_MIN_BLOCKS
+#define RT_STREAM4_MIN_BLOCKS 5
+#endif
+// threads per block and resident blocks per SM of the stream kernels, by hierarchy width (registers per thread follow from them:
+// two-wide 256 x 3 = 80 registers; four-wide 128 x 5 = 96 registers - its node step holds seven rows of a node at once)
+template <int WIDE> struct StreamCfg { static constexpr int THREADS = RT_STREAM_THREADS, MIN_BLOCKS = RT_STREAM_MIN_BLOCKS; };
+template <> struct StreamCfg<4> { static constexpr int THREADS = RT_STREAM4_THREADS, MIN_BLOCKS = RT_STREAM4_MIN_BLOCKS; };
 constexpr int STREAM_BURST = RT_STREAM_BURST;                // rounds (node steps + one leaf phase) between completion phases
 constexpr int STREAM_NODE_STEPS = RT_STREAM_NODE_STEPS;      // single-node steps per round; a lane that reaches a leaf parks until the leaf phase
 constexpr int STREAM_LEAF_MIN = RT_STREAM_LEAF_MIN;          // run the leaf phase when this many lanes are parked ...
@@ -69,24 +74,31 @@ __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox
 
 // ---- the traversal stack of a lane, by hierarchy width -------------------------------------------------------------------------
 // Two-wide (rt_bvh.cuh): 16-byte entries in thread-local memory, as in round 1.
-// Four-wide (rt_bvh4.cuh): 8-byte entries; the first STREAM_SSTACK of a lane live in shared memory (one column per thread:
-// consecutive lanes are consecutive 8-byte words, so a warp's access is two conflict-free wavefronts whatever the lanes'
-// depths), deeper ones - rare - in a thread-local tail.  No stack traffic reaches L1, which the node fetches need.
+// Four-wide (rt_bvh4.cuh): 8-byte entries in SHARED memory, one column per thread (consecutive lanes are consecutive 8-byte
+// words, so a warp's access is two conflict-free wavefronts whatever the lanes' depths); no stack traffic reaches L1, which the
+// node fetches need, and a push is one predicated STS.64 with no branch around it.  The block's dynamic shared memory holds
+// bvh4_stack_need + 1 rows - the worst case of the scene's hierarchy, computed when it is collapsed (host/bvh4_collapse.hpp:
+// 24-35 entries on the tested scenes, 24-35 KB per 128-thread block), so there is no overflow path.
 template <int WIDE> struct StreamStack;
 template <> struct StreamStack<2> {
     AccelStackEntry e[ACCEL_STACK];
-    __device__ __forceinline__ void bind(uint2*) {}
+    __device__ __forceinline__ void bind() {}
 };
+extern __shared__ uint2 stream_shared_stack[];
 template <> struct StreamStack<4> {
-    uint2* col;                                  // this thread's column of the block's shared stack
-    uint2 tail[BVH4_STACK - STREAM_SSTACK];
-    __device__ __forceinline__ void bind(uint2* shared_rows) { col = shared_rows + threadIdx.x; }
+    static constexpr uint32_t ROW = uint32_t(StreamCfg<4>::THREADS) * 8u;
+    uint32_t col;                                // shared-memory address of this thread's column
+    __device__ __forceinline__ void bind() { col = uint32_t(__cvta_generic_to_shared(stream_shared_stack + threadIdx.x)); }
     __device__ __forceinline__ void put(int pos, float t0, uint32_t child) {
-        const uint2 v = make_uint2(__float_as_uint(t0), child);
-        if (pos < STREAM_SSTACK) col[pos * STREAM_THREADS] = v; else tail[pos - STREAM_SSTACK] = v;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(col + uint32_t(pos) * ROW), "r"(__float_as_uint(t0)), "r"(child) : "memory");
+    }
+    __device__ __forceinline__ void put_if(bool on, int pos, float t0, uint32_t child) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
+                     :: "r"(col + uint32_t(pos) * ROW), "r"(__float_as_uint(t0)), "r"(child), "r"(uint32_t(on)) : "memory");
     }
     __device__ __forceinline__ void get(int pos, float& t0, uint32_t& child) const {
-        const uint2 v = pos < STREAM_SSTACK ? col[pos * STREAM_THREADS] : tail[pos - STREAM_SSTACK];
+        uint2 v;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(col + uint32_t(pos) * ROW) : "memory");
         t0 = __uint_as_float(v.x); child = v.y;
     }
 };
@@ -110,9 +122,8 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     AccelState st;
-    __shared__ uint2 shared_stack[WIDE == 4 ? STREAM_SSTACK * STREAM_THREADS : 1];
     StreamStack<WIDE> stack;
-    stack.bind(shared_stack);
+    stack.bind();
     st.sp = 0; st.phase = KD8_DONE; st.any_hit = false; st.best.tri = -1; st.best.t = FLT_MAX; st.best.tie_t = -1.0f; st.t_far = FLT_MAX;
     st.ox = st.oy = st.oz = st.dx = st.dy = st.dz = 0.0f;
     bool busy = false, exhausted = false;
@@ -245,9 +256,10 @@ struct PrimaryPolicy {
 };
 
 template <bool FAST, int WIDE>
-__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN_BLOCKS) k_stream_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                         PassState* __restrict__ ps, int work_slot) {
     pdl_wait();
+    if (ps->skipped) return;
     PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
     stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
@@ -317,6 +329,7 @@ __device__ __forceinline__ V3 first_pass_miss_colour(const DScene& sc, const Fra
 __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, float* __restrict__ fb, int divide, PassState* __restrict__ ps,
                                                    uint32_t* __restrict__ tile_list) {
     pdl_wait();
+    if (ps->skipped) return;
     const uint32_t n_tiles = fp.plane >> 5, lane = threadIdx.x & 31u, FULL = 0xFFFFFFFFu;
     const V3 miss = first_pass_miss_colour(sc, fp, divide);
     TileCamera cam;
@@ -358,10 +371,11 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
 }
 
 template <bool FAST, int WIDE>
-__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN_BLOCKS) k_stream_primary_sparse(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                                uint32_t* __restrict__ mask0, float* __restrict__ fb, int divide,
                                                                PassState* __restrict__ ps, int work_slot, const uint32_t* __restrict__ tile_list) {
     pdl_wait();
+    if (ps->skipped) return;
     SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb; p.tile_list = tile_list;
     p.per_sample = tile_list ? ps->n_tiles0 * 32u : fp.plane;
     p.miss_rgb = first_pass_miss_colour(sc, fp, divide);
@@ -389,7 +403,7 @@ struct LevelPolicy {
 };
 
 template <bool FAST, int WIDE>
-__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
+__global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN_BLOCKS) k_stream_level(DScene sc, FrameParams fp, const Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                       PassState* __restrict__ ps, int level, int work_slot) {
     pdl_wait();
     const uint32_t begin = ps->lv[level];
@@ -449,7 +463,7 @@ struct ShadowPolicy {
 };
 
 template <bool TRANSMISSIVE, bool FAST, int WIDE>
-__global__ void __launch_bounds__(RT_STREAM_THREADS, RT_STREAM_MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
+__global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN_BLOCKS) k_stream_shadow(DScene sc, FrameParams fp, ShadowJob* __restrict__ jobs, PassState* __restrict__ ps,
                                                        int work_slot) {
     pdl_wait();
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);

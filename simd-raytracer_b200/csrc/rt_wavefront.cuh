@@ -48,9 +48,14 @@ struct FrameCounters {                  // device memory, reset at the start of 
     unsigned long long primary, primary_hits, shadow, shadow_hits, secondary, secondary_hits;
 };
 
-struct PassState {                      // device memory, reset at the start of every pass
+struct PassState {                      // device memory, reset at the start of every pass (k_pass_init)
     uint32_t pool_count, shadow_count, overflow;
     uint32_t n_tiles0;                  // sparse level 0: tiles k_tile_cull left for the primary stream kernel
+    // Multi-pass frames are queued without a host round trip between passes.  When a pass outgrows its pools it is discarded
+    // on the device as before (overflow != 0) and k_pass_commit sets `carry`, the one word k_pass_init keeps: every LATER pass
+    // of the frame starts with skipped != 0 and does nothing - the framebuffer holds exactly the passes in front of the failed
+    // one, and the host resumes from it after growing the pools.  The first pass of a frame clears `carry`.
+    uint32_t skipped, carry;
     uint32_t lv[MAX_LEVELS + 2];        // level d = pool entries [lv[d], lv[d+1])
     uint32_t work[N_WORK];
     FrameCounters pc;                   // this pass's ray counts; folded into the frame's when the pass is kept
@@ -186,6 +191,7 @@ template <bool FAST, bool ORDERED>
 __global__ void __launch_bounds__(256) k_primary(DScene sc, FrameParams fp, Ray* __restrict__ rays, Hit* __restrict__ hits,
                                                  PassState* __restrict__ ps, int work_slot) {
     pdl_wait();
+    if (ps->skipped) return;
     FrameCounters* fc = &ps->pc;
     const uint32_t n0 = fp.plane * fp.n_samples;
     unsigned long long n_rays = 0, n_hits = 0;
@@ -570,7 +576,7 @@ __global__ void __launch_bounds__(256) k_accumulate(DScene sc, FrameParams fp, c
                                                     const PassState* __restrict__ ps, int first_pass, int divide, uint32_t* __restrict__ mask0) {
     pdl_wait();
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;               // plane is a multiple of 32: a warp is one 8x4 tile
-    if (j >= fp.plane) return;
+    if (j >= fp.plane || ps->skipped) return;
     const bool discard = ps->overflow != 0u;        // an overflowed pass is discarded and rendered again by the host
     uint32_t x, y;
     const bool valid = level0_pixel(fp, j, x, y);

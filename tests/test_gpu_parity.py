@@ -306,16 +306,69 @@ def test_sparse_level0_equals_dense_frames(rt):
 
 
 def test_sparse_level0_in_later_one_sample_passes(rt):
-    """a frame whose samples do not fit one pass: 1920x1080 at 5 spp renders a 4-sample pass and then a ONE-sample pass that
+    """a frame whose samples do not fit one pass: 1920x1080 at 17 spp renders a 16-sample pass and then a ONE-sample pass that
     adds to the framebuffer (sparse level 0 through k_accumulate, not the fused first-pass path)"""
     s, _ = gpu_scene(rt, "hw09_scene5")
-    want = s.render_frame(rt.default_params(samples_per_pixel=5))
+    want = s.render_frame(rt.default_params(samples_per_pixel=17))
     cw = s.counters()
-    got = s.render_frame(rt.default_params(samples_per_pixel=5, flags=rt.FLAG_ORDERED))
+    got = s.render_frame(rt.default_params(samples_per_pixel=17, flags=rt.FLAG_ORDERED))
     cg = s.counters()
     assert cg.passes == 2
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
     assert (cw.primary, cw.primary_hits, cw.shadow, cw.secondary) == (cg.primary, cg.primary_hits, cg.shadow, cg.secondary)
+
+
+_MULTIPASS_CHILD = r"""
+import importlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+rt = importlib.import_module("simd-raytracer_b200")
+from tests.conftest import resized, scene_bytes
+out = {}
+for name, size, kw in (("hw15_scene2", (200, 120), dict(samples_per_pixel=7, diffuse_reflection_ray_count=2, max_ray_depth=4)),
+                       ("hw11_scene8", (160, 96), dict(samples_per_pixel=5, max_ray_depth=6))):
+    for flags in (0, rt.FLAG_ORDERED):
+        s = rt.Scene.from_rtsc(resized(scene_bytes(name), *size))           # FRESH scene: its pools are grown by overflowing passes
+        a = s.render_frame(rt.default_params(flags=flags, **kw))
+        ca = s.counters()
+        b = s.render_frame(rt.default_params(flags=flags, **kw))            # pools are large enough now: no pass is discarded
+        host = np.zeros_like(a)
+        t = s.render_frame_begin(rt.default_params(flags=flags, **kw), host)  # the same frame queued as part of a sequence
+        s.frame_wait(t)
+        cq = s.counters()
+        out[f"{name}_{flags}"] = a
+        out[f"{name}_{flags}_again"] = b
+        out[f"{name}_{flags}_queued"] = host
+        out[f"{name}_{flags}_passes"] = np.array([ca.passes, cq.passes, ca.primary, ca.shadow, ca.secondary, cq.primary, cq.shadow, cq.secondary])
+        s.close()
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_multi_pass_frames_queue_without_a_host_round_trip_per_pass(rt, tmp_path):
+    """render.hpp:35-74's sample loop over several passes: a child process with a tiny pass budget (RT_B200_PASS_ENTRIES, read
+    once per process) renders multi-sample frames as 5-7 one-sample passes queued back to back - on a FRESH scene, so passes
+    outgrow the pools, are discarded on the device, the passes behind them skip themselves and the host resumes from the failed
+    pass.  Every such frame (synchronous, repeated, queued as a sequence frame) must equal the one-pass frame of this process
+    bit for bit, with the same ray counts: samples are added in the same order whatever the pass structure."""
+    import subprocess, sys
+    from .conftest import REPO
+    out = tmp_path / "multipass.npz"
+    env = dict(os.environ, RT_B200_PASS_ENTRIES="30000")
+    subprocess.run([sys.executable, "-c", _MULTIPASS_CHILD, REPO, str(out)], check=True, env=env, timeout=600)
+    z = np.load(out)
+    for name, size, kw, n_pass in (("hw15_scene2", (200, 120), dict(samples_per_pixel=7, diffuse_reflection_ray_count=2, max_ray_depth=4), 7),
+                                   ("hw11_scene8", (160, 96), dict(samples_per_pixel=5, max_ray_depth=6), 5)):
+        s, _ = gpu_scene(rt, name, size=size)
+        for flags in (0, rt.FLAG_ORDERED):
+            want = s.render_frame(rt.default_params(flags=flags, **kw))
+            c = s.counters()
+            assert c.passes == 1 or os.environ.get("RT_B200_PASS_ENTRIES")          # (the suite itself may run with a small budget)
+            for tag in ("", "_again", "_queued"):
+                assert np.array_equal(want.view(np.uint32), z[f"{name}_{flags}{tag}"].view(np.uint32)), (name, flags, tag)
+            p = z[f"{name}_{flags}_passes"]
+            assert p[0] == n_pass and p[1] == n_pass
+            assert tuple(p[2:5]) == (c.primary, c.shadow, c.secondary) and tuple(p[5:8]) == (c.primary, c.shadow, c.secondary)
 
 
 def test_tile_culling_is_conservative(rt):
