@@ -33,6 +33,7 @@
 #include <ostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <unordered_map>
 #include <variant>
@@ -49,6 +50,9 @@ struct b200_accel {
     struct handle_deleter { void operator()(rt_scene* s) const noexcept { rt_scene_destroy(s); } };
     std::shared_ptr<rt_scene> handle;                   // shared: the reference copies accelerators by value in places
     std::vector<std::size_t> mesh_first_triangle;       // global triangle id -> (mesh, local triangle)
+    // page-locked staging frame of the render_frame overload below (pageable memory halves the PCIe rate); shared like `handle`
+    struct pinned_deleter { void operator()(float* p) const noexcept { rt_free_pinned(p); } };
+    mutable std::shared_ptr<float> staging;
 
     explicit b200_accel(std::shared_ptr<const scene<F>> sp, std::uint32_t kd_max_depth = 8, std::uint32_t kd_max_leaf_size = 64,
                         int device = 0)
@@ -188,11 +192,28 @@ inline rt_params b200_config_params() {
     return p;
 }
 
+// image<F> (scene/image.hpp:7-31: one std::vector<color<F>> per row) from a packed float frame.  color<F> is three F in a row
+// (scene/color.hpp:3-7), so a row is one contiguous copy; the rows are filled by a few threads because at 1080p the cost is the
+// page faults of 25 MB of fresh vectors, not the copy.
 template <typename F>
 image<F> b200_image_from_rgb(const float* rgb, std::size_t h, std::size_t w) {
-    std::vector<std::vector<color<F>>> pixels(h, std::vector<color<F>>(w));
-    for (std::size_t y = 0; y < h; ++y)
-        for (std::size_t x = 0; x < w; ++x) pixels[y][x] = color<F>{rgb[(y * w + x) * 3], rgb[(y * w + x) * 3 + 1], rgb[(y * w + x) * 3 + 2]};
+    static_assert(std::is_same_v<F, float> && sizeof(color<F>) == 3 * sizeof(F) && std::is_trivially_copyable_v<color<F>>);
+    std::vector<std::vector<color<F>>> pixels(h);
+    auto fill = [&](std::size_t y0, std::size_t y1) {
+        for (std::size_t y = y0; y < y1; ++y) {
+            const color<F>* row = reinterpret_cast<const color<F>*>(rgb + y * w * 3);
+            pixels[y].assign(row, row + w);
+        }
+    };
+    const std::size_t n_threads = std::min<std::size_t>({8, std::max<std::size_t>(1, std::thread::hardware_concurrency()), std::max<std::size_t>(1, h * w / 200000)});
+    if (n_threads <= 1) fill(0, h);
+    else {
+        std::vector<std::thread> pool;
+        const std::size_t step = (h + n_threads - 1) / n_threads;
+        for (std::size_t y0 = step; y0 < h; y0 += step) pool.emplace_back(fill, y0, std::min(h, y0 + step));
+        fill(0, std::min(h, step));
+        for (auto& t : pool) t.join();
+    }
     return image<F>(h, w, std::move(pixels));
 }
 
@@ -203,7 +224,17 @@ requires std::is_same_v<A, b200_accel<F>>
 image<F> render_frame(const b200_accel<F>& accel, const scheduling_type /* tiles are scheduled by the device */) {
     const rt_params p = b200_config_params();
     const std::size_t h = accel.scene_ptr->config.image_height, w = accel.scene_ptr->config.image_width;
-    std::vector<float> rgb(h * w * 3);
+    if (!accel.staging) accel.staging = std::shared_ptr<float>(static_cast<float*>(rt_alloc_pinned(h * w * 3 * sizeof(float))),
+                                                              typename b200_accel<F>::pinned_deleter{});
+    if (accel.staging) {
+        // the queued path (one frame in flight): its kernels chain without per-launch timing events, the download is one DMA
+        std::uint64_t ticket = 0;
+        int st = rt_render_frame_begin(accel.handle.get(), &p, accel.staging.get(), &ticket);
+        if (st == RT_OK) st = rt_frame_wait(accel.handle.get(), ticket);
+        if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame: ") + rt_status_string(st) + ": " + rt_last_error());
+        return b200_image_from_rgb<F>(accel.staging.get(), h, w);
+    }
+    std::vector<float> rgb(h * w * 3);                  // no page-locked memory to be had: the synchronous call
     const int st = rt_render_frame(accel.handle.get(), &p, rgb.data());
     if (st != RT_OK) throw std::runtime_error(std::string("b200 render_frame: ") + rt_status_string(st) + ": " + rt_last_error());
     return b200_image_from_rgb<F>(rgb.data(), h, w);

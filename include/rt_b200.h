@@ -104,7 +104,7 @@ typedef struct rt_build_opts {
 /* config.hpp:6-17 as run-time parameters, plus the tile / sample slice used for multi-GPU sharding. */
 typedef struct rt_params {
     double fov_degrees;              /* config.hpp:6 */
-    float epsilon;                   /* config.hpp:8 (narrowed to float as src/main.cpp:37) */
+    float epsilon;                   /* config.hpp:8 (narrowed to float as src/main.cpp:37); must be >= FLT_MIN (RT_ERR_BAD_ARG otherwise) */
     float shadow_bias;               /* config.hpp:9  */
     float reflection_bias;           /* config.hpp:10 */
     float refraction_bias;           /* config.hpp:11 */
@@ -169,6 +169,9 @@ RT_API int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts,
 RT_API int rt_scene_create_from_crtscene(const char* path, const char* asset_root, const rt_build_opts* opts, rt_scene** out);
 /* same, from the flat RTSC container used by the test fixtures (tests/helpers/crtscene.py documents the layout) */
 RT_API int rt_scene_create_from_rtsc(const void* bytes, uint64_t n_bytes, const rt_build_opts* opts, rt_scene** out);
+/* the scene as loaded (io/json/loader.hpp:235-265 semantics: every number float(double), 3-component uvs cut to 2, bitmaps decoded
+ * to RGB8) in the flat RTSC container; *n_bytes = its size; buf may be null to ask for the size */
+RT_API int rt_scene_export_rtsc(const rt_scene* s, void* buf, uint64_t cap, uint64_t* n_bytes);
 RT_API void rt_scene_destroy(rt_scene* s);
 RT_API int rt_scene_get_info(const rt_scene* s, rt_scene_info* info);
 

@@ -31,7 +31,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 # every symbol include/rt_b200.h declares
 ABI_SYMBOLS = (
     "rt_abi_version", "rt_status_string", "rt_last_error", "rt_default_build_opts", "rt_default_params",
-    "rt_scene_create", "rt_scene_create_from_crtscene", "rt_scene_create_from_rtsc", "rt_scene_destroy",
+    "rt_scene_create", "rt_scene_create_from_crtscene", "rt_scene_create_from_rtsc", "rt_scene_export_rtsc", "rt_scene_destroy",
     "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_build_kd_accel", "rt_scene_get_bvh_layout",
     "rt_scene_get_geometry",
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
@@ -129,6 +129,7 @@ def _load():
     L.rt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(BuildOpts), C.POINTER(vp)]
     L.rt_scene_create_from_crtscene.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(BuildOpts), C.POINTER(vp)]
     L.rt_scene_create_from_rtsc.argtypes = [vp, u64, C.POINTER(BuildOpts), C.POINTER(vp)]
+    L.rt_scene_export_rtsc.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.rt_scene_destroy.argtypes = [vp]
     L.rt_scene_destroy.restype = None
     L.rt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
@@ -308,6 +309,14 @@ class Scene:
         self.close()
 
     # ---- host-side structures (no GPU needed) -----------------------------------------------------------------------
+    def export_rtsc(self) -> bytes:
+        """the scene as loaded, in the flat RTSC container (rt_scene_export_rtsc)"""
+        n = C.c_uint64(0)
+        _check(lib.rt_scene_export_rtsc(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(lib.rt_scene_export_rtsc(self.h, C.cast(buf, C.c_void_p), n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
     def tree(self):
         n, r = self.info.n_nodes, self.info.n_leaf_refs
         node5 = np.zeros((n, 5), np.uint64)

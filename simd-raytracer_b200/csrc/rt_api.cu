@@ -481,7 +481,15 @@ FrameParams frame_params(const rt_scene* s, const rt_params& p, const Rect& r) {
     return fp;
 }
 
+// The exact-mode pre-filter of the triangle test estimates 1/det with rcp.approx.ftz, which flushes a subnormal determinant to
+// zero; with epsilon >= FLT_MIN the determinant test has rejected such a triangle before (kd_tree_simd.hpp:33-38), so the
+// bit-exact contract holds for every epsilon from the smallest normal float up (the reference's is 1e-6, config.hpp:8).
+void check_epsilon(float eps) {
+    if (!(eps >= FLT_MIN)) throw rt_error(RT_ERR_BAD_ARG, "epsilon must be >= FLT_MIN (1.17549435e-38)");
+}
+
 void check_params(const rt_params& p) {
+    check_epsilon(p.epsilon);
     if (p.samples_per_pixel == 0) throw rt_error(RT_ERR_BAD_ARG, "samples_per_pixel == 0");
     if (p.max_ray_depth > 64) throw rt_error(RT_ERR_BAD_ARG, "max_ray_depth > 64");
     if (p.diffuse_reflection_ray_count > 1024) throw rt_error(RT_ERR_BAD_ARG, "diffuse_reflection_ray_count > 1024");
@@ -754,7 +762,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     const uint32_t n_passes = (spp + per_pass - 1) / per_pass;
     // per-launch timing events only where they can be read back as a per-class split of ONE pass structure; a long multi-pass
     // frame is queued bare (the events would also switch programmatic dependent launch off between its kernels)
-    const bool with_spans = n_passes <= 8;
+    const bool with_spans = n_passes <= 64;
     auto timed = [&](int cls, auto&& launch) {
         if (!with_spans) { launch(); CK(cudaGetLastError()); ++s->launches; return; }
         rt_scene::Span sp{s->next_event(), s->next_event(), cls};
@@ -1029,6 +1037,16 @@ int rt_scene_get_info(const rt_scene* s, rt_scene_info* info) {
     return RT_OK;
 }
 
+int rt_scene_export_rtsc(const rt_scene* s, void* buf, uint64_t cap, uint64_t* n_bytes) {
+    return guarded([&] {
+        if (!s || !n_bytes) throw rt_error(RT_ERR_BAD_ARG, "null argument");
+        const std::vector<uint8_t> out = scene_to_rtsc(s->host);
+        *n_bytes = out.size();
+        if (buf && cap >= out.size()) std::memcpy(buf, out.data(), out.size());
+        return int(RT_OK);
+    });
+}
+
 int rt_scene_get_tree(const rt_scene* s, uint64_t* node5, float* boxes, uint32_t* refs) {
     if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
     const auto& nodes = s->tree.nodes;
@@ -1092,6 +1110,7 @@ int rt_trace_closest_device(rt_scene* s, const float* d_rays, uint64_t n, int ba
     return guarded([&] {
         require_device(s);
         if (n && (!d_rays || !d_hits)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        check_epsilon(epsilon);
         CK(cudaSetDevice(s->device));
         static_assert(sizeof(rt_hit) == sizeof(Hit), "rt_hit layout");
         launch_trace_batch(s, d_rays, n, backface_culling != 0, epsilon, mode_of(flags), reinterpret_cast<Hit*>(d_hits),
@@ -1105,6 +1124,7 @@ int rt_trace_occluded_device(rt_scene* s, const float* d_rays, const float* d_ma
     return guarded([&] {
         require_device(s);
         if (n && (!d_rays || !d_max_t || !d_occluded)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        check_epsilon(epsilon);
         CK(cudaSetDevice(s->device));
         launch_occluded_batch(s, d_rays, d_max_t, n, epsilon, shadow_bias, mode_of(flags), d_occluded,
                               stream ? static_cast<cudaStream_t>(stream) : s->stream);
@@ -1116,6 +1136,7 @@ int rt_trace_closest(rt_scene* s, const float* rays, uint64_t n, int backface_cu
     return guarded([&] {
         require_device(s);
         if (n && (!rays || !hits)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        check_epsilon(epsilon);
         if (!n) return int(RT_OK);
         std::lock_guard<std::mutex> lock(s->mtx);    // called concurrently by the reference's tile workers (render.hpp:93-101)
         CK(cudaSetDevice(s->device));
@@ -1133,6 +1154,7 @@ int rt_trace_occluded(rt_scene* s, const float* rays, const float* max_t, uint64
     return guarded([&] {
         require_device(s);
         if (n && (!rays || !max_t || !occluded)) throw rt_error(RT_ERR_BAD_ARG, "null buffer");
+        check_epsilon(epsilon);
         if (!n) return int(RT_OK);
         std::lock_guard<std::mutex> lock(s->mtx);
         CK(cudaSetDevice(s->device));
@@ -1467,8 +1489,15 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
         const uint64_t g0 = n4 * g->rank / g->world, g1 = n4 * (g->rank + 1) / g->world;
         int n_sm = 0;
         CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g->device));
+        // A SMALL grid on purpose: the combine of frame i runs beside the render of frame i+1, whose persistent grids fill the
+        // machine, so what matters is how few SM slots it needs, not how fast it is alone.  64 blocks x 256 threads x eight 16-byte
+        // peer loads in flight keep ~2 MB on the wire - enough for NVLink's latency-bandwidth product - and leave > 90 % of the
+        // slots to the render; issued on a high-priority stream its blocks are placed first at the next kernel boundary.  (It
+        // also bounds how many blocks can sit spinning on the READY flags.)  RT_B200_PEER_BLOCKS overrides.
+        static const uint64_t max_blocks = [] { unsigned v = 0; if (const char* e = std::getenv("RT_B200_PEER_BLOCKS")) std::sscanf(e, "%u", &v); return uint64_t(v ? v : 64u); }();
+        (void)n_sm;
         const uint64_t want = (g1 - g0 + 255) / 256;
-        const int blocks = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(n_sm) * 8)));
+        const int blocks = int(std::max<uint64_t>(1, std::min<uint64_t>(want, max_blocks)));
         uint8_t* root = g->peer[0] + g->last_slot();
         k_peer_reduce_resolve<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             g->table, uint64_t(g->last_slot() / 4), int(g->world), int(g->rank), g0, g1, float(spp_total),

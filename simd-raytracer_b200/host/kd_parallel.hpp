@@ -22,7 +22,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -45,11 +47,19 @@ template <class F>
 void parallel_for(uint64_t n, uint64_t min_chunk, F&& fn) {
     const uint64_t threads = std::max<uint64_t>(1, std::min<uint64_t>(build_threads(), n / std::max<uint64_t>(min_chunk, 1)));
     if (threads <= 1) { fn(uint64_t(0), n); return; }
+    // an exception in a worker (bad_alloc on a huge scene) must reach the caller's guarded() block, not std::terminate
     std::vector<std::thread> pool;
+    std::exception_ptr failed;
+    std::mutex failed_mutex;
+    auto guarded_fn = [&](uint64_t b, uint64_t e) {
+        try { fn(b, e); }
+        catch (...) { std::lock_guard<std::mutex> g(failed_mutex); if (!failed) failed = std::current_exception(); }
+    };
     const uint64_t step = (n + threads - 1) / threads;
-    for (uint64_t b = step; b < n; b += step) pool.emplace_back([&fn, b, step, n] { fn(b, std::min(n, b + step)); });
-    fn(uint64_t(0), std::min(n, step));
+    for (uint64_t b = step; b < n; b += step) pool.emplace_back([&guarded_fn, b, step, n] { guarded_fn(b, std::min(n, b + step)); });
+    guarded_fn(uint64_t(0), std::min(n, step));
     for (auto& th : pool) th.join();
+    if (failed) std::rethrow_exception(failed);
 }
 
 // the sequential loop: builds the subtree rooted at `root` into t (local indices, root parent = KD_NONE)
@@ -115,16 +125,25 @@ void kd_build_piece(const Policy& pol, typename Policy::Work&& w, KdPiece<Policy
     const uint64_t depth = w.depth;
     { Work drop = std::move(w); (void)drop; }
     std::thread other;
+    std::exception_ptr other_failed;                  // an exception on the spawned thread is rethrown here, after the join
     if (!c1.empty()) {
         p.c[1] = std::make_unique<KdPiece<Policy>>();
         if (spawn_levels > 0 && !c0.empty())
-            other = std::thread([&pol, &p, &c1, cutoff, spawn_levels] { kd_build_piece(pol, std::move(c1), *p.c[1], cutoff, spawn_levels - 1); });
+            other = std::thread([&pol, &p, &c1, &other_failed, cutoff, spawn_levels] {
+                try { kd_build_piece(pol, std::move(c1), *p.c[1], cutoff, spawn_levels - 1); }
+                catch (...) { other_failed = std::current_exception(); }
+            });
     }
-    if (!c0.empty()) {
-        p.c[0] = std::make_unique<KdPiece<Policy>>();
-        kd_build_piece(pol, std::move(c0), *p.c[0], cutoff, spawn_levels - 1);
+    try {
+        if (!c0.empty()) {
+            p.c[0] = std::make_unique<KdPiece<Policy>>();
+            kd_build_piece(pol, std::move(c0), *p.c[0], cutoff, spawn_levels - 1);
+        }
+    } catch (...) {
+        if (other.joinable()) other.join();
+        throw;
     }
-    if (other.joinable()) other.join();
+    if (other.joinable()) { other.join(); if (other_failed) std::rethrow_exception(other_failed); }
     else if (p.c[1]) kd_build_piece(pol, std::move(c1), *p.c[1], cutoff, spawn_levels - 1);
     p.n_nodes = 1 + (p.c[0] ? p.c[0]->n_nodes : 0) + (p.c[1] ? p.c[1]->n_nodes : 0);
     p.n_refs = (p.c[0] ? p.c[0]->n_refs : 0) + (p.c[1] ? p.c[1]->n_refs : 0);

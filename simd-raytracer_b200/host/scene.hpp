@@ -52,6 +52,7 @@ struct HostScene {
 // validates indices (the reference indexes unchecked and would crash) and copies the caller's arrays
 HostScene scene_from_desc(const rt_scene_desc& d);
 HostScene scene_from_rtsc(const void* bytes, uint64_t n);
+std::vector<uint8_t> scene_to_rtsc(const HostScene& s);
 // .crtscene JSON, semantics of io/json/loader.hpp:235-265
 HostScene scene_from_crtscene(const std::string& path, const std::string& asset_root);
 void validate_scene(const HostScene& s);
@@ -59,5 +60,7 @@ void validate_scene(const HostScene& s);
 // decoded image for bitmap textures: RGB8 row major
 struct Bitmap { uint32_t w = 0, h = 0; std::vector<uint8_t> rgb; };
 Bitmap load_bitmap_file(const std::string& path);
+// baseline JPEG bytes -> RGB8 (host/jpeg_decode.cpp); `what` names the file in error messages
+Bitmap decode_jpeg(const std::string& file, const std::string& what);
 
 }  // namespace rtb

@@ -87,6 +87,26 @@ HostScene scene_from_desc(const rt_scene_desc& d) {
     return s;
 }
 
+// the inverse of scene_from_rtsc: what a scene loaded from a .crtscene file looks like in the flat container
+std::vector<uint8_t> scene_to_rtsc(const HostScene& s) {
+    std::vector<uint8_t> out;
+    auto put = [&](const void* src, uint64_t k) { const auto* b = static_cast<const uint8_t*>(src); out.insert(out.end(), b, b + k); };
+    auto u32 = [&](uint64_t v) { const uint32_t w = uint32_t(v); put(&w, 4); };
+    put("RTSC", 4); u32(1);
+    put(s.background, 12);
+    u32(s.width); u32(s.height); u32(s.bucket_size);
+    put(s.camera_position, 12);
+    put(s.camera_matrix, 36);
+    u32(s.lights.size()); put(s.lights.data(), s.lights.size() * sizeof(rt_light_desc));
+    u32(s.textures.size()); put(s.textures.data(), s.textures.size() * sizeof(rt_texture_desc));
+    u32(s.materials.size()); put(s.materials.data(), s.materials.size() * sizeof(rt_material_desc));
+    u32(s.meshes.size());
+    for (const auto& m : s.meshes) { u32(m.material); u32(m.vertices.size() / 3); u32(m.uvs.size() / 2); u32(m.triangles.size() / 3); }
+    for (const auto& m : s.meshes) { put(m.vertices.data(), m.vertices.size() * 4); put(m.uvs.data(), m.uvs.size() * 4); put(m.triangles.data(), m.triangles.size() * 4); }
+    u32(s.texels.size()); put(s.texels.data(), s.texels.size());
+    return out;
+}
+
 // RTSC v1 - layout documented in tests/helpers/crtscene.py
 HostScene scene_from_rtsc(const void* bytes, uint64_t n) {
     const auto* p = static_cast<const uint8_t*>(bytes);
@@ -106,13 +126,19 @@ HostScene scene_from_rtsc(const void* bytes, uint64_t n) {
     get(s.camera_position, 12);
     get(s.camera_matrix, 36);
     static_assert(sizeof(rt_light_desc) == 16 && sizeof(rt_texture_desc) == 44 && sizeof(rt_material_desc) == 28);
-    s.lights.resize(u32());
+    // a count is only believed when the bytes it promises are there (a 40-byte file must not ask for gigabytes)
+    auto counted = [&](uint64_t elem_bytes) {
+        const uint32_t k = u32();
+        if (uint64_t(k) * elem_bytes > n - off) throw rt_error(RT_ERR_PARSE, "RTSC truncated");
+        return k;
+    };
+    s.lights.resize(counted(sizeof(rt_light_desc)));
     get(s.lights.data(), s.lights.size() * sizeof(rt_light_desc));
-    s.textures.resize(u32());
+    s.textures.resize(counted(sizeof(rt_texture_desc)));
     get(s.textures.data(), s.textures.size() * sizeof(rt_texture_desc));
-    s.materials.resize(u32());
+    s.materials.resize(counted(sizeof(rt_material_desc)));
     get(s.materials.data(), s.materials.size() * sizeof(rt_material_desc));
-    s.meshes.resize(u32());
+    s.meshes.resize(counted(16));
     struct head { uint32_t mat, nv, nuv, nt; };
     std::vector<head> heads(s.meshes.size());
     get(heads.data(), heads.size() * sizeof(head));
@@ -266,9 +292,10 @@ HostScene scene_from_crtscene(const std::string& path, const std::string& asset_
 
 // ---------------------------------------------------------------------------------------------------------------
 // bitmap files.  The reference decodes through stb_image (scene/texture/bitmap.hpp:11-37), which is not vendored
-// and not available offline.  Binary PPM (P6) is read natively; for any other file a pre-decoded sidecar
-// "<file>.ppm" is used when present.  Texel bytes are 'parity unpinned' at the bit level anyway (stb's JPEG IDCT
-// differs from libjpeg's by up to 2/255); everything downstream of the bytes is exact.
+// and not available offline.  JPEG (the format of the one bitmap the reference ships) is decoded by
+// host/jpeg_decode.cpp, whose arithmetic reproduces the bitmap quadrant of the published outputs/textures.png
+// exactly; binary PPM (P6) is read natively; for any other file a pre-decoded sidecar "<file>.ppm" is used when
+// present.  Everything downstream of the texel bytes is exact.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 bool parse_ppm(const std::string& data, Bitmap& out) {
@@ -303,12 +330,13 @@ Bitmap load_bitmap_file(const std::string& path) {
     bool opened = true;
     try { data = read_file(path); } catch (const rt_error&) { opened = false; }
     if (opened && parse_ppm(data, bm)) return bm;
+    if (opened && data.size() > 3 && uint8_t(data[0]) == 0xFF && uint8_t(data[1]) == 0xD8) return decode_jpeg(data, path);
     try {
         data = read_file(path + ".ppm");
         if (parse_ppm(data, bm)) return bm;
     } catch (const rt_error&) {}
     if (!opened) throw rt_error(RT_ERR_IO, "cannot open bitmap " + path);
-    throw rt_error(RT_ERR_UNSUPPORTED, "bitmap " + path + ": only binary PPM (P6), or a '" + path + ".ppm' sidecar, can be decoded");
+    throw rt_error(RT_ERR_UNSUPPORTED, "bitmap " + path + ": only JPEG (baseline), binary PPM (P6), or a '" + path + ".ppm' sidecar, can be decoded");
 }
 
 }  // namespace rtb

@@ -165,6 +165,73 @@ def test_crtscene_loader_follows_the_reference_schema(rt, oracle_mod, tmp_path):
         assert x.tobytes() == y.tobytes()
 
 
+REAL_SCENES = {"hw15_scene2": "scenes/hw15/scene2.crtscene", "hw09_scene5": "scenes/hw09/scene5.crtscene",
+               "hw11_scene8": "scenes/hw11/scene8.crtscene", "hw12_scene4": "scenes/hw12/scene4.crtscene"}
+
+
+def _real_scene_tree(tmp_path, name: str) -> str:
+    """the reference's own scene file (and the one JPEG it ships), unpacked from tests/golden/crtscene/ into the directory layout
+    the file's relative bitmap path expects (README.md:32-35: paths are relative to the project root)"""
+    import gzip
+    import shutil
+    rel = REAL_SCENES[name]
+    dst = tmp_path / rel
+    dst.parent.mkdir(parents=True, exist_ok=True)
+    with gzip.open(os.path.join(REPO, "tests", "golden", "crtscene", name + ".crtscene.gz"), "rb") as fh:
+        dst.write_bytes(fh.read())
+    tex = tmp_path / "scenes" / "hw12" / "textures"
+    tex.mkdir(parents=True, exist_ok=True)
+    shutil.copy(os.path.join(REPO, "tests", "golden", "crtscene", "textures", "dragon.jpg"), tex / "dragon.jpg")
+    return str(dst)
+
+
+@pytest.mark.parametrize("name", sorted(REAL_SCENES))
+def test_crtscene_loader_reads_the_reference_scene_files(rt, tmp_path, name):
+    """rt_scene_create_from_crtscene on the reference's REAL scene files (io/json/loader.hpp:235-265; configs 1-4 of
+    BASELINE.json, committed as gz copies) gives, byte for byte, the RTSC fixture every parity test is fed - the fixture the
+    compiled unmodified reference rendered the goldens from.  hw12/scene4 includes the JPEG texture (scene/texture/bitmap.hpp:
+    11-37): the product's decoder (host/jpeg_decode.cpp) must produce the very texel bytes of the fixture, which an independent
+    restatement (tests/helpers/jpeg_stb.py) decoded and which reproduce the published outputs/textures.png exactly."""
+    path = _real_scene_tree(tmp_path, name)
+    s = rt.Scene.from_crtscene(path, asset_root=str(tmp_path), device=rt.DEVICE_HOST_ONLY)
+    assert s.export_rtsc() == scene_bytes(name)
+    # and the test-side loader that writes the fixtures agrees with both
+    assert crtscene.to_rtsc_bytes(crtscene.load_crtscene(path, root=str(tmp_path))) == scene_bytes(name)
+
+
+def test_jpeg_decoder_edge_cases(rt, tmp_path):
+    """the bitmap path beyond the one file the reference ships: grey-scale, 4:2:0 / 4:2:2 chroma, restart intervals and odd sizes
+    decode (to within the usual +-3/255 of libjpeg, whose IDCT and upsampling differ in the last bits), progressive files and
+    garbage are refused with a status instead of a crash"""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    base = np.clip(np.add.outer(np.linspace(0, 200, 37), np.linspace(0, 55, 53))[..., None] + rng.normal(0, 6, (37, 53, 3)), 0, 255).astype(np.uint8)
+    doc = json.loads(json.dumps(CRT))
+    doc["textures"].append({"name": "bmp", "type": "bitmap", "file_path": "t.jpg"})
+
+    def load(**save_kw):
+        img = Image.fromarray(base if save_kw.pop("colour", True) else base[..., 0])
+        img.save(tmp_path / "t.jpg", format="JPEG", quality=92, **save_kw)
+        (tmp_path / "t.crtscene").write_text(json.dumps(doc))
+        s = rt.Scene.from_crtscene(str(tmp_path / "t.crtscene"), asset_root=str(tmp_path), device=rt.DEVICE_HOST_ONLY)
+        got = np.frombuffer(s.export_rtsc()[-37 * 53 * 3:], np.uint8).reshape(37, 53, 3)
+        want = np.asarray(Image.open(tmp_path / "t.jpg").convert("RGB"))
+        return np.abs(got.astype(int) - want.astype(int)).max()
+
+    assert load(subsampling=0) <= 3                      # 4:4:4
+    assert load(subsampling=1) <= 8                      # 4:2:2: libjpeg's default upsampling is another filter than the triangle one
+    assert load(subsampling=2) <= 8                      # 4:2:0
+    assert load(colour=False) <= 3                       # one component
+    assert load(subsampling=2, restart_marker_blocks=3) <= 8
+    with pytest.raises(rt.RtError) as e:
+        load(progressive=True)
+    assert e.value.status == rt.RT_ERR_UNSUPPORTED
+    (tmp_path / "t.jpg").write_bytes(b"\xff\xd8\xff\xdb\x00\x03\x00" + bytes(40))
+    with pytest.raises(rt.RtError) as e:
+        rt.Scene.from_crtscene(str(tmp_path / "t.crtscene"), asset_root=str(tmp_path), device=rt.DEVICE_HOST_ONLY)
+    assert e.value.status in (rt.RT_ERR_PARSE, rt.RT_ERR_UNSUPPORTED)
+
+
 @pytest.mark.parametrize("mutate,status", [
     (lambda d: d["materials"].__setitem__(0, {"type": "glossy", "smooth_shading": False}), 5),      # loader.hpp:145
     (lambda d: d["textures"].__setitem__(0, {"name": "chk", "type": "noise"}), 5),                   # loader.hpp:104

@@ -122,9 +122,9 @@ def test_oracle_philox_gi_within_the_reference_run_to_run_floor(oracle_mod):
 
 
 def test_oracle_reproduces_the_exact_quadrants_of_textures_png(oracle_mod):
-    """outputs/textures.png == scenes/hw12/scene4.crtscene at the default config (README.md:64-65).  The albedo, edges and
-    checker quadrants are exact; the bitmap quadrant (bottom right) depends on the JPEG decoder (stb_image there, another
-    decoder in the fixture: SURVEY.md section 8c) and is held to +-2/255 on <= 0.1 % of the frame's pixels."""
+    """outputs/textures.png == scenes/hw12/scene4.crtscene at the default config (README.md:64-65).  The whole frame is a
+    golden: the albedo, edges and checker quadrants, and the bitmap quadrant as well now that the fixture's texel bytes are decoded
+    with the reference decoder's arithmetic (tests/helpers/jpeg_stb.py) - 0 differing pixels."""
     tex = np.load(os.path.join(HERE, "golden", "textures_png.npz"))["rgb8"]
     o = oracle_mod.Oracle(scene_bytes("hw12_scene4"))
     img, _ = o.render(oracle_mod.default_params())
