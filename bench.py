@@ -343,7 +343,8 @@ def north_star_scaling(rt, args, rank: int, world: int, local: int, flags: int):
         out["sample_slices"] = rec
         # ---- row bands (bucket rows dealt round-robin): all samples of the rank's bands; the other rows of its frame stay zero ----
         g = group()
-        bands = rt.row_bands(H, 64, rank, world)
+        BAND = 16                                                   # rows per band: 135 bands at 4K, so 16 or 17 per rank at N = 8
+        bands = rt.row_bands(H, BAND, rank, world)
         band_params = [rt.default_params(samples_per_pixel=T, y0=y0, y1=y1, flags=flags, **kw) for y0, y1 in bands]
         def by_bands():
             for bp in band_params:
@@ -351,7 +352,7 @@ def north_star_scaling(rt, args, rank: int, world: int, local: int, flags: int):
             g.combine(1, rt.PEER_OUT_RGB, stream=stream.cuda_stream)      # sum of disjoint bands; dividing by 1 is exact
         # both frame slots of the group must hold this rank's bands and zeros elsewhere: three frames touch both slots
         ms = timed(by_bands, frames=2, warm=2)
-        rec = {"ms_per_frame": ms, "mrays_s": rays / ms / 1e3, "efficiency_vs_n1": ms1 / (world * ms), "bands_per_gpu": len(bands), "band_rows": 64}
+        rec = {"ms_per_frame": ms, "mrays_s": rays / ms / 1e3, "efficiency_vs_n1": ms1 / (world * ms), "bands_per_gpu": len(bands), "band_rows": BAND}
         if rank == 0:
             got, _ = g.read_result(stream.cuda_stream, want_rgb8=False)
             rec["combined_frame_equals_single_gpu_frame"] = bool(np.array_equal(got, frame1.cpu().numpy()))
@@ -452,8 +453,10 @@ def main() -> None:
     # N > 1, peer combine: one step = the render of frame i (main stream) and, concurrently on a second stream, the fused
     # wait+reduce+resolve of frame i-1 (rt_peer_* keeps two frame slots per rank).  The combine is released by the step's
     # start event, so every timed step [a, b] contains exactly one render and one combine; nothing runs during the L2 flush.
-    side = torch.cuda.Stream(priority=-1) if peer else None      # high priority: its few blocks are placed first at a kernel boundary
+    # BENCH_SIDE_PRIORITY=-1 (high priority for the combine) was measured slower: 0.470 vs 0.448 ms per step at N = 2
+    side = torch.cuda.Stream(priority=int(os.environ.get("BENCH_SIDE_PRIORITY", "0"))) if peer else None
     ev_done = torch.cuda.Event() if peer else None
+    ev_rendered = torch.cuda.Event() if peer else None
     outputs = rt.PEER_OUT_RGB                      # N = 1 leaves a float frame in HBM; so does the combine (rank 0)
     pending = [False]
 
@@ -469,19 +472,34 @@ def main() -> None:
             if rank == 0:
                 scene.resolve_sum_device(fb.data_ptr(), spp_total, d_rgb=fb.data_ptr(), d_rgb8=rgb8.data_ptr(), stream=stream.cuda_stream)
 
+    trace = [] if os.environ.get("BENCH_TRACE_COMBINE") else None      # developer probe: where a pipelined step spends its time
+
     def combine_pending(start_event, out=None):
         """the combine of the frame signalled last, on the side stream, not before `start_event`"""
         side.wait_event(start_event)
         peer.reduce_resolve(spp_total, out or outputs, stream=side.cuda_stream)
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(side); trace[-1]["reduce_end"] = e
         peer.wait_done(stream=side.cuda_stream)
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(side); trace[-1]["wait_done_end"] = e
         ev_done.record(side)
 
     def step_pipelined(a, b):
         a.record(stream)
+        if trace is not None:
+            trace.append({"a": a, "b": b})
         if pending[0]:
             combine_pending(a)
         t = scene.render_frame_device_begin(params, peer.framebuffer, stream=stream.cuda_stream)     # queued, no host sync
-        peer.signal_ready(stream.cuda_stream)                                                        # flips the frame slot
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(stream); trace[-1]["render_end"] = e
+        # "frame i is rendered" is published from the SIDE stream, behind an event of the render stream: the system-scope release
+        # towards the peers (~10 us) then runs beside the next frame's first kernels instead of in front of them; the combine of
+        # this frame follows it in side-stream order
+        ev_rendered.record(stream)
+        side.wait_event(ev_rendered)
+        peer.signal_ready(side.cuda_stream)                                                          # flips the frame slot
         if pending[0]:
             stream.wait_event(ev_done)             # frame i+1 renders into the slot the combined frame used
         pending[0] = True
@@ -547,6 +565,11 @@ def main() -> None:
         barrier()
         t_wall = time.perf_counter() - t_wall0
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    if trace:
+        import statistics
+        rows = [t for t in trace if "reduce_end" in t and t["a"] in [x for x, _ in ev]]
+        for k in ("reduce_end", "wait_done_end", "render_end", "b"):
+            print(f"rank {rank}: a -> {k:14s} median {statistics.median(t['a'].elapsed_time(t[k]) for t in rows) * 1e3:8.1f} us", file=sys.stderr)
     if peer:
         # drain (untimed): the combine of the last timed frame
         e1 = torch.cuda.Event()

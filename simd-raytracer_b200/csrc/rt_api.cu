@@ -1364,6 +1364,8 @@ struct rt_peer_group {
     float* host_dev = nullptr;              // the same memory as this device addresses it
     size_t host_bytes = 0;
     uint32_t host_epoch = 0;                // last frame that was sent to the shared host frame
+    uint8_t* stage = nullptr;               // copy-engine gather: this rank's slice of every OTHER rank's raw sums ((world - 1) x stage_stride bytes)
+    size_t stage_stride = 0;
     size_t next_slot() const { return size_t(epoch & 1u) * slot_bytes; }           // where the NEXT frame is rendered
     size_t last_slot() const { return size_t((epoch - 1u) & 1u) * slot_bytes; }    // the frame signalled last
 };
@@ -1473,7 +1475,7 @@ int rt_peer_signal_ready(rt_peer_group* g, void* stream) {
         if (!g || !g->connected) throw rt_error(RT_ERR_BAD_ARG, "peer group is not connected");
         CK(cudaSetDevice(g->device));
         ++g->epoch;
-        k_peer_signal_ready<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table, int(g->world), int(g->rank), g->epoch);
+        launch_ks(k_peer_signal_ready, 1, 32, 0, static_cast<cudaStream_t>(stream), g->table, int(g->world), int(g->rank), g->epoch);
         CK(cudaGetLastError());
         return int(RT_OK);
     });
@@ -1489,20 +1491,49 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
         const uint64_t g0 = n4 * g->rank / g->world, g1 = n4 * (g->rank + 1) / g->world;
         int n_sm = 0;
         CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g->device));
-        // A SMALL grid on purpose: the combine of frame i runs beside the render of frame i+1, whose persistent grids fill the
-        // machine, so what matters is how few SM slots it needs, not how fast it is alone.  64 blocks x 256 threads x eight 16-byte
-        // peer loads in flight keep ~2 MB on the wire - enough for NVLink's latency-bandwidth product - and leave > 90 % of the
-        // slots to the render; issued on a high-priority stream its blocks are placed first at the next kernel boundary.  (It
-        // also bounds how many blocks can sit spinning on the READY flags.)  RT_B200_PEER_BLOCKS overrides.
-        static const uint64_t max_blocks = [] { unsigned v = 0; if (const char* e = std::getenv("RT_B200_PEER_BLOCKS")) std::sscanf(e, "%u", &v); return uint64_t(v ? v : 64u); }();
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        // How the peers' samples reach this rank.  "ce" (default): the rank's COPY ENGINES fetch its slice of every other rank's
+        // framebuffer into a local staging buffer (one D2D copy per peer over NVLink, behind a one-block kernel that waits for
+        // the READY flags), and the reduce kernel then reads local memory only - no SM waits on an NVLink round trip, which is
+        // what slowed the render of the next frame the combine runs beside (N = 2, config 2: 422 -> 40x us per render with the
+        // P2P-load kernel beside it).  "kernel": the kernel loads from the peers' memory itself (16 loads in flight per thread).
+        // The results go to rank 0 by P2P stores either way.  RT_B200_PEER_GATHER / RT_B200_PEER_BLOCKS override (A/B runs).
+        static const bool use_ce = [] { const char* e = std::getenv("RT_B200_PEER_GATHER"); return !(e && std::strcmp(e, "kernel") == 0); }();
+        static const uint64_t max_blocks = [] { unsigned v = 0; if (const char* e = std::getenv("RT_B200_PEER_BLOCKS")) std::sscanf(e, "%u", &v); return uint64_t(v ? v : 128u); }();
         (void)n_sm;
-        const uint64_t want = (g1 - g0 + 255) / 256;
+        const bool last_rank = g->rank + 1 == g->world;
+        const uint64_t f0 = g0 * 4, f1 = last_rank ? g->n : g1 * 4;               // this rank's float range, the frame's tail included
+        PeerSources src{};
+        const bool gather = use_ce && g->world > 1;
+        if (gather) {
+            if (!g->stage) {
+                g->stage_stride = align256((g->n / g->world + 8) * sizeof(float));
+                CK(cudaMalloc(&g->stage, g->stage_stride * (g->world - 1)));
+            }
+            k_peer_wait_ready<<<1, 32, 0, st>>>(g->table.flags[g->rank], int(g->world), g->epoch);
+            CK(cudaGetLastError());
+            uint32_t k = 0;
+            for (uint32_t r = 0; r < g->world; ++r) {
+                const float* fb_r = reinterpret_cast<const float*>(g->peer[r] + g->last_slot());
+                if (r == g->rank) { src.p[r] = fb_r; continue; }
+                float* dst = reinterpret_cast<float*>(g->stage + size_t(k++) * g->stage_stride);
+                CK(cudaMemcpyAsync(dst, fb_r + f0, (f1 - f0) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                src.p[r] = dst - f0;                                             // indexed with the frame's element index
+            }
+        } else {
+            for (uint32_t r = 0; r < g->world; ++r) src.p[r] = reinterpret_cast<const float*>(g->peer[r] + g->last_slot());
+        }
+        const int unroll = gather ? 2 : (g->world <= 2 ? 8 : g->world <= 4 ? 4 : g->world <= 8 ? 2 : 1);
+        const uint64_t want = (g1 - g0 + uint64_t(256) * unroll - 1) / (uint64_t(256) * unroll);
         const int blocks = int(std::max<uint64_t>(1, std::min<uint64_t>(want, max_blocks)));
         uint8_t* root = g->peer[0] + g->last_slot();
-        k_peer_reduce_resolve<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            g->table, uint64_t(g->last_slot() / 4), int(g->world), int(g->rank), g0, g1, float(spp_total),
-            (outputs & 1u) ? reinterpret_cast<float*>(root + g->off_rgb) : nullptr, (outputs & 2u) ? root + g->off_rgb8 : nullptr,
-            g->epoch, n4 * 4, g->n, (outputs & RT_PEER_OUT_HOST_RGB) ? reinterpret_cast<float*>(g->block + g->last_slot() + g->off_rgb) : nullptr);
+#define PEER_REDUCE(U)                                                                                                                        \
+        k_peer_reduce_resolve<U><<<blocks, 256, 0, st>>>(                                                                                     \
+            g->table, src, gather ? 0 : 1, int(g->world), int(g->rank), g0, g1, float(spp_total),                                             \
+            (outputs & 1u) ? reinterpret_cast<float*>(root + g->off_rgb) : nullptr, (outputs & 2u) ? root + g->off_rgb8 : nullptr,            \
+            g->epoch, n4 * 4, g->n, (outputs & RT_PEER_OUT_HOST_RGB) ? reinterpret_cast<float*>(g->block + g->last_slot() + g->off_rgb) : nullptr)
+        if (unroll == 8) PEER_REDUCE(8); else if (unroll == 4) PEER_REDUCE(4); else if (unroll == 2) PEER_REDUCE(2); else PEER_REDUCE(1);
+#undef PEER_REDUCE
         CK(cudaGetLastError());
         if (outputs & RT_PEER_OUT_HOST_RGB) {
             // this rank's slice: its own copy engine, its own PCIe link; then tell every rank (the consumer waits in rt_peer_wait_done)
@@ -1595,6 +1626,7 @@ void rt_peer_group_destroy(rt_peer_group* g) {
     for (uint32_t r = 0; r < g->world; ++r)
         if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
     if (g->block) cudaFree(g->block);
+    if (g->stage) cudaFree(g->stage);
     delete g;
 }
 

@@ -44,8 +44,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
-// "my framebuffer holds frame `epoch`": one remote store per peer
+// "my framebuffer holds frame `epoch`": one remote store per peer.  Launched with programmatic stream serialisation like the
+// kernels of a pass (rt_api.cu launch_ks): it is set up while the frame's last kernel drains and waits here for its completion.
 __global__ void k_peer_signal_ready(PeerTable t, int world, int rank, uint32_t epoch) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = threadIdx.x;
     if (i < world) st_release_sys(t.flags[i] + PEER_FLAG_READY + rank, epoch);
 }
@@ -72,41 +74,74 @@ __device__ __forceinline__ uint8_t peer_quantise(float c) {          // io/image
     return uint8_t(__dmul_rn(255.999, double(cl)));
 }
 
-// n4 = number of float4 groups of the whole frame; this rank owns groups [g0, g1)
-__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, uint64_t slot_floats, int world, int rank, uint64_t g0, uint64_t g1, float div,
+// n4 = number of float4 groups of the whole frame; this rank owns groups [g0, g1).
+// U groups per thread and round, U x RB = 16 peer loads of 16 bytes in flight per thread (RB = ranks per batch): the kernel is
+// bound by the NVLink round trip, not by bandwidth, so what it needs is loads in flight - with them a SMALL grid moves the frame
+// in a few tens of microseconds and leaves the SM slots to the render of the next frame it runs beside.
+// Where rank r's samples of this frame are read from, as a pointer that is indexed with the FRAME's element index: the peer's
+// framebuffer slot itself (P2P loads through NVLink), or this rank's staging copy of its slice of it - which the copy engines
+// fetched, so that no SM waits on an NVLink round trip (rt_peer_reduce_resolve, RT_B200_PEER_GATHER) - shifted back by the
+// slice's first element.
+struct PeerSources { const float* p[PEER_MAX]; };
+
+// every peer has published "frame `epoch` rendered" (in front of the copy-engine gather, which cannot wait on a flag itself)
+__global__ void k_peer_wait_ready(const uint32_t* my_flags, int world, uint32_t epoch) {
+    const int i = threadIdx.x;
+    if (i < world)
+        while (ld_acquire_sys(my_flags + PEER_FLAG_READY + i) < epoch) __nanosleep(32);
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, PeerSources src, int wait_ready, int world, int rank, uint64_t g0, uint64_t g1, float div,
                                                              float* __restrict__ root_rgb, uint8_t* __restrict__ root_rgb8,
                                                              uint32_t epoch, uint64_t n_tail_begin, uint64_t n_total, float* __restrict__ own_rgb) {
+    constexpr int RB = 16 / U;
     // ---- wait until every peer has rendered frame `epoch` (flags are in MY memory, peers store into them) ----
-    if (threadIdx.x < world)
-        while (ld_acquire_sys(t.flags[rank] + PEER_FLAG_READY + threadIdx.x) < epoch) __nanosleep(32);
-    __syncthreads();
+    if (wait_ready) {
+        if (threadIdx.x < world)
+            while (ld_acquire_sys(t.flags[rank] + PEER_FLAG_READY + threadIdx.x) < epoch) __nanosleep(32);
+        __syncthreads();
+    }
 
-    // slot_floats: offset of this frame's slot inside every rank's block (the blocks have the same layout)
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-    for (uint64_t g = g0 + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < g1; g += stride) {
-        float4 s = __ldcg(reinterpret_cast<const float4*>(t.fb[0] + slot_floats) + g);
-        // all peers' loads are issued before the first add (one NVLink round trip per eight ranks, not one per rank);
+    for (uint64_t base = g0 + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; base < g1; base += stride * U) {
+        float4 s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (base + u * stride < g1) s[u] = __ldcg(reinterpret_cast<const float4*>(src.p[0]) + base + u * stride);
+        // a batch of peers' loads is issued before the first add (one NVLink round trip per batch, not one per rank);
         // the adds stay in rank order = sample order (render.hpp:66-72)
-        for (int r0 = 1; r0 < world; r0 += 8) {
-            float4 v[8];
+        for (int r0 = 1; r0 < world; r0 += RB) {
+            float4 v[U][RB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (r0 + k < world) v[k] = __ldcg(reinterpret_cast<const float4*>(t.fb[r0 + k] + slot_floats) + g);
+            for (int k = 0; k < RB; ++k)
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (r0 + k < world) { s.x = s.x + v[k].x; s.y = s.y + v[k].y; s.z = s.z + v[k].z; s.w = s.w + v[k].w; }
+                for (int u = 0; u < U; ++u)
+                    if (r0 + k < world && base + u * stride < g1)
+                        v[u][k] = __ldcg(reinterpret_cast<const float4*>(src.p[r0 + k]) + base + u * stride);
+#pragma unroll
+            for (int k = 0; k < RB; ++k)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (r0 + k < world && base + u * stride < g1) { s[u].x = s[u].x + v[u][k].x; s[u].y = s[u].y + v[u][k].y; s[u].z = s[u].z + v[u][k].z; s[u].w = s[u].w + v[u][k].w; }
         }
-        s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);   // :74
-        if (root_rgb) reinterpret_cast<float4*>(root_rgb)[g] = s;
-        if (own_rgb) reinterpret_cast<float4*>(own_rgb)[g] = s;            // this rank's slice in its OWN memory: copied to the shared host frame next
-        if (root_rgb8)
-            reinterpret_cast<uchar4*>(root_rgb8)[g] = make_uchar4(peer_quantise(s.x), peer_quantise(s.y), peer_quantise(s.z), peer_quantise(s.w));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t g = base + u * stride;
+            if (g >= g1) continue;
+            float4 q = s[u];
+            q.x = __fdiv_rn(q.x, div); q.y = __fdiv_rn(q.y, div); q.z = __fdiv_rn(q.z, div); q.w = __fdiv_rn(q.w, div);   // :74
+            if (root_rgb) reinterpret_cast<float4*>(root_rgb)[g] = q;
+            if (own_rgb) reinterpret_cast<float4*>(own_rgb)[g] = q;        // this rank's slice in its OWN memory: copied to the shared host frame next
+            if (root_rgb8)
+                reinterpret_cast<uchar4*>(root_rgb8)[g] = make_uchar4(peer_quantise(q.x), peer_quantise(q.y), peer_quantise(q.z), peer_quantise(q.w));
+        }
     }
     // the last rank also owns the (< 4 element) tail of a frame whose size is not a multiple of four floats
     if (rank == world - 1 && blockIdx.x == 0) {
         for (uint64_t i = n_tail_begin + threadIdx.x; i < n_total; i += blockDim.x) {
-            float s = __ldcg(t.fb[0] + slot_floats + i);
-            for (int r = 1; r < world; ++r) s = s + __ldcg(t.fb[r] + slot_floats + i);
+            float s = __ldcg(src.p[0] + i);
+            for (int r = 1; r < world; ++r) s = s + __ldcg(src.p[r] + i);
             s = __fdiv_rn(s, div);
             if (root_rgb) root_rgb[i] = s;
             if (own_rgb) own_rgb[i] = s;
