@@ -89,10 +89,6 @@ typedef struct rt_build_opts {
     uint32_t kd_max_depth;           /* default 8  (kd_tree_simd.hpp:65) */
     uint32_t kd_max_leaf_size;       /* default 64 (kd_tree_simd.hpp:66) */
     int32_t device;                  /* CUDA ordinal; RT_DEVICE_HOST_ONLY builds tree + layout without a GPU */
-    /* the backend's own tree used by RT_FLAG_ORDERED (surface-area heuristic, clipped triangles).
-     * 0 = automatic: depth min(30, 8 + 1.3 log2(n_triangles)); the heuristic decides where leaves end (leaf size is a floor) */
-    uint32_t accel_max_depth;
-    uint32_t accel_max_leaf_size;
     /* width of the bounding-volume hierarchy the accelerated mode walks: 2 = 64-byte two-child nodes (csrc/rt_bvh.cuh), 4 = their
      * four-wide collapse, 128-byte nodes (csrc/rt_bvh4.cuh; the reference author's own TODO, README.md:118-124); 0 = the default
      * (RT_DEFAULT_ACCEL_WIDTH).  Frames, hits and ray counts do not depend on it. */
@@ -120,8 +116,14 @@ typedef struct rt_params {
 
 #define RT_FLAG_RAW_SUM       0x1u   /* write the slice's sample sum; the caller divides after combining ranks */
 #define RT_FLAG_FAST_MATH     0x2u   /* FMA-contracted traversal + intersection (not bit-exact) */
-#define RT_FLAG_ORDERED       0x4u   /* accelerated query: front-to-back split-plane traversal over the 8-byte nodes of the
-                                        backend's own deeper kd-tree; same t/u/v bits, ties by lowest triangle index */
+#define RT_FLAG_ORDERED       0x4u   /* accelerated query: near-child-first traversal of the backend's OWN bounding-volume hierarchy
+                                        (binned SAH, <= 4 triangles per leaf; two-wide 64-byte or four-wide 128-byte nodes, see
+                                        rt_build_opts.accel_width) instead of the reference's kd-tree in the reference's visit
+                                        order.  Same hits bit for bit: every triangle test is the reference's arithmetic, and a
+                                        query with an exact-t tie between two triangles is re-run in reference order.  This is a
+                                        stated deviation from "8-byte kd nodes, short stack in registers" (DESIGN.md section 0):
+                                        the reference's own tree is still flattened to 8-byte nodes (rt_scene_get_device_layout)
+                                        and walked by flags = 0 */
 
 typedef struct rt_hit {              /* the part of hit<F> (render/hit.hpp:9-21) that cannot be recomputed */
     float t, u, v;
@@ -135,8 +137,7 @@ typedef struct rt_scene_info {
     uint64_t device_bytes;           /* resident scene bytes in HBM */
     double build_seconds, flatten_seconds, upload_seconds;
     int32_t device;
-    uint32_t accel_max_depth, accel_max_leaf_size;       /* parameters the accelerated tree was built with */
-    uint64_t accel_n_nodes, accel_n_leaf_refs, accel_n_leaves, accel_tree_depth;
+    uint32_t reserved1;
     uint64_t bvh_n_nodes, bvh_n_refs, bvh_n_leaves, bvh_depth;   /* the bounding-volume hierarchy (64-byte two-child nodes) */
     uint32_t accel_width, reserved0;                             /* 2 or 4: what the accelerated mode walks */
     uint64_t bvh4_n_nodes, bvh4_stack_need;                      /* four-wide collapse: nodes, worst-case traversal stack entries */
@@ -183,11 +184,6 @@ RT_API int rt_scene_get_info(const rt_scene* s, rt_scene_info* info);
 RT_API int rt_scene_get_tree(const rt_scene* s, uint64_t* node5, float* boxes, uint32_t* refs);
 /*   nodes8 : the 8-byte device nodes (2 x u32 per node); packets: 40 x u32 per 4-triangle SoA packet          */
 RT_API int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* packets);
-/* the accelerated tree (sizes in rt_scene_info.accel_*): 8-byte nodes; tris12 = 12 x u32 per leaf reference
- * { v0.xyz, id } { e1.xyz, 0 } { e2.xyz, 0 }; root6 = min xyz, max xyz of the root box                                          */
-RT_API int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* tris12, float* root6);
-/* builds that kd-tree if it has not been built yet (it is not needed by the shipped BVH query) and fills rt_scene_info.accel_* */
-RT_API int rt_scene_build_kd_accel(rt_scene* s);
 /* the bounding-volume hierarchy (rt_scene_info.bvh_*): nodes16 = 16 x u32 per inner node
  * { c0.min.xyz, c0.max.xyz, c1.min.xyz, c1.max.xyz, ref0, ref1, cnt0, cnt1 }; tris12 as above, one record per triangle   */
 RT_API int rt_scene_get_bvh_layout(const rt_scene* s, uint32_t* nodes16, uint32_t* tris12, float* root6);

@@ -32,7 +32,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 ABI_SYMBOLS = (
     "rt_abi_version", "rt_status_string", "rt_last_error", "rt_default_build_opts", "rt_default_params",
     "rt_scene_create", "rt_scene_create_from_crtscene", "rt_scene_create_from_rtsc", "rt_scene_export_rtsc", "rt_scene_destroy",
-    "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_accel_layout", "rt_scene_build_kd_accel", "rt_scene_get_bvh_layout",
+    "rt_scene_get_info", "rt_scene_get_tree", "rt_scene_get_device_layout", "rt_scene_get_bvh_layout",
     "rt_scene_get_geometry",
     "rt_trace_closest", "rt_trace_occluded", "rt_trace_closest_device", "rt_trace_occluded_device",
     "rt_render_frame", "rt_render_frame_rgb8", "rt_render_frame_begin", "rt_render_frame_rgb8_begin", "rt_frame_wait", "rt_alloc_pinned", "rt_free_pinned", "rt_render_frame_device_begin", "rt_render_frame_device", "rt_trace_primary",
@@ -81,7 +81,7 @@ class SceneDesc(C.Structure):
 
 class BuildOpts(C.Structure):
     _fields_ = [("kd_max_depth", C.c_uint32), ("kd_max_leaf_size", C.c_uint32), ("device", C.c_int32),
-                ("accel_max_depth", C.c_uint32), ("accel_max_leaf_size", C.c_uint32), ("accel_width", C.c_uint32)]
+                ("accel_width", C.c_uint32)]
 
 
 class Params(C.Structure):
@@ -98,8 +98,7 @@ class SceneInfo(C.Structure):
                 ("n_leaf_refs", C.c_uint64), ("n_packets", C.c_uint64), ("max_leaf_refs", C.c_uint64), ("tree_depth", C.c_uint64),
                 ("device_bytes", C.c_uint64), ("build_seconds", C.c_double), ("flatten_seconds", C.c_double),
                 ("upload_seconds", C.c_double), ("device", C.c_int32),
-                ("accel_max_depth", C.c_uint32), ("accel_max_leaf_size", C.c_uint32), ("accel_n_nodes", C.c_uint64),
-                ("accel_n_leaf_refs", C.c_uint64), ("accel_n_leaves", C.c_uint64), ("accel_tree_depth", C.c_uint64),
+                ("reserved1", C.c_uint32),
                 ("bvh_n_nodes", C.c_uint64), ("bvh_n_refs", C.c_uint64), ("bvh_n_leaves", C.c_uint64), ("bvh_depth", C.c_uint64),
                 ("accel_width", C.c_uint32), ("reserved0", C.c_uint32), ("bvh4_n_nodes", C.c_uint64), ("bvh4_stack_need", C.c_uint64)]
 
@@ -136,9 +135,7 @@ def _load():
     L.rt_scene_get_tree.argtypes = [vp, vp, vp, vp]
     L.rt_scene_get_device_layout.argtypes = [vp, vp, vp]
     L.rt_scene_get_geometry.argtypes = [vp, vp, vp, vp]
-    L.rt_scene_get_accel_layout.argtypes = [vp, vp, vp, vp]
     L.rt_scene_get_bvh_layout.argtypes = [vp, vp, vp, vp]
-    L.rt_scene_build_kd_accel.argtypes = [vp]
     L.rt_trace_closest.argtypes = [vp, vp, u64, i32, f32, u32, vp]
     L.rt_trace_occluded.argtypes = [vp, vp, vp, u64, f32, f32, u32, vp]
     L.rt_trace_closest_device.argtypes = [vp, vp, u64, i32, f32, u32, vp, vp]
@@ -202,11 +199,10 @@ def default_params(**kw) -> Params:
     return p
 
 
-def build_opts(kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel=(0, 0), accel_width: int = 0) -> BuildOpts:
+def build_opts(kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel_width: int = 0) -> BuildOpts:
     o = BuildOpts()
     lib.rt_default_build_opts(C.byref(o))
     o.kd_max_depth, o.kd_max_leaf_size, o.device = kd_max_depth, kd_max_leaf_size, device
-    o.accel_max_depth, o.accel_max_leaf_size = accel
     o.accel_width = accel_width
     return o
 
@@ -223,10 +219,9 @@ class Scene:
 
     # ---- construction -------------------------------------------------------------------------------------------
     @classmethod
-    def from_rtsc(cls, data: bytes, kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel=(0, 0),
-                  accel_width: int = 0) -> "Scene":
+    def from_rtsc(cls, data: bytes, kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel_width: int = 0) -> "Scene":
         h = C.c_void_p()
-        o = build_opts(kd_max_depth, kd_max_leaf_size, device, accel, accel_width)
+        o = build_opts(kd_max_depth, kd_max_leaf_size, device, accel_width)
         buf = C.create_string_buffer(data, len(data))
         _check(lib.rt_scene_create_from_rtsc(C.cast(buf, C.c_void_p), len(data), C.byref(o), C.byref(h)))
         return cls(h.value)
@@ -330,16 +325,6 @@ class Scene:
         packets = np.zeros((self.info.n_packets, 10, 4), np.uint32)
         _check(lib.rt_scene_get_device_layout(self.h, nodes8.ctypes.data, packets.ctypes.data))
         return nodes8, packets
-
-    def accel_layout(self):
-        """nodes8 / 48-byte triangle records / root box of the backend's own tree (RT_FLAG_ORDERED)"""
-        _check(lib.rt_scene_build_kd_accel(self.h))            # built on demand; refresh the sizes
-        _check(lib.rt_scene_get_info(self.h, C.byref(self.info)))
-        nodes8 = np.zeros((self.info.accel_n_nodes, 2), np.uint32)
-        tris = np.zeros((max(self.info.accel_n_leaf_refs, 1), 12), np.uint32)
-        root = np.zeros(6, np.float32)
-        _check(lib.rt_scene_get_accel_layout(self.h, nodes8.ctypes.data, tris.ctypes.data, root.ctypes.data))
-        return nodes8, tris, root
 
     def bvh_layout(self):
         """64-byte two-child nodes / 48-byte triangle records / root box of the bounding-volume hierarchy (RT_FLAG_ORDERED)"""

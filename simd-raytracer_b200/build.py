@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "librt_b200.so")
 BUILD = os.path.join(HERE, "build")
 
 CU = [os.path.join(HERE, "csrc", "rt_api.cu")]
-CPP = [os.path.join(HERE, "host", f) for f in ("kd_build.cpp", "kd_sah.cpp", "bvh_build.cpp", "scene_io.cpp", "jpeg_decode.cpp")]
+CPP = [os.path.join(HERE, "host", f) for f in ("kd_build.cpp", "bvh_build.cpp", "scene_io.cpp", "jpeg_decode.cpp")]
 import glob  # noqa: E402
 
 DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "host", "*.hpp"))) + \

@@ -102,13 +102,9 @@ struct rt_scene {
     Geometry geom;
     KdTree tree;
     DeviceLayout layout;
-    KdTree accel_tree;               // the backend's own deeper tree (RT_FLAG_ORDERED)
-    AccelLayout accel_layout;
     BvhLayout bvh_layout;            // the bounding-volume hierarchy (RT_FLAG_ORDERED, csrc/rt_bvh.cuh)
     std::vector<uint32_t> bvh4_nodes; // its four-wide collapse (csrc/rt_bvh4.cuh, host/bvh4_collapse.hpp); empty when accel_width == 2
     bool wide = false;               // the accelerated mode walks the four-wide nodes
-    rt_build_opts accel_opts{};
-    bool accel_built = false;
     rt_scene_info info{};
 
     int device = RT_DEVICE_HOST_ONLY;
@@ -233,17 +229,9 @@ void upload_scene(rt_scene* s) {
     uint64_t bytes = 0;
     DScene& d = s->d;
     auto keep = [&](auto* p) { s->owned.push_back((void*)p); return p; };
-#if RT_ACCEL_BVH
-    d.a_nodes8 = nullptr; d.a_tris = nullptr;
     d.b_nodes = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.nodes.data(), s->bvh_layout.nodes.size() / 4, bytes)));
     d.b_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.tris.data(), s->bvh_layout.tris.size() / 4, bytes)));
     d.w_nodes = s->wide ? reinterpret_cast<const float*>(keep(upload<float4>(s->bvh4_nodes.data(), s->bvh4_nodes.size() / 4, bytes))) : nullptr;
-#else
-    d.w_nodes = nullptr;
-    d.b_nodes = nullptr; d.b_tris = nullptr;
-    d.a_nodes8 = keep(upload<uint32_t>(s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size(), bytes));
-    d.a_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->accel_layout.tris.data(), s->accel_layout.tris.size() / 4, bytes)));
-#endif
     std::memcpy(d.b_root_min, s->bvh_layout.root_min, 12);
     std::memcpy(d.b_root_max, s->bvh_layout.root_max, 12);
     d.nodes32 = keep(upload<float4>(L.nodes32.data(), L.nodes32.size() / 4, bytes));
@@ -281,31 +269,6 @@ void upload_scene(rt_scene* s) {
     s->info.upload_seconds = now_s() - t0;
 }
 
-// The SAH kd-tree of the accelerated mode's kd variant (rt_kd8.cuh).  With the BVH as the shipped structure it is only built
-// on demand (rt_scene_get_accel_layout: host-side parity tests of the kd traversal), not at scene creation.
-void build_accel_kd(rt_scene* s) {
-    if (s->accel_built) return;
-    const rt_build_opts& o = s->accel_opts;
-    const double t1 = now_s();
-    const uint64_t n = std::max<uint64_t>(s->geom.tris.size(), 1);
-    uint32_t lg = 0;
-    while ((1ull << lg) < n) ++lg;
-    // the usual kd-tree depth bound 8 + 1.3 log2(N); the surface-area heuristic stops earlier where it does not pay
-    uint32_t env_d = 0, env_l = 0;                                 // RT_B200_ACCEL="depth,leaf": tuning sweeps only
-    if (const char* e = std::getenv("RT_B200_ACCEL")) std::sscanf(e, "%u,%u", &env_d, &env_l);
-    const uint32_t ad = o.accel_max_depth ? o.accel_max_depth : env_d ? env_d : std::min<uint32_t>(30, 8 + (13 * lg + 9) / 10);
-    const uint32_t al = o.accel_max_leaf_size ? o.accel_max_leaf_size : env_l ? env_l : 2;
-    if (ad > 30) throw rt_error(RT_ERR_BAD_ARG, "accel_max_depth > 30");
-    s->accel_tree = build_kd_tree_sah(s->geom, ad, al);
-    const double t2 = now_s();
-    s->accel_layout = flatten_accel(s->geom, s->accel_tree);
-    s->info.accel_max_depth = ad; s->info.accel_max_leaf_size = al;
-    s->info.accel_n_nodes = s->accel_tree.nodes.size(); s->info.accel_n_leaf_refs = s->accel_tree.refs.size();
-    s->info.accel_n_leaves = s->accel_tree.n_leaves; s->info.accel_tree_depth = s->accel_tree.depth;
-    s->accel_built = true;
-    if (std::getenv("RT_B200_VERBOSE")) std::fprintf(stderr, "[rt_b200] kd accel build %.3f s, flatten %.3f s\n", t2 - t1, now_s() - t2);
-}
-
 int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     rt_build_opts o;
     rt_default_build_opts(&o);
@@ -318,10 +281,6 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     s->info.build_seconds = now_s() - t0;
     t0 = now_s();
     s->layout = flatten(s->host, s->geom, s->tree);
-    s->accel_opts = o;
-#if !RT_ACCEL_BVH
-    build_accel_kd(s);
-#endif
     {
         const double t3 = now_s();
         uint32_t leaf = 4;                                             // RT_B200_BVH_LEAF: tuning sweeps only
@@ -1002,7 +961,7 @@ const char* rt_last_error(void) { return g_last_error.c_str(); }
 
 void rt_default_build_opts(rt_build_opts* o) {
     if (!o) return;
-    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_max_depth = 0; o->accel_max_leaf_size = 0; o->accel_width = 0;
+    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_width = 0;
 }
 
 void rt_default_params(rt_params* p) {
@@ -1064,25 +1023,6 @@ int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* pa
     if (nodes8) std::memcpy(nodes8, s->layout.nodes8.data(), s->layout.nodes8.size() * 4);
     if (packets) std::memcpy(packets, s->layout.packets.data(), size_t(s->layout.n_packets) * PACKET_WORDS * 4);
     return RT_OK;
-}
-
-int rt_scene_get_accel_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* tris12, float* root6) {
-    if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
-    const int st = rt_scene_build_kd_accel(const_cast<rt_scene*>(s));
-    if (st != RT_OK) return st;
-    if (nodes8) std::memcpy(nodes8, s->accel_layout.nodes8.data(), s->accel_layout.nodes8.size() * 4);
-    if (tris12) std::memcpy(tris12, s->accel_layout.tris.data(), size_t(s->accel_layout.n_refs) * 12 * 4);
-    if (root6) { std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12); }
-    return RT_OK;
-}
-
-int rt_scene_build_kd_accel(rt_scene* s) {
-    return guarded([&] {
-        if (!s) throw rt_error(RT_ERR_BAD_ARG, "null scene");
-        std::lock_guard<std::mutex> lock(s->mtx);
-        build_accel_kd(s);
-        return int(RT_OK);
-    });
 }
 
 int rt_scene_get_bvh_layout(const rt_scene* s, uint32_t* nodes16, uint32_t* tris12, float* root6) {

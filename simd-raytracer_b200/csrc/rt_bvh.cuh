@@ -1,8 +1,8 @@
 // csrc/rt_bvh.cuh - the accelerated closest-hit query over the backend's bounding-volume hierarchy (host/bvh_build.cpp),
 // one ray per thread, near child first.  SURVEY.md section 8 row f4.
 //
-// Same contract as the kd-tree traversal in rt_kd8.cuh, whose triangle test (kd_test_tri - the reference's own
-// arithmetic, kd_tree_simd.hpp:25-60) it shares: t/u/v of the winner are the reference's bits; the minimum is taken over
+// The contract (rt_tri.cuh, whose triangle test kd_test_tri - the reference's own arithmetic, kd_tree_simd.hpp:25-60 - it
+// uses): t/u/v of the winner are the reference's bits; the minimum is taken over
 // every triangle whose box the ray touches; an exact-t tie between two different triangles is only recorded
 // (KdHit::tie_t == t) and the caller re-runs those rays in reference order.  Box tests are conservative: both ends of a
 // slab interval are widened by a relative slack far above the rounding of the slab arithmetic, a NaN (0 * inf) never
@@ -15,7 +15,7 @@
 // Compiles as CUDA device code and as plain C++ (tests/helpers/kd8_host.cpp runs this very source on the CPU).
 #pragma once
 
-#include "rt_kd8.cuh"
+#include "rt_tri.cuh"
 
 #ifndef BVH_COUNT_NODE
 #define BVH_COUNT_NODE() ((void)0)

@@ -34,9 +34,7 @@ struct DTexture { uint32_t kind; float c0[3], c1[3], scalar; uint32_t w, h, off;
 struct DLight { float pos[3], intensity; };                                                              // 16 B
 
 struct DScene {
-    const uint32_t* __restrict__ a_nodes8;  // accelerated mode, kd variant: 8-byte nodes of the backend's own SAH kd-tree (rt_kd8.cuh)
-    const float* __restrict__ a_tris;       //                   and its 48-byte leaf triangle records
-    const float* __restrict__ b_nodes;      // accelerated mode, BVH variant (default): 64-byte two-child nodes (rt_bvh.cuh)
+    const float* __restrict__ b_nodes;      // accelerated mode: 64-byte two-child nodes of the bounding-volume hierarchy (rt_bvh.cuh)
     const float* __restrict__ b_tris;       //                   and its 48-byte triangle records (one per triangle)
     const float* __restrict__ w_nodes;      // accelerated mode, four-wide variant (rt_bvh4.cuh): 128-byte nodes over the same records; null = two-wide
     const float4* __restrict__ nodes32;     // 2 x float4 per node: box + the same two words (reference-order traversal)
@@ -80,12 +78,8 @@ __device__ __forceinline__ float max_std(float a, float b) { return (a < b) ? b 
 struct Hit { float t, u, v; int tri; };
 
 // ---- the structure behind the accelerated query mode -----------------------------------------------------------------------
-// RT_ACCEL_BVH = 1 (default): the bounding-volume hierarchy (rt_bvh.cuh); 0: the SAH kd-tree (rt_kd8.cuh), kept as a
-// compile-time alternative for A/B measurements.  Both give the same hits (same triangle arithmetic, same tie rule).
-#ifndef RT_ACCEL_BVH
-#define RT_ACCEL_BVH 1
-#endif
-#if RT_ACCEL_BVH
+// The backend's own bounding-volume hierarchy (host/bvh_build.cpp), two-wide (rt_bvh.cuh) or four-wide (rt_bvh4.cuh); both give
+// the same hits (same triangle arithmetic, same tie rule).
 using AccelState = BvhState;
 using AccelStackEntry = BvhStackEntry;
 constexpr int ACCEL_STACK = BVH_STACK;
@@ -106,25 +100,6 @@ __device__ __forceinline__ KdHit accel_trace(const DScene& sc, float ox, float o
     if (sc.w_nodes) return bvh4_trace<CULL, FAST>(sc.w_nodes, sc.b_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
     return bvh_trace<CULL, FAST>(sc.b_nodes, sc.b_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
 }
-#else
-using AccelState = Kd8State;
-using AccelStackEntry = KdStackEntry;
-constexpr int ACCEL_STACK = KD8_STACK;
-__device__ __forceinline__ bool accel_init(AccelState& st, const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
-                                           float t_far, bool any_hit) {
-    return kd8_init(st, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, t_far, any_hit);
-}
-__device__ __forceinline__ void accel_node_step(AccelState& st, AccelStackEntry* stack, const DScene& sc) { kd8_node_step(st, stack, sc.a_nodes8); }
-template <bool CULL, bool FAST>
-__device__ __forceinline__ void accel_leaf_step(AccelState& st, const AccelStackEntry* stack, const DScene& sc, float eps) {
-    kd8_leaf_step<CULL, FAST>(st, stack, sc.a_nodes8, sc.a_tris, eps);
-}
-template <bool CULL, bool FAST>
-__device__ __forceinline__ KdHit accel_trace(const DScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
-                                             float t_far, bool any_hit) {
-    return kd8_trace<CULL, FAST>(sc.a_nodes8, sc.a_tris, sc.root_min, sc.root_max, ox, oy, oz, dx, dy, dz, eps, t_far, any_hit);
-}
-#endif
 
 // ---- ray vs. 4-triangle SoA packet --------------------------------------------------------------------------------
 // triangle_packet<F,W>::intersect (kd_tree_simd.hpp:25-60), one lane, in the reference's operation order, folded
@@ -351,7 +326,7 @@ __device__ __forceinline__ Hit trace_warp(const DScene& sc, bool active, V3 o, V
 // ---- one entry point for the kernels -----------------------------------------------------------------------------------
 // ACCEL == false: the reference's tree in the reference's order (bit-exact by construction, statistics included).
 //                 any_hit lets a lane stop once closest.t <= t_far is decided; t_far is otherwise ignored.
-// ACCEL == true : rt_kd8.cuh - the backend's own deeper tree, front-to-back, one ray per thread; nodes beyond t_far are
+// ACCEL == true : rt_bvh.cuh / rt_bvh4.cuh - the backend's own hierarchy, near child first, one ray per thread; nodes beyond t_far are
 //                 not visited at all (a hit beyond t_far and a miss mean the same to every caller that passes t_far).
 //                 Must be called by all 32 lanes (tie re-runs use the warp-cooperative query).
 template <bool CULL, bool FAST, bool ACCEL>

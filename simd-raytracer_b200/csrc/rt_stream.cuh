@@ -1,5 +1,5 @@
 // csrc/rt_stream.cuh - the trace kernels of the accelerated mode (RT_FLAG_ORDERED): persistent warps that keep every lane
-// busy.  A lane owns one query at a time (rt_kd8.cuh state machine); when it finishes - early for an occluded shadow ray,
+// busy.  A lane owns one query at a time (the BvhState machine of rt_bvh.cuh); when it finishes - early for an occluded shadow ray,
 // at once for a camera ray that misses the scene box - it takes the next query from the level's device-side counter
 // instead of idling until the slowest ray of a 32-ray chunk is done.  Bursts of traversal steps alternate with a
 // warp-uniform completion phase, which is where exact-t ties are re-run in reference order (trace_warp) and where the

@@ -241,45 +241,4 @@ DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t) {
     return d;
 }
 
-AccelLayout flatten_accel(const Geometry& g, const KdTree& t) {
-    AccelLayout d;
-    auto bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
-    const uint64_t n_nodes = t.nodes.size();
-    d.nodes8.resize(2 * n_nodes);
-    d.n_refs = t.refs.size();
-    if (d.n_refs >= (1ull << 32)) throw rt_error(RT_ERR_UNSUPPORTED, "too many leaf references");
-    d.tris.assign(12 * (d.n_refs ? d.n_refs : 1), 0u);
-    for (uint64_t i = 0; i < n_nodes; ++i) {
-        const KdNode& n = t.nodes[i];
-        if (n.first_ref == KD_NONE) {
-            if (n.child0 != KD_NONE && n.child0 != i + 1) throw rt_error(RT_ERR_BAD_ARG, "kd-tree is not in DFS pre-order");
-            if (n.child1 != KD_NONE && n.child1 >= (1ull << 28)) throw rt_error(RT_ERR_UNSUPPORTED, "kd-tree has too many nodes");
-        } else if (n.ref_count >= (1ull << 30)) throw rt_error(RT_ERR_UNSUPPORTED, "leaf too large");
-    }
-    parallel_for(n_nodes, 1 << 16, [&](uint64_t nb, uint64_t ne) {
-    for (uint64_t i = nb; i < ne; ++i) {
-        const KdNode& n = t.nodes[i];
-        if (n.first_ref == KD_NONE) {
-            d.nodes8[2 * i] = bits(n.split);
-            d.nodes8[2 * i + 1] = (n.axis & 3u) | (n.child0 != KD_NONE ? 4u : 0u) | (n.child1 != KD_NONE ? 8u : 0u) |
-                                  (n.child1 != KD_NONE ? uint32_t(n.child1) << 4 : 0u);
-        } else {
-            d.nodes8[2 * i] = uint32_t(n.first_ref);
-            d.nodes8[2 * i + 1] = 3u | (uint32_t(n.ref_count) << 2);
-        }
-    }
-    });
-    parallel_for(d.n_refs, 1 << 16, [&](uint64_t rb, uint64_t re) {
-    for (uint64_t r = rb; r < re; ++r) {
-        const uint32_t id = t.refs[r];
-        const TriGeom& tg = g.tris[id];
-        uint32_t* p = d.tris.data() + 12 * r;
-        p[0] = bits(tg.v0[0]); p[1] = bits(tg.v0[1]); p[2] = bits(tg.v0[2]); p[3] = id;
-        p[4] = bits(tg.e1[0]); p[5] = bits(tg.e1[1]); p[6] = bits(tg.e1[2]);
-        p[8] = bits(tg.e2[0]); p[9] = bits(tg.e2[1]); p[10] = bits(tg.e2[2]);
-    }
-    });
-    return d;
-}
-
 }  // namespace rtb

@@ -45,8 +45,6 @@ struct KdTree {
 
 Geometry prepare_geometry(const HostScene& s);
 KdTree build_kd_tree(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size);
-// the backend's own tree for the accelerated mode: binned SAH with triangle clipping (kd_sah.cpp); same output structure
-KdTree build_kd_tree_sah(const Geometry& g, uint32_t max_depth, uint32_t max_leaf_size);
 
 // ---- device layout -------------------------------------------------------------------------------------------
 //
@@ -79,15 +77,6 @@ struct DeviceLayout {
 
 DeviceLayout flatten(const HostScene& s, const Geometry& g, const KdTree& t);
 DeviceLayout flatten_tree_only(const Geometry& g, const KdTree& t);   // nodes8 / nodes32 / packets only
-
-// layout of the accelerated tree (csrc/rt_kd8.cuh): 8-byte nodes whose leaves index an array of 48-byte triangle records
-//   nodes8 leaf: { u32 first_ref, u32 3 | count << 2 }      tris: { v0.xyz, id } { e1.xyz, 0 } { e2.xyz, 0 } per leaf reference
-struct AccelLayout {
-    std::vector<uint32_t> nodes8;
-    std::vector<uint32_t> tris;        // 12 words per leaf reference
-    uint64_t n_refs = 0;
-};
-AccelLayout flatten_accel(const Geometry& g, const KdTree& t);
 
 // the bounding-volume hierarchy of the accelerated mode (bvh_build.cpp, csrc/rt_bvh.cuh): same KdTree container (node boxes
 // are the tight bounds, `axis`/`split` record the SAH decision), flattened to 64-byte two-child nodes

@@ -1,7 +1,7 @@
-// host/kd_parallel.hpp - task-parallel driver shared by the two top-down kd-tree builders.
+// host/kd_parallel.hpp - task-parallel driver shared by the top-down builders.
 //
-// Both builders (kd_build.cpp: the reference's median tree, kd_tree_simd.hpp:146-185; kd_sah.cpp: the backend's own SAH
-// tree) decide a node's split from the node's own triangle list only, so subtrees are independent and the tree is a pure
+// Both builders (kd_build.cpp: the reference's median kd-tree, kd_tree_simd.hpp:146-185; bvh_build.cpp: the backend's own
+// bounding-volume hierarchy) decide a node's split from the node's own triangle list only, so subtrees are independent and the tree is a pure
 // function of the input.  The driver exploits that without changing a single node:
 //
 //   1. the top of the tree is expanded by recursive tasks (child1 on a new thread, child0 inline) until a subtree holds

@@ -1,13 +1,12 @@
-// tests/helpers/kd8_host.cpp - TEST INFRASTRUCTURE: compiles simd-raytracer_b200/csrc/rt_bvh.cuh and rt_kd8.cuh (the accelerated traversals the
-// CUDA kernels run) as plain C++ so that tests/test_kd8_host.py can check the algorithm and the flattened tree against the
+// tests/helpers/kd8_host.cpp - TEST INFRASTRUCTURE: compiles simd-raytracer_b200/csrc/rt_bvh.cuh, rt_bvh4.cuh and rt_tri.cuh (the accelerated
+// traversals the CUDA kernels run and their triangle test) as plain C++ so that tests/test_kd8_host.py can check the algorithm and the flattened tree against the
 // oracle on a machine without a GPU.  Built with -ffp-contract=off (the device TU is built with -fmad=false).
 #include <cstdint>
-static uint64_t g_kd8_nodes, g_kd8_tris, g_bvh_leaves;   // visit counters (rt_kd8.cuh / rt_bvh.cuh instrumentation hooks)
-#define KD8_COUNT_NODE() (++g_kd8_nodes)
+static uint64_t g_kd8_nodes, g_kd8_tris, g_bvh_leaves;   // visit counters (rt_tri.cuh / rt_bvh.cuh instrumentation hooks)
 #define KD8_COUNT_TRI() (++g_kd8_tris)
 #define BVH_COUNT_NODE() (++g_kd8_nodes)
 #define BVH_COUNT_LEAF() (++g_bvh_leaves)
-#include "../../simd-raytracer_b200/csrc/rt_bvh.cuh"          // includes rt_kd8.cuh
+#include "../../simd-raytracer_b200/csrc/rt_bvh.cuh"          // includes rt_tri.cuh
 
 extern "C" void kd8_counters(uint64_t* nodes, uint64_t* tris, int reset) {
     if (nodes) *nodes = g_kd8_nodes;
@@ -20,23 +19,7 @@ extern "C" uint64_t bvh_leaf_visits(int reset) {
     return v;
 }
 
-extern "C" void kd8_trace_batch(const uint32_t* nodes8, const float* tris, const float* root6, const float* rays6, uint64_t n,
-                                int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie) {
-    for (uint64_t i = 0; i < n; ++i) {
-        const float* q = rays6 + 6 * i;
-        const float far = t_far ? t_far[i] : FLT_MAX;
-        rtb::KdHit h;
-        if (cull) h = fast ? rtb::kd8_trace<true, true>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
-                           : rtb::kd8_trace<true, false>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
-        else h = fast ? rtb::kd8_trace<false, true>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
-                      : rtb::kd8_trace<false, false>(nodes8, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
-        tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
-        tri[i] = h.tri;
-        if (tie) tie[i] = (h.tri == rtb::KD_RERUN || (h.tri >= 0 && h.tie_t == h.t)) ? 1 : 0;     // the device re-runs these through the reference-order query
-    }
-}
-
-// the same batch through the bounding-volume hierarchy (rt_scene_get_bvh_layout)
+// a batch of queries through the two-wide bounding-volume hierarchy (rt_scene_get_bvh_layout)
 extern "C" void bvh_trace_batch(const float* nodes16, const float* tris, const float* root6, const float* rays6, uint64_t n,
                                 int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie) {
     for (uint64_t i = 0; i < n; ++i) {
@@ -90,6 +73,11 @@ static const std::vector<uint32_t>& bvh4_of(const float* nodes16, uint64_t n_nod
     return it->second;
 }
 extern "C" uint64_t bvh4_node_count(const float* nodes16, uint64_t n_nodes2) { return bvh4_of(nodes16, n_nodes2).size() / 32; }
+// worst-case traversal stack entries of the collapsed hierarchy (what scene creation checks against BVH4_STACK), and that bound
+extern "C" uint64_t bvh4_stack_need_host(const float* nodes16, uint64_t n_nodes2, uint64_t* capacity) {
+    if (capacity) *capacity = uint64_t(rtb::BVH4_STACK);
+    return rtb::bvh4_stack_need(rtb::bvh4_collapse(reinterpret_cast<const uint32_t*>(nodes16), n_nodes2));
+}
 extern "C" void bvh4_trace_batch(const float* nodes16, uint64_t n_nodes2, const float* tris, const float* root6, const float* rays6, uint64_t n,
                                  int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie,
                                  uint32_t* node_visits) {

@@ -303,7 +303,7 @@ def test_parallel_builder_is_thread_invariant(rt, oracle_mod, kd, monkeypatch):
         n5, bx, rf = s.tree()
         assert np.array_equal(n5, on5) and np.array_equal(bx.view(np.uint32), obx.view(np.uint32)) and np.array_equal(rf, orf)
         assert (s.info.n_leaves, s.info.max_leaf_refs, s.info.tree_depth) == (o.n_leaves, o.max_leaf_refs, o.tree_depth)
-        layouts.append([np.ascontiguousarray(a).tobytes() for a in s.device_layout() + s.accel_layout()] +
-                       [(s.info.accel_n_nodes, s.info.accel_n_leaves, s.info.accel_n_leaf_refs, s.info.accel_tree_depth)])
+        layouts.append([np.ascontiguousarray(a).tobytes() for a in s.device_layout() + s.bvh_layout()] +
+                       [(s.info.bvh_n_nodes, s.info.bvh_n_leaves, s.info.bvh_n_refs, s.info.bvh_depth, s.info.bvh4_n_nodes, s.info.bvh4_stack_need)])
         s.close()
     assert layouts[0] == layouts[1] == layouts[2]

@@ -1,7 +1,7 @@
-"""The accelerated traversals (RT_FLAG_ORDERED) checked on the CPU: the bounding-volume hierarchy the kernels ship with
-(simd-raytracer_b200/csrc/rt_bvh.cuh) and its kd-tree alternative (rt_kd8.cuh).  The same source the CUDA kernels compile is
-built as plain C++ (tests/helpers/kd8_host.cpp) and run over the product's flattened structures (rt_scene_get_bvh_layout /
-rt_scene_get_accel_layout, host-only scene) against the oracle's reference-order traversal.  No product compute runs here."""
+"""The accelerated traversals (RT_FLAG_ORDERED) checked on the CPU: the two-wide bounding-volume hierarchy
+(simd-raytracer_b200/csrc/rt_bvh.cuh) and its four-wide collapse (rt_bvh4.cuh, host/bvh4_collapse.hpp).  The same source the CUDA
+kernels compile is built as plain C++ (tests/helpers/kd8_host.cpp) and run over the product's flattened structures
+(rt_scene_get_bvh_layout, host-only scene) against the oracle's reference-order traversal.  No product compute runs here."""
 from __future__ import annotations
 
 import ctypes as C
@@ -15,22 +15,22 @@ from .conftest import REPO, SCENES, resized, scene_bytes
 from .helpers import crtscene
 
 
-@pytest.fixture(scope="module", params=["bvh", "kd", "bvh4"])
+@pytest.fixture(scope="module", params=["bvh", "bvh4"])
 def kd8(tmp_path_factory, request):
     structure = request.param
     out = tmp_path_factory.mktemp("kd8") / "libkd8_host.so"
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
                            os.path.join(REPO, "tests", "helpers", "kd8_host.cpp"), "-o", str(out)])
     lib = C.CDLL(str(out))
-    for fn in (lib.kd8_trace_batch, lib.bvh_trace_batch):
+    for fn in (lib.bvh_trace_batch,):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bvh4_trace_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    batch = lib.bvh_trace_batch if structure == "bvh" else lib.kd8_trace_batch
+    batch = lib.bvh_trace_batch
 
     def trace(scene, rays, cull, fast=False, t_far=None, any_hit=False, eps=np.float32(1e-6)):
-        nodes8, packets, root = scene.bvh_layout() if structure in ("bvh", "bvh4") else scene.accel_layout()
+        nodes8, packets, root = scene.bvh_layout()
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         tuv = np.zeros((len(rays), 3), np.float32)
         tri = np.zeros(len(rays), np.int32)
@@ -91,10 +91,10 @@ def test_kd8_equals_reference_traversal(rt, oracle_mod, kd8, name):
         assert np.array_equal(tuv[h & ~tie].view(np.uint32), want_tuv[h & ~tie].view(np.uint32))
 
 
-@pytest.mark.parametrize("kd,accel", [((8, 64), (0, 0)), ((24, 64), (0, 0)), ((8, 64), (20, 2)), ((8, 64), (6, 128))])
-def test_kd8_synthetic_mesh(rt, oracle_mod, kd8, kd, accel):
+@pytest.mark.parametrize("kd", [(8, 64), (24, 64)])
+def test_kd8_synthetic_mesh(rt, oracle_mod, kd8, kd):
     data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=20_000, seed=9, width=160, height=120))
-    s = rt.Scene.from_rtsc(data, kd_max_depth=kd[0], kd_max_leaf_size=kd[1], device=rt.DEVICE_HOST_ONLY, accel=accel)
+    s = rt.Scene.from_rtsc(data, kd_max_depth=kd[0], kd_max_leaf_size=kd[1], device=rt.DEVICE_HOST_ONLY)
     o = oracle_mod.Oracle(data, *kd)
     for rays, cull in ((o.primary_rays(), True), (scene_rays(o, s, 60_000), False)):
         want_tuv, want_tri = o.trace(rays, cull)
@@ -255,3 +255,49 @@ def test_tile_culling_predicate_is_conservative_and_effective(tmp_path):
                 wrong += int(says_miss and hit.any())
     assert wrong == 0
     assert culled >= 0.8 * empty, (culled, empty)            # sub-pixel margin: nearly every empty tile is culled
+
+
+def test_bvh4_stack_bound_on_a_degenerate_chain(tmp_path):
+    """the four-wide traversal's stack must be PROVEN deep enough.  A two-wide hierarchy that is one long chain
+    (every node = one leaf + the rest of the chain, 44 levels - the builder's depth cap) is the worst shape for the collapse:
+    host/bvh4_collapse.hpp computes the stack entries any ray can need, that number must stay within BVH4_STACK (3 * 44 + 4), and
+    the four-wide traversal must answer rays through all 45 nested boxes exactly as the two-wide one does."""
+    out = tmp_path / "libkd8_host.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                           os.path.join(REPO, "tests", "helpers", "kd8_host.cpp"), "-o", str(out)])
+    lib = C.CDLL(str(out))
+    lib.bvh4_stack_need_host.restype = C.c_uint64
+    lib.bvh4_stack_need_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    depth = 44
+    nodes = np.zeros((depth, 16), np.uint32)
+    tris = np.zeros((depth + 1, 12), np.float32)
+    f = nodes.view(np.float32)
+    for i in range(depth + 1):                        # triangle i: a small quad half in the plane z = i, all inside the nested boxes
+        tris[i, 0:3] = (-0.4, -0.4, float(i)); tris[i, 4:7] = (0.8, 0.0, 0.0); tris[i, 8:11] = (0.0, 0.8, 0.0)
+        tris[i].view(np.uint32)[3] = i
+    for i in range(depth):
+        f[i, 0:6] = (-0.5, -0.5, i - 0.01, 0.5, 0.5, i + 0.01)                       # child 0: the leaf with triangle i
+        f[i, 6:12] = (-0.5, -0.5, i + 0.99, 0.5, 0.5, depth + 0.01)                  # child 1: the rest of the chain
+        nodes[i, 12:16] = (i, i + 1, 1, 0) if i + 1 < depth else (i, depth, 1, 1)    # ref0, ref1, cnt0, cnt1
+    cap = C.c_uint64(0)
+    need = lib.bvh4_stack_need_host(nodes.ctypes.data, depth, C.byref(cap))
+    assert 3 <= need <= cap.value == 3 * 44 + 4
+    lib.bvh_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
+                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bvh4_trace_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rays = np.zeros((64, 6), np.float32)
+    rng = np.random.default_rng(1)
+    rays[:, 0:2] = rng.uniform(-0.45, 0.45, (64, 2)); rays[:, 2] = depth + 1.0
+    rays[:, 3:5] = rng.uniform(-0.01, 0.01, (64, 2)); rays[:, 5] = -1.0                # down through all 45 planes: the LAST one is the farthest
+    rays[:32, 2] = -1.0; rays[:32, 5] = 1.0                                          # and up: triangle 0 first
+    root = np.array([-0.5, -0.5, -0.01, 0.5, 0.5, depth + 0.01], np.float32)
+    res = []
+    for wide in (False, True):
+        tuv, tri, tie = np.zeros((64, 3), np.float32), np.zeros(64, np.int32), np.zeros(64, np.uint8)
+        args = [nodes.ctypes.data] + ([depth] if wide else []) + [tris.ctypes.data, root.ctypes.data, rays.ctypes.data, 64, 0, 0,
+                C.c_float(1e-6), None, 0, tuv.ctypes.data, tri.ctypes.data, tie.ctypes.data] + ([None] if wide else [])
+        (lib.bvh4_trace_batch if wide else lib.bvh_trace_batch)(*args)
+        res.append((tuv.copy(), tri.copy()))
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))
+    assert (res[0][1] >= 0).sum() >= 16 and len(set(res[0][1].tolist())) >= 8          # rays end on many different links of the chain
