@@ -46,8 +46,11 @@ for kind, m, cu, far, ah in (("primary", cull, 1, None, 0), ("secondary", (~cull
                          C.c_void_p(r.ctypes.data), C.c_uint64(n), cu, 0, C.c_float(1e-6), None if f is None else C.c_void_p(f.ctypes.data), ah,
                          C.c_void_p(tuv.ctypes.data), C.c_void_p(tri.ctypes.data), None, C.c_void_p(nv4.ctypes.data))
     a, b = C.c_uint64(0), C.c_uint64(0); lib.kd8_counters(C.byref(a), C.byref(b), 1)
-    w4 = nv4.astype(np.int64); q4 = np.percentile(w4, [50, 90, 99, 99.9, 100])
+    w4 = (nv4 & 0xFFFF).astype(np.int64); q4 = np.percentile(w4, [50, 90, 99, 99.9, 100])
+    sp4 = (nv4 >> 16).astype(np.int64)          # deepest traversal stack of the query (entries)
     print(f"  {'':9s} four-wide : node visits mean {w4.mean():6.1f} p50 {q4[0]:.0f} p90 {q4[1]:.0f} p99 {q4[2]:.0f} p99.9 {q4[3]:.0f} max {q4[4]:.0f}; tri tests mean {b.value/max(n,1):5.1f}")
+    print(f"  {'':9s} four-wide stack depth: mean {sp4.mean():.2f} p99 {np.percentile(sp4, 99):.0f} p99.9 {np.percentile(sp4, 99.9):.0f} max {sp4.max()}; queries deeper than 8 / 12 / 16 entries: "
+          f"{100 * (sp4 > 8).mean():.4f} % / {100 * (sp4 > 12).mean():.4f} % / {100 * (sp4 > 16).mean():.4f} %")
     for width in (8, 16):      # statistics only: how many dependent node visits would wider nodes need?
         nvw = np.zeros(n, np.uint32)
         lib.bvh_wide_visit_counts(C.c_void_p(nodes.ctypes.data), C.c_uint64(int(s.info.bvh_n_nodes)), width, C.c_void_p(tris.ctypes.data), C.c_void_p(root.ctypes.data),

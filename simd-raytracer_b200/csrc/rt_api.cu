@@ -248,6 +248,9 @@ void upload_scene(rt_scene* s) {
     d.texels = keep(upload<uint8_t>(H.texels.data(), H.texels.size(), bytes));
     d.n_lights = uint32_t(H.lights.size());
     d.n_nodes = uint32_t(s->tree.nodes.size());
+    uint32_t start_rows = STREAM4_STACK_START;                       // RT_B200_STACK_ROWS: tests force the overflow path with it
+    if (const char* e = std::getenv("RT_B200_STACK_ROWS")) std::sscanf(e, "%u", &start_rows);
+    d.w_stack_rows = s->wide ? uint32_t(std::min<uint64_t>(s->info.bvh4_stack_need + 1, std::max(start_rows, 1u))) : 0u;
     d.width = H.width; d.height = H.height;
     std::memcpy(d.bg, H.background, 12);
     std::memcpy(d.cam_pos, H.camera_position, 12);
@@ -347,8 +350,8 @@ int grid_for(rt_scene* s, K kernel, int threads = 256, size_t dyn_smem = 0) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
     return s->n_sm * std::max(per_sm, 1);
 }
-// the four-wide stream kernels keep every lane's traversal stack in shared memory: worst case of the scene's hierarchy + 1 rows
-size_t wide_stack_bytes(const rt_scene* s) { return s->wide ? (size_t(s->info.bvh4_stack_need) + 1) * StreamCfg<4>::THREADS * sizeof(uint2) : 0; }
+// the four-wide stream kernels keep every lane's traversal stack in shared memory: d.w_stack_rows entries per lane (rt_stream.cuh)
+size_t wide_stack_bytes(const rt_scene* s) { return s->wide ? size_t(s->d.w_stack_rows) * StreamCfg<4>::THREADS * sizeof(uint2) : 0; }
 
 #define DISPATCH_MODE(m, CALL)                                      \
     do {                                                            \
@@ -412,6 +415,7 @@ __global__ void k_pass_commit(PassState* ps, FrameCounters* fc, uint32_t* out, u
     fc->primary += ps->pc.primary; fc->primary_hits += ps->pc.primary_hits;
     fc->shadow += ps->pc.shadow; fc->shadow_hits += ps->pc.shadow_hits;
     fc->secondary += ps->pc.secondary; fc->secondary_hits += ps->pc.secondary_hits;
+    fc->stack_overflows += ps->pc.stack_overflows;
 }
 
 struct Rect { uint32_t x0, y0, x1, y1; };
@@ -674,11 +678,26 @@ void grow_pools_after_overflow(rt_scene* s, const uint32_t* flags, uint64_t n0) 
 
 void drain_sequence(rt_scene* s);
 
+// Queries that outgrew the shared-memory stack of the four-wide stream kernels were answered by the reference-order traversal:
+// exact, but slow.  More than one in 2^14 of a frame's queries: the next frame gets twice the rows (up to the hierarchy's worst
+// case, where no query can overflow).  The grids are sized again, because the rows are the kernels' dynamic shared memory.
+void adapt_stack_rows(rt_scene* s, const FrameCounters& c) {
+    if (!s->wide || !c.stack_overflows) return;
+    const uint64_t queries = c.primary + c.shadow + c.secondary, worst = s->info.bvh4_stack_need + 1;
+    if (c.stack_overflows * 16384ull <= queries || s->d.w_stack_rows >= worst) return;
+    s->d.w_stack_rows = uint32_t(std::min<uint64_t>(worst, uint64_t(s->d.w_stack_rows) * 2));
+    for (int* g : {s->gs_primary, s->gs_sparse, s->gs_level}) g[0] = g[1] = 0;
+    for (int& g : s->gs_shadow) g = 0;
+    if (std::getenv("RT_B200_VERBOSE")) std::fprintf(stderr, "[rt_b200] %llu of %llu queries outgrew the shared stack: %u rows from now on\n",
+                                                     (unsigned long long)c.stack_overflows, (unsigned long long)queries, s->d.w_stack_rows);
+}
+
 // counters of the last synchronously rendered frame: waits for it, reads the per-class CUDA events
 void fetch_counters(rt_scene* s) {
     if (!s->counters_pending) return;
     CK(cudaSetDevice(s->device));
     CK(cudaEventSynchronize(s->frame_c));      // not a device-wide sync: a frame download may be in flight on the copy stream
+    adapt_stack_rows(s, *s->h_fc);
     rt_counters k{};
     k.primary = s->h_fc->primary; k.primary_hits = s->h_fc->primary_hits;
     k.shadow = s->h_fc->shadow; k.shadow_hits = s->h_fc->shadow_hits;
@@ -837,6 +856,7 @@ void finalize_slot(rt_scene* s, int k) {
         q.rerendered = true;
         return;
     }
+    adapt_stack_rows(s, *q.h_fc);
     s->pool_hwm = pool_hwm; s->shadow_hwm = shadow_hwm;
     if (std::memcmp(&q.key, &s->hint_params, sizeof q.key) == 0 && (s->levels_hint == 0 || levels_used > s->levels_hint))
         s->levels_hint = std::max<uint32_t>(levels_used, 1);

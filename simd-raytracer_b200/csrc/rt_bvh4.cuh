@@ -15,13 +15,17 @@
 //   SAME 48-byte records as the two-wide tree); child == ~0u: no child
 //
 // Traversal stack: 8-byte entries { entry distance, child }.  The stack is a template parameter - put(pos, t0, child) /
-// get(pos, t0, child) - because its home differs: shared memory with a local-memory tail in the stream kernels
+// put_if / get(pos, t0, child) / overflows(entries) - because its home differs: shared memory with a local-memory tail in the stream kernels
 // (rt_stream.cuh StreamStack4), a plain array in the one-ray-per-thread query below and on the CPU.
 //
 // Compiles as CUDA device code and as plain C++ (tests/helpers/kd8_host.cpp runs this very source on the CPU).
 #pragma once
 
 #include "rt_bvh.cuh"
+
+#ifndef BVH4_TRACK_SP
+#define BVH4_TRACK_SP(sp) ((void)0)     // instrumentation hook for host-side experiments: stack entries after a visit
+#endif
 
 #if !RT_BVH_FMA_SLAB || !RT_BVH_POP_CULL
 #error "rt_bvh4.cuh is written against the fused slab test (RT_BVH_FMA_SLAB=1) and the pop-time cull (RT_BVH_POP_CULL>=1) of rt_bvh.cuh"
@@ -44,6 +48,7 @@ struct Bvh4ArrayStack {
     struct Entry { float t0; uint32_t child; } e[BVH4_STACK];
     RT_HD void put(int pos, float t0, uint32_t child) { e[pos].t0 = t0; e[pos].child = child; }
     RT_HD void put_if(bool on, int pos, float t0, uint32_t child) { if (on) put(pos, t0, child); }
+    RT_HD bool overflows(int) const { return false; }          // BVH4_STACK entries cover every tree the builder can produce
     RT_HD void get(int pos, float& t0, uint32_t& child) const { t0 = e[pos].t0; child = e[pos].child; }
 };
 
@@ -101,6 +106,10 @@ RT_HD void bvh4_node_step(BvhState& s, Stack& stack, const float* __restrict__ n
             const int r2 = (2 - n20 - n21) + n32;
             const int r3 = 3 - n30 - n31 - n32;
             const int top = s.sp + touched - 1;                             // rank r >= 1 goes to top - r: rank 1 is popped first
+            // a stack with fewer entries than the tree's worst case (the shared-memory stack of the stream kernels, sized for
+            // what rays really need): a query that would outgrow it is not continued with a subtree missing - it ends here with
+            // the KD_OVERFLOW mark and is answered by the reference-order traversal, like a query with an exact-t tie
+            if (stack.overflows(top)) { s.best.tri = KD_OVERFLOW; s.phase = KD8_DONE; return; }
             // exactly one touched child has rank 0 (an untouched one ranks behind every touched one): it becomes the current node;
             // the others store themselves, no branch between them
             stack.put_if(h0 & (r0 != 0), top - r0, t0, c0);
@@ -109,6 +118,7 @@ RT_HD void bvh4_node_step(BvhState& s, Stack& stack, const float* __restrict__ n
             stack.put_if(h3 & (r3 != 0), top - r3, t3, c3);
             const uint32_t cur = (r0 == 0) ? c0 : (r1 == 0) ? c1 : (r2 == 0) ? c2 : c3;
             s.sp = top;
+            BVH4_TRACK_SP(top);
             s.ref = cur >> 3; s.cnt = cur & 7u;
             s.phase = s.cnt ? KD8_LEAF : KD8_WALK;
         }

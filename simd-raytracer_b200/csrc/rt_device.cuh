@@ -48,6 +48,7 @@ struct DScene {
     const DLight* __restrict__ lights;
     const uint8_t* __restrict__ texels;
     uint32_t n_lights, n_nodes;
+    uint32_t w_stack_rows;                  // four-wide stream kernels: stack entries per lane in shared memory (rt_stream.cuh)
     uint32_t width, height;
     float bg[3];
     float cam_pos[3];

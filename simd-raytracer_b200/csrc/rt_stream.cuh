@@ -39,6 +39,12 @@ namespace rtb {
 #ifndef RT_STREAM4_MIN_BLOCKS
 #define RT_STREAM4_MIN_BLOCKS 5
 #endif
+#ifndef RT_STREAM4_STACK_START
+#define RT_STREAM4_STACK_START 16
+#endif
+// four-wide traversal: stack entries per lane a scene starts with (fewer when the hierarchy's worst case is smaller; doubled by
+// the host while queries overflow, see StreamStack<4>)
+constexpr uint32_t STREAM4_STACK_START = RT_STREAM4_STACK_START;
 // threads per block and resident blocks per SM of the stream kernels, by hierarchy width (registers per thread follow from them:
 // two-wide 256 x 3 = 80 registers; four-wide 128 x 5 = 96 registers - its node step holds seven rows of a node at once)
 template <int WIDE> struct StreamCfg { static constexpr int THREADS = RT_STREAM_THREADS, MIN_BLOCKS = RT_STREAM_MIN_BLOCKS; };
@@ -75,23 +81,28 @@ __device__ __noinline__ void exact_rerun(const DScene& sc, bool active, float ox
 // ---- the traversal stack of a lane, by hierarchy width -------------------------------------------------------------------------
 // Two-wide (rt_bvh.cuh): 16-byte entries in thread-local memory, as in round 1.
 // Four-wide (rt_bvh4.cuh): 8-byte entries in SHARED memory, one column per thread (consecutive lanes are consecutive 8-byte
-// words, so a warp's access is two conflict-free wavefronts whatever the lanes' depths); no stack traffic reaches L1, which the
-// node fetches need, and a push is one predicated STS.64 with no branch around it.  The block's dynamic shared memory holds
-// bvh4_stack_need + 1 rows - the worst case of the scene's hierarchy, computed when it is collapsed (host/bvh4_collapse.hpp:
-// 24-35 entries on the tested scenes, 24-35 KB per 128-thread block), so there is no overflow path.
+// words, so a warp's access is two conflict-free wavefronts whatever the lanes' depths): no stack traffic reaches L1, which the
+// node fetches need, and the pushes of a visit are predicated STS.64 with no branch between them.  The block's dynamic shared
+// memory holds `rows` entries per lane.  The worst case of a hierarchy (host/bvh4_collapse.hpp) is 24-43 entries on the tested
+// scenes, but every KB of shared memory is a KB less L1 for the node and triangle fetches and no recorded query of configs 1-4
+// goes deeper than 14 (scripts/bvh_ray_lengths_cpu.py), so a scene starts with min(worst case, STREAM4_STACK_START) rows.  A
+// query that would need more ends with the KD_OVERFLOW mark (rt_bvh4.cuh), is answered exactly by the reference-order traversal
+// in the completion phase - and is counted: when more than one query in 2^14 of a frame overflowed, the host doubles the rows
+// for the next frame, up to the worst case, where overflow is impossible (rays through the dense random mesh of config 5 go
+// deep: that scene renders its second frame with the full stack).  Measured against a thread-local tail for the deep entries
+// (one branch per visit): 0.386 vs 0.400 ms on config 2, 3.40 vs 3.52 on config 3, 29.1 vs 30.3 on config 5 at 1 M triangles.
 template <int WIDE> struct StreamStack;
 template <> struct StreamStack<2> {
     AccelStackEntry e[ACCEL_STACK];
-    __device__ __forceinline__ void bind() {}
+    __device__ __forceinline__ void bind(uint32_t) {}
 };
 extern __shared__ uint2 stream_shared_stack[];
 template <> struct StreamStack<4> {
     static constexpr uint32_t ROW = uint32_t(StreamCfg<4>::THREADS) * 8u;
     uint32_t col;                                // shared-memory address of this thread's column
-    __device__ __forceinline__ void bind() { col = uint32_t(__cvta_generic_to_shared(stream_shared_stack + threadIdx.x)); }
-    __device__ __forceinline__ void put(int pos, float t0, uint32_t child) {
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(col + uint32_t(pos) * ROW), "r"(__float_as_uint(t0)), "r"(child) : "memory");
-    }
+    int rows;                                    // entries per lane
+    __device__ __forceinline__ void bind(uint32_t n_rows) { col = uint32_t(__cvta_generic_to_shared(stream_shared_stack + threadIdx.x)); rows = int(n_rows); }
+    __device__ __forceinline__ bool overflows(int entries) const { return entries > rows; }
     __device__ __forceinline__ void put_if(bool on, int pos, float t0, uint32_t child) {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
                      :: "r"(col + uint32_t(pos) * ROW), "r"(__float_as_uint(t0)), "r"(child), "r"(uint32_t(on)) : "memory");
@@ -118,16 +129,17 @@ __device__ __forceinline__ void stream_leaf_step(AccelState& st, StreamStack<WID
 //   void entered(uint32_t idx, V3 o, V3 d)                                                  the query touches the scene box and will be traced
 //   bool finish(const DScene&, uint32_t idx, const Hit& h, AccelState& st)                  true: lane re-armed (st re-initialised)
 template <bool CULL, bool FAST, int WIDE, class Policy>
-__device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps) {
+__device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_t* __restrict__ counter, uint32_t end, float eps,
+                                            unsigned long long* __restrict__ overflow_count) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     AccelState st;
     StreamStack<WIDE> stack;
-    stack.bind();
+    stack.bind(sc.w_stack_rows);
     st.sp = 0; st.phase = KD8_DONE; st.any_hit = false; st.best.tri = -1; st.best.t = FLT_MAX; st.best.tie_t = -1.0f; st.t_far = FLT_MAX;
     st.ox = st.oy = st.oz = st.dx = st.dy = st.dz = 0.0f;
     bool busy = false, exhausted = false;
-    uint32_t idx = 0;
+    uint32_t idx = 0, n_overflow = 0;
 #ifdef RT_STREAM_STATS
     unsigned long long stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const unsigned long long log_t0 = stream_now_ns();
@@ -200,13 +212,15 @@ __device__ __forceinline__ void stream_loop(const DScene& sc, Policy& p, uint32_
         STREAM_STAT(8, 1);
         const bool fin = busy && st.phase == KD8_DONE;
         Hit h; h.t = st.best.t; h.u = st.best.u; h.v = st.best.v; h.tri = st.best.tri;
-        const bool tie = fin && (st.best.tri == KD_RERUN || (!st.any_hit && st.best.tri >= 0 && st.best.tie_t == st.best.t));
+        const bool tie = fin && (st.best.tri == KD_RERUN || st.best.tri == KD_OVERFLOW || (!st.any_hit && st.best.tri >= 0 && st.best.tie_t == st.best.t));
+        n_overflow += (fin && st.best.tri == KD_OVERFLOW);
         if (__ballot_sync(FULL, tie)) {
             // two different triangles at exactly the winner's t: the reference's leaf order decides, so ask it
             exact_rerun<CULL, FAST>(sc, tie, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, eps, &h);
         }
         if (fin) busy = p.finish(sc, idx, h, st);
     }
+    if (n_overflow) atomicAdd(overflow_count, (unsigned long long)n_overflow);      // rare: queries that outgrew the shared stack
 #ifdef RT_STREAM_STATS
     for (int o = 16; o; o >>= 1) log_taken += __shfl_xor_sync(FULL, log_taken, o);
     if (lane == 0) {
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN
     pdl_wait();
     if (ps->skipped) return;
     PrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits;
-    stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps);                // render.hpp:64, culling ON
+    stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], fp.plane * fp.n_samples, fp.eps, &ps->pc.stack_overflows);                // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 
@@ -379,7 +393,7 @@ __global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN
     SparsePrimaryPolicy p; p.fp = &fp; p.rays = rays; p.hits = hits; p.mask0 = mask0; p.fb = fb; p.tile_list = tile_list;
     p.per_sample = tile_list ? ps->n_tiles0 * 32u : fp.plane;
     p.miss_rgb = first_pass_miss_colour(sc, fp, divide);
-    stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], p.per_sample * fp.n_samples, fp.eps);             // render.hpp:64, culling ON
+    stream_loop<true, FAST, WIDE>(sc, p, &ps->work[work_slot], p.per_sample * fp.n_samples, fp.eps, &ps->pc.stack_overflows);             // render.hpp:64, culling ON
     warp_sum_to(&ps->pc.primary, &ps->pc.primary_hits, p.n_rays, p.n_hits);
 }
 
@@ -410,7 +424,7 @@ __global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN
     const uint32_t end = min(ps->pool_count, fp.pool_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) ps->lv[level + 1] = end;
     LevelPolicy p; p.rays = rays; p.hits = hits; p.begin = begin;
-    stream_loop<false, FAST, WIDE>(sc, p, &ps->work[work_slot], end - begin, fp.eps);
+    stream_loop<false, FAST, WIDE>(sc, p, &ps->work[work_slot], end - begin, fp.eps, &ps->pc.stack_overflows);
     warp_sum_to(&ps->pc.secondary, &ps->pc.secondary_hits, p.n_rays, p.n_hits);
 }
 
@@ -469,7 +483,7 @@ __global__ void __launch_bounds__(StreamCfg<WIDE>::THREADS, StreamCfg<WIDE>::MIN
     const uint32_t end = min(ps->shadow_count, fp.shadow_cap);
     ShadowPolicy<TRANSMISSIVE> p; p.jobs = jobs; p.shadow_bias = fp.shadow_bias;
     p.n_lights = sc.n_lights; p.n_jobs = end;
-    stream_loop<false, FAST, WIDE>(sc, p, &ps->work[work_slot], end, fp.eps);
+    stream_loop<false, FAST, WIDE>(sc, p, &ps->work[work_slot], end, fp.eps, &ps->pc.stack_overflows);
     warp_sum_to(&ps->pc.shadow, &ps->pc.shadow_hits, p.n_q, p.n_h);
 }
 

@@ -33,6 +33,8 @@ namespace rtb {
 struct KdHit { float t, u, v; int tri; float tie_t; };   // tie_t == t: another triangle has exactly the winner's t
 // tri == KD_RERUN: the query has to be answered by the reference-order traversal (see bvh_init)
 constexpr int KD_RERUN = -3;
+// tri == KD_OVERFLOW: the same, because the query outgrew its traversal stack (rt_bvh4.cuh); counted, so that the host can react
+constexpr int KD_OVERFLOW = -4;
 
 RT_HD float kd_bits_to_float(uint32_t u) {
 #if defined(__CUDA_ARCH__)

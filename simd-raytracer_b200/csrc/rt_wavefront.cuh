@@ -46,6 +46,7 @@ struct FrameParams {
 
 struct FrameCounters {                  // device memory, reset at the start of every frame
     unsigned long long primary, primary_hits, shadow, shadow_hits, secondary, secondary_hits;
+    unsigned long long stack_overflows; // queries of the four-wide stream kernels that outgrew the shared-memory stack (rt_stream.cuh)
 };
 
 struct PassState {                      // device memory, reset at the start of every pass (k_pass_init)

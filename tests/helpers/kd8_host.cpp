@@ -64,6 +64,8 @@ extern "C" int tile_misses_box_host(const float* m9, const float* pos3, float wi
 // ---- four-wide hierarchy (csrc/rt_bvh4.cuh), collapsed on the fly from the two-wide nodes the scene exports ----------------
 #include <map>
 #include <vector>
+static int g_bvh4_max_sp;               // deepest stack of the current query (rt_bvh4.cuh instrumentation hook)
+#define BVH4_TRACK_SP(sp) (g_bvh4_max_sp = (sp) > g_bvh4_max_sp ? (sp) : g_bvh4_max_sp)
 #include "../../simd-raytracer_b200/csrc/rt_bvh4.cuh"
 #include "../../simd-raytracer_b200/host/bvh4_collapse.hpp"
 static const std::vector<uint32_t>& bvh4_of(const float* nodes16, uint64_t n_nodes2) {
@@ -88,6 +90,7 @@ extern "C" void bvh4_trace_batch(const float* nodes16, uint64_t n_nodes2, const 
         const float* q = rays6 + 6 * i;
         const float far = t_far ? t_far[i] : FLT_MAX;
         const uint64_t n0 = g_kd8_nodes;
+        g_bvh4_max_sp = 0;
         rtb::KdHit h;
         if (cull) h = fast ? rtb::bvh4_trace<true, true>(nodes4, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0)
                            : rtb::bvh4_trace<true, false>(nodes4, tris, root6, root6 + 3, q[0], q[1], q[2], q[3], q[4], q[5], eps, far, any_hit != 0);
@@ -96,7 +99,7 @@ extern "C" void bvh4_trace_batch(const float* nodes16, uint64_t n_nodes2, const 
         tuv[3 * i] = h.tri >= 0 ? h.t : 0; tuv[3 * i + 1] = h.tri >= 0 ? h.u : 0; tuv[3 * i + 2] = h.tri >= 0 ? h.v : 0;
         tri[i] = h.tri;
         if (tie) tie[i] = (h.tri == rtb::KD_RERUN || (h.tri >= 0 && h.tie_t == h.t)) ? 1 : 0;
-        if (node_visits) node_visits[i] = uint32_t(g_kd8_nodes - n0);
+        if (node_visits) node_visits[i] = uint32_t(g_kd8_nodes - n0) | (uint32_t(g_bvh4_max_sp) << 16);     // low half: node visits, high half: deepest stack
     }
 }
 

@@ -371,6 +371,46 @@ def test_multi_pass_frames_queue_without_a_host_round_trip_per_pass(rt, tmp_path
             assert tuple(p[2:5]) == (c.primary, c.shadow, c.secondary) and tuple(p[5:8]) == (c.primary, c.shadow, c.secondary)
 
 
+_OVERFLOW_CHILD = r"""
+import importlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+rt = importlib.import_module("simd-raytracer_b200")
+from tests.conftest import resized, scene_bytes
+out = {}
+for name, size, kw in (("hw15_scene2", (200, 120), dict(samples_per_pixel=3, diffuse_reflection_ray_count=2, max_ray_depth=4)),
+                       ("hw11_scene8", (240, 136), dict(max_ray_depth=8)), ("hw09_scene5", (240, 136), dict())):
+    s = rt.Scene.from_rtsc(resized(scene_bytes(name), *size))
+    for k in range(4):                                  # the host doubles the rows between frames while queries overflow
+        out[f"{name}_{k}"] = s.render_frame(rt.default_params(flags=rt.FLAG_ORDERED, **kw))
+        c = s.counters()
+        out[f"{name}_{k}_counts"] = np.array([c.primary, c.primary_hits, c.shadow, c.secondary])
+    s.close()
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_queries_that_outgrow_the_shared_stack_are_answered_exactly(rt, tmp_path):
+    """The four-wide stream kernels keep a few traversal-stack entries per lane in shared memory; a query that needs more ends
+    with the KD_OVERFLOW mark and is answered by the reference-order traversal, and the host doubles the rows for the next frame
+    while more than one query in 2^14 overflows (csrc/rt_stream.cuh).  A child process that starts every scene with TWO rows
+    (RT_B200_STACK_ROWS) overflows on most queries of its first frames: every frame, from the first (2 rows) to the fourth (16),
+    must be the frame of this process bit for bit, with the same ray counts."""
+    import subprocess, sys
+    from .conftest import REPO
+    out = tmp_path / "overflow.npz"
+    subprocess.run([sys.executable, "-c", _OVERFLOW_CHILD, REPO, str(out)], check=True, env=dict(os.environ, RT_B200_STACK_ROWS="2"), timeout=600)
+    z = np.load(out)
+    for name, size, kw in (("hw15_scene2", (200, 120), dict(samples_per_pixel=3, diffuse_reflection_ray_count=2, max_ray_depth=4)),
+                           ("hw11_scene8", (240, 136), dict(max_ray_depth=8)), ("hw09_scene5", (240, 136), dict())):
+        s, _ = gpu_scene(rt, name, size=size)
+        want = s.render_frame(rt.default_params(flags=rt.FLAG_ORDERED, **kw))
+        c = s.counters()
+        for k in range(4):
+            assert np.array_equal(want.view(np.uint32), z[f"{name}_{k}"].view(np.uint32)), (name, k)
+            assert tuple(z[f"{name}_{k}_counts"]) == (c.primary, c.primary_hits, c.shadow, c.secondary)
+
+
 def test_tile_culling_is_conservative(rt):
     """k_tile_cull finishes 8x4 pixel tiles whose camera rays cannot reach the scene's root box.  A small constant-colour
     quad seen by rotated / sheared cameras from many positions (box in a corner of the frame, partly off-screen, behind the
@@ -521,6 +561,31 @@ def test_config5_shape_synthetic_gi_frame(rt, oracle_mod, width):
     for flags in (0, rt.FLAG_ORDERED):
         img = s.render_frame(rt.default_params(flags=flags))
         assert np.array_equal(img[crop].view(np.uint32), oi0[crop].view(np.uint32))
+    s.close()
+
+
+def test_config5_at_full_scale_crops_equal_the_oracle(rt, oracle_mod):
+    """BASELINE.json configs[4] at the size bench.py times it: 10,000,000 triangles, 3840x2160, kd<24,64>.  Crops of the 4K frame
+    - the centre of the mesh, a corner of the box - must equal the oracle bit for bit in the deterministic configuration (1 spp,
+    no GI) in both query modes, and to the GI tolerance (same Philox rays, cos/sin last bits) with GI 1."""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=10_000_000, seed=1234, width=3840, height=2160))
+    s = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64)
+    o = oracle_mod.Oracle(data, 24, 64)
+    assert s.info.n_triangles == o.n_tris == 10_000_010 and s.info.n_nodes == o.n_nodes
+    img = np.zeros((2160, 3840, 3), np.float32)
+    for rect in ((1888, 1048, 1952, 1112), (40, 30, 104, 62)):
+        crop = (slice(rect[1], rect[3]), slice(rect[0], rect[2]))
+        want, oc = o.render(oracle_mod.default_params(), rect=rect)
+        for flags in (rt.FLAG_ORDERED, 0):
+            s.render_frame(rt.default_params(x0=rect[0], y0=rect[1], x1=rect[2], y1=rect[3], flags=flags), out=img)
+            c = s.counters()
+            assert np.array_equal(img[crop].view(np.uint32), want[crop].view(np.uint32)), (rect, flags)
+            assert (c.primary, c.primary_hits, c.shadow + c.secondary) == (int(oc[0]), int(oc[1]), int(oc[2] + oc[4]))
+        gi, _ = o.render(oracle_mod.default_params(spp=2, gi_rays=1, max_ray_depth=5), rect=rect)
+        s.render_frame(rt.default_params(x0=rect[0], y0=rect[1], x1=rect[2], y1=rect[3], samples_per_pixel=2, diffuse_reflection_ray_count=1,
+                                         max_ray_depth=5, flags=rt.FLAG_ORDERED), out=img)
+        assert (quantise(img[crop]) == quantise(gi[crop])).all(axis=2).mean() >= 0.99
+        assert psnr8(img[crop], gi[crop]) >= 45.0
     s.close()
 
 
