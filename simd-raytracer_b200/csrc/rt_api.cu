@@ -289,7 +289,9 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         uint32_t leaf = 4;                                             // RT_B200_BVH_LEAF: tuning sweeps only
         if (const char* e = std::getenv("RT_B200_BVH_LEAF")) std::sscanf(e, "%u", &leaf);
         KdTree bvh = build_bvh(s->geom, leaf);
+        const double t4 = now_s();
         s->bvh_layout = flatten_bvh(s->geom, bvh);
+        if (std::getenv("RT_B200_VERBOSE")) std::fprintf(stderr, "[rt_b200] bvh build %.3f s, flatten %.3f s\n", t4 - t3, now_s() - t4);
         s->info.bvh_n_nodes = s->bvh_layout.n_nodes; s->info.bvh_n_refs = s->bvh_layout.n_refs;
         s->info.bvh_n_leaves = bvh.n_leaves; s->info.bvh_depth = bvh.depth;
         // the four-wide form of the same hierarchy (rt_build_opts.accel_width; RT_B200_ACCEL_WIDTH overrides the default for sweeps)
@@ -1483,7 +1485,7 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
         } else {
             for (uint32_t r = 0; r < g->world; ++r) src.p[r] = reinterpret_cast<const float*>(g->peer[r] + g->last_slot());
         }
-        const int unroll = gather ? 2 : (g->world <= 2 ? 8 : g->world <= 4 ? 4 : g->world <= 8 ? 2 : 1);
+        const int unroll = gather ? 8 : (g->world <= 2 ? 8 : g->world <= 4 ? 4 : g->world <= 8 ? 2 : 1);
         const uint64_t want = (g1 - g0 + uint64_t(256) * unroll - 1) / (uint64_t(256) * unroll);
         const int blocks = int(std::max<uint64_t>(1, std::min<uint64_t>(want, max_blocks)));
         uint8_t* root = g->peer[0] + g->last_slot();
