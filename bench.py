@@ -253,7 +253,8 @@ def north_star_scaling(rt, args, rank: int, world: int, local: int, flags: int):
     T = int(args.ns_spp)
     t0 = time.perf_counter()
     data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=args.ns_tris, seed=cfg["seed"], width=cfg["width"], height=cfg["height"]))
-    scene = rt.Scene.from_rtsc(data, kd_max_depth=cfg["kd"][0], kd_max_leaf_size=cfg["kd"][1], device=local, accel_width=args.accel_width)
+    scene = rt.Scene.from_rtsc(data, kd_max_depth=cfg["kd"][0], kd_max_leaf_size=cfg["kd"][1], device=local, accel_width=args.accel_width,
+                               accel_build=rt.ACCEL_BUILD_DEVICE if args.accel_build == "device" else rt.ACCEL_BUILD_HOST)
     del data
     t_build = time.perf_counter() - t0
     H, W = scene.height, scene.width
@@ -376,6 +377,8 @@ def main() -> None:
     ap.add_argument("--tris", type=int, default=None, help="triangle count of the synthetic workload (cfg5; default 10,000,000)")
     ap.add_argument("--spp", type=int, default=None, help="samples per pixel per GPU and step (default: the workload's own)")
     ap.add_argument("--accel-width", type=int, default=0, choices=[0, 2, 4], help="hierarchy width of the ordered modes (0 = default)")
+    ap.add_argument("--accel-build", default="host", choices=["host", "device"],
+                    help="where the backend's hierarchy is built: binned SAH on the host threads, or a linear BVH by CUDA kernels (csrc/rt_lbvh.cuh)")
     ap.add_argument("--ns-tris", type=int, default=1_000_000, help="north_star_scaling: triangles of the config-5 scene (0 = skip)")
     ap.add_argument("--ns-spp", type=int, default=64, help="north_star_scaling: total samples per pixel of the 4K GI frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -403,7 +406,8 @@ def main() -> None:
     rt = importlib.import_module("simd-raytracer_b200")
     kd = w.get("kd", [8, 64])
     t_build = time.perf_counter()
-    scene = rt.Scene.from_rtsc(w["rtsc"], kd_max_depth=kd[0], kd_max_leaf_size=kd[1], device=local, accel_width=args.accel_width)
+    scene = rt.Scene.from_rtsc(w["rtsc"], kd_max_depth=kd[0], kd_max_leaf_size=kd[1], device=local, accel_width=args.accel_width,
+                               accel_build=rt.ACCEL_BUILD_DEVICE if args.accel_build == "device" else rt.ACCEL_BUILD_HOST)
     t_build = time.perf_counter() - t_build
     H, W = scene.height, scene.width
     flags = MODES[args.mode]
@@ -757,7 +761,8 @@ def main() -> None:
         accel = args.mode.endswith("ordered")
         # the structure the timed trace kernels walk: the reference's own kd<depth,leaf> tree in reference order (exact / fast), or
         # the backend's bounding-volume hierarchy, two- or four-wide (ordered modes; rt_build_opts.accel_width)
-        accel_name = f"bvh{int(scene.info.accel_width)}" if accel else f"reference kd<{kd[0]},{kd[1]}>"
+        built_on_device = int(scene.info.accel_build) == rt.ACCEL_BUILD_DEVICE
+        accel_name = f"{'lbvh' if built_on_device else 'bvh'}{int(scene.info.accel_width)}" if accel else f"reference kd<{kd[0]},{kd[1]}>"
         class_kernels = ({"primary": ["k_tile_cull", "k_stream_primary_sparse", "k_stream_primary"], "secondary": ["k_stream_level"],
                           "shadow": ["k_stream_shadow"]} if accel else
                          {"primary": ["k_primary"], "secondary": ["k_trace_level"], "shadow": ["k_shadow"]})
@@ -892,7 +897,10 @@ def main() -> None:
             "north_star_scaling": ns,
             "scene": {"triangles": int(scene.info.n_triangles), "kd_nodes": int(scene.info.n_nodes), "packets": int(scene.info.n_packets),
                       "bvh_nodes": int(scene.info.bvh_n_nodes), "bvh_depth": int(scene.info.bvh_depth),
-                      "device_bytes": int(scene.info.device_bytes), "host_build_s": round(t_build, 3)},
+                      "device_bytes": int(scene.info.device_bytes), "host_build_s": round(t_build, 3),
+                      "accel_build": "device" if int(scene.info.accel_build) == rt.ACCEL_BUILD_DEVICE else "host",
+                      "accel_build_s": round(float(scene.info.accel_build_seconds), 4),
+                      "kd_build_s": round(float(scene.info.build_seconds), 3), "bvh4_stack_need": int(scene.info.bvh4_stack_need)},
         }
         if world == 1 and not args.no_cpu_baseline:
             if w.get("synthetic"):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RT_API __attribute__((visibility("default")))
@@ -93,8 +93,17 @@ typedef struct rt_build_opts {
      * four-wide collapse, 128-byte nodes (csrc/rt_bvh4.cuh; the reference author's own TODO, README.md:118-124); 0 = the default
      * (RT_DEFAULT_ACCEL_WIDTH).  Frames, hits and ray counts do not depend on it. */
     uint32_t accel_width;
+    /* where the backend's own hierarchy is built: RT_ACCEL_BUILD_HOST (0, the default) = binned SAH on the host threads
+     * (host/bvh_build.cpp; seconds at 10 M triangles, the cheapest tree to walk); RT_ACCEL_BUILD_DEVICE (1) = a linear BVH built by
+     * CUDA kernels (csrc/rt_lbvh.cuh; tens of milliseconds at 10 M triangles, more node visits per ray), concurrently with the host
+     * build of the reference's kd-tree.  Needs a device and more than 16 triangles; a scene whose linear hierarchy comes out
+     * deeper than the traversal stacks allow is built on the host instead (rt_scene_info.accel_build tells which ran).  Frames,
+     * hits and ray counts do not depend on it. */
+    uint32_t accel_build;
 } rt_build_opts;
 #define RT_DEFAULT_ACCEL_WIDTH 4
+#define RT_ACCEL_BUILD_HOST   0u
+#define RT_ACCEL_BUILD_DEVICE 1u
 #define RT_DEVICE_HOST_ONLY (-1)
 
 /* config.hpp:6-17 as run-time parameters, plus the tile / sample slice used for multi-GPU sharding. */
@@ -139,8 +148,9 @@ typedef struct rt_scene_info {
     int32_t device;
     uint32_t reserved1;
     uint64_t bvh_n_nodes, bvh_n_refs, bvh_n_leaves, bvh_depth;   /* the bounding-volume hierarchy (64-byte two-child nodes) */
-    uint32_t accel_width, reserved0;                             /* 2 or 4: what the accelerated mode walks */
+    uint32_t accel_width, accel_build;                           /* 2 or 4: what the accelerated mode walks; RT_ACCEL_BUILD_* that built it */
     uint64_t bvh4_n_nodes, bvh4_stack_need;                      /* four-wide collapse: nodes, worst-case traversal stack entries */
+    double accel_build_seconds;                                  /* the backend's hierarchy alone: build + flatten + collapse (device build: + its uploads) */
 } rt_scene_info;
 
 typedef struct rt_counters {         /* of the last rt_render_frame* call */

@@ -81,7 +81,7 @@ class SceneDesc(C.Structure):
 
 class BuildOpts(C.Structure):
     _fields_ = [("kd_max_depth", C.c_uint32), ("kd_max_leaf_size", C.c_uint32), ("device", C.c_int32),
-                ("accel_width", C.c_uint32)]
+                ("accel_width", C.c_uint32), ("accel_build", C.c_uint32)]
 
 
 class Params(C.Structure):
@@ -100,7 +100,8 @@ class SceneInfo(C.Structure):
                 ("upload_seconds", C.c_double), ("device", C.c_int32),
                 ("reserved1", C.c_uint32),
                 ("bvh_n_nodes", C.c_uint64), ("bvh_n_refs", C.c_uint64), ("bvh_n_leaves", C.c_uint64), ("bvh_depth", C.c_uint64),
-                ("accel_width", C.c_uint32), ("reserved0", C.c_uint32), ("bvh4_n_nodes", C.c_uint64), ("bvh4_stack_need", C.c_uint64)]
+                ("accel_width", C.c_uint32), ("accel_build", C.c_uint32), ("bvh4_n_nodes", C.c_uint64), ("bvh4_stack_need", C.c_uint64),
+                ("accel_build_seconds", C.c_double)]
 
 
 class Counters(C.Structure):
@@ -199,11 +200,15 @@ def default_params(**kw) -> Params:
     return p
 
 
-def build_opts(kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel_width: int = 0) -> BuildOpts:
+ACCEL_BUILD_HOST, ACCEL_BUILD_DEVICE = 0, 1
+
+
+def build_opts(kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel_width: int = 0,
+               accel_build: int = ACCEL_BUILD_HOST) -> BuildOpts:
     o = BuildOpts()
     lib.rt_default_build_opts(C.byref(o))
     o.kd_max_depth, o.kd_max_leaf_size, o.device = kd_max_depth, kd_max_leaf_size, device
-    o.accel_width = accel_width
+    o.accel_width, o.accel_build = accel_width, accel_build
     return o
 
 
@@ -219,9 +224,10 @@ class Scene:
 
     # ---- construction -------------------------------------------------------------------------------------------
     @classmethod
-    def from_rtsc(cls, data: bytes, kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel_width: int = 0) -> "Scene":
+    def from_rtsc(cls, data: bytes, kd_max_depth: int = 8, kd_max_leaf_size: int = 64, device: int = 0, accel_width: int = 0,
+                  accel_build: int = ACCEL_BUILD_HOST) -> "Scene":
         h = C.c_void_p()
-        o = build_opts(kd_max_depth, kd_max_leaf_size, device, accel_width)
+        o = build_opts(kd_max_depth, kd_max_leaf_size, device, accel_width, accel_build)
         buf = C.create_string_buffer(data, len(data))
         _check(lib.rt_scene_create_from_rtsc(C.cast(buf, C.c_void_p), len(data), C.byref(o), C.byref(h)))
         return cls(h.value)

@@ -28,6 +28,12 @@
 #include "../host/bvh4_collapse.hpp"
 #include "rt_stream.cuh"
 #include "rt_peer.cuh"
+#include "rt_lbvh.cuh"
+#include "../host/kd_parallel.hpp"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thread>
 
 using namespace rtb;
 
@@ -104,6 +110,15 @@ struct rt_scene {
     DeviceLayout layout;
     BvhLayout bvh_layout;            // the bounding-volume hierarchy (RT_FLAG_ORDERED, csrc/rt_bvh.cuh)
     std::vector<uint32_t> bvh4_nodes; // its four-wide collapse (csrc/rt_bvh4.cuh, host/bvh4_collapse.hpp); empty when accel_width == 2
+    // the same structures built ON THE DEVICE (rt_build_opts.accel_build = 1, csrc/rt_lbvh.cuh): device arrays, owned by the scene
+    struct DeviceBvh {
+        uint32_t *nodes16 = nullptr, *tris12 = nullptr, *nodes32 = nullptr;
+        uint64_t n_nodes2 = 0, n_nodes4 = 0, n_tris = 0, bytes = 0;
+        uint32_t stack_need = 0, depth2 = 0;
+        float root_min[3] = {0, 0, 0}, root_max[3] = {0, 0, 0};
+        double seconds = 0;
+        bool built = false;
+    } dev_bvh;
     bool wide = false;               // the accelerated mode walks the four-wide nodes
     rt_scene_info info{};
 
@@ -208,8 +223,8 @@ void require_device(const rt_scene* s) {
     if (s->device < 0) throw rt_error(RT_ERR_NO_DEVICE, "scene was built host-only (RT_DEVICE_HOST_ONLY): no device to compute on");
 }
 
-void upload_scene(rt_scene* s) {
-    const double t0 = now_s();
+// the device the scene is to live on exists and is an sm_100 part; makes it current for the calling thread
+void select_device(rt_scene* s) {
     int count = 0;
     const cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -222,6 +237,130 @@ void upload_scene(rt_scene* s) {
     if (prop.major != 10) throw rt_error(RT_ERR_NO_DEVICE, std::string("device is not an sm_100 part: ") + prop.name);
     s->n_sm = prop.multiProcessorCount;
     CK(cudaSetDevice(s->device));
+}
+
+// ---- the backend's hierarchy built on the device (csrc/rt_lbvh.cuh) -----------------------------------------------------------
+// Runs on its own host thread beside the host build of the reference's kd-tree (finish_create); temporaries are freed before it
+// returns, the three result arrays stay with the scene.  Throws RT_ERR_UNSUPPORTED when the tree comes out deeper than the
+// traversal stacks allow (degenerate inputs: thousands of coincident triangles) - the caller then builds on the host.
+struct DevTmp {
+    std::vector<void*> p;
+    template <class T> T* get(size_t n) { void* q = nullptr; CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T))); p.push_back(q); return static_cast<T*>(q); }
+    ~DevTmp() { for (void* q : p) cudaFree(q); }
+};
+
+void device_build_bvh(rt_scene* s, bool wide) {
+    const double t0 = now_s();
+    select_device(s);
+    const auto& tris = s->geom.tris;
+    const uint64_t n64 = tris.size();
+    if (n64 <= 4 * LBVH_LEAF || n64 >= (1ull << 29)) throw rt_error(RT_ERR_UNSUPPORTED, "device build: triangle count outside (16, 2^29)");
+    const uint32_t n = uint32_t(n64), n_inner = n - 1;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    DevTmp tmp;
+    rt_scene::DeviceBvh out;
+    auto fail_free = [&] { for (uint32_t* q : {out.nodes16, out.tris12, out.nodes32}) if (q) cudaFree(q); };
+    try {
+        // v0, e1, e2 of every triangle: the only geometry the builder (and every triangle test) reads
+        std::vector<float> tri9(size_t(n) * 9);
+        parallel_for(n, 1 << 16, [&](uint64_t b, uint64_t e) {
+            for (uint64_t i = b; i < e; ++i) { std::memcpy(&tri9[9 * i], tris[i].v0, 12); std::memcpy(&tri9[9 * i + 3], tris[i].e1, 12); std::memcpy(&tri9[9 * i + 6], tris[i].e2, 12); }
+        });
+        float* d_tri9 = tmp.get<float>(size_t(n) * 9);
+        CK(cudaMemcpyAsync(d_tri9, tri9.data(), size_t(n) * 36, cudaMemcpyHostToDevice, st));
+        float root6[6];
+        std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12);
+        float* d_root = tmp.get<float>(6);
+        CK(cudaMemcpyAsync(d_root, root6, 24, cudaMemcpyHostToDevice, st));
+        uint64_t *keys = tmp.get<uint64_t>(n), *keys_alt = tmp.get<uint64_t>(n);
+        uint32_t *ids = tmp.get<uint32_t>(n), *ids_alt = tmp.get<uint32_t>(n);
+        const unsigned B = 256, G = (n + B - 1) / B;
+        k_lbvh_morton<<<G, B, 0, st>>>(d_tri9, n, d_root, keys, ids);
+        CK(cudaGetLastError());
+        cub::DoubleBuffer<uint64_t> kb(keys, keys_alt);
+        cub::DoubleBuffer<uint32_t> vb(ids, ids_alt);
+        size_t sort_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb, vb, int(n), 0, 63, st));
+        void* sort_tmp = tmp.get<uint8_t>(sort_bytes);
+        CK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, kb, vb, int(n), 0, 63, st));
+        const uint64_t* skeys = kb.Current();
+        const uint32_t* sids = vb.Current();
+        uint32_t *left = tmp.get<uint32_t>(n), *right = tmp.get<uint32_t>(n), *first = tmp.get<uint32_t>(n), *last = tmp.get<uint32_t>(n);
+        uint32_t *parent_inner = tmp.get<uint32_t>(n), *parent_leaf = tmp.get<uint32_t>(n), *arrived = tmp.get<uint32_t>(n);
+        LbvhBox *leaf_box = tmp.get<LbvhBox>(n), *inner_box = tmp.get<LbvhBox>(n);
+        k_lbvh_tree<<<G, B, 0, st>>>(skeys, int(n), left, right, first, last, parent_inner, parent_leaf);
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(arrived, 0, size_t(n) * 4, st));
+        k_lbvh_boxes<<<G, B, 0, st>>>(d_tri9, sids, int(n), left, right, parent_inner, parent_leaf, leaf_box, inner_box, arrived);
+        CK(cudaGetLastError());
+        uint32_t *kept = tmp.get<uint32_t>(n), *dense = tmp.get<uint32_t>(n);
+        k_lbvh_mark<<<G, B, 0, st>>>(first, last, int(n_inner), kept);
+        CK(cudaGetLastError());
+        size_t scan_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, kept, dense, int(n_inner), st));
+        void* scan_tmp = tmp.get<uint8_t>(scan_bytes);
+        CK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, kept, dense, int(n_inner), st));
+        uint32_t tail[2] = {0, 0};
+        CK(cudaMemcpyAsync(&tail[0], dense + (n_inner - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&tail[1], kept + (n_inner - 1), 4, cudaMemcpyDeviceToHost, st));
+        LbvhBox root_box;
+        CK(cudaMemcpyAsync(&root_box, inner_box, sizeof root_box, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t n2 = tail[0] + tail[1];
+        if (n2 == 0) throw rt_error(RT_ERR_UNSUPPORTED, "device build: empty hierarchy");
+        float scale = 0.0f;
+        for (int c = 0; c < 3; ++c) scale = std::max(scale, std::max(std::fabs(root_box.lo[c]), std::fabs(root_box.hi[c])));
+        const float pad = 2e-5f * scale;                       // host/bvh_build.cpp flatten_bvh explains the padding
+        CK(cudaMalloc(&out.nodes16, size_t(n2) * 64));
+        CK(cudaMalloc(&out.tris12, size_t(n) * 48));
+        k_lbvh_emit_nodes<<<G, B, 0, st>>>(left, right, first, last, kept, dense, leaf_box, inner_box, int(n_inner), pad, out.nodes16);
+        CK(cudaGetLastError());
+        k_lbvh_emit_tris<<<G, B, 0, st>>>(d_tri9, sids, n, out.tris12);
+        CK(cudaGetLastError());
+        // four-wide collapse, level by level (also measures the two-wide depth and the worst-case stack need)
+        uint32_t* nodes32 = tmp.get<uint32_t>(size_t(n2) * 32);
+        LbvhFrontier *fa = tmp.get<LbvhFrontier>(n2), *fb = tmp.get<LbvhFrontier>(n2);
+        LbvhCounters* ctr = tmp.get<LbvhCounters>(1);
+        LbvhCounters hc{1u, 0u, 0u, 0u};
+        const LbvhFrontier rootf{0u, 0u, 0u, 0u};
+        CK(cudaMemcpyAsync(fa, &rootf, sizeof rootf, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctr, &hc, sizeof hc, cudaMemcpyHostToDevice, st));
+        uint32_t n_in = 1;
+        for (int level = 0; n_in; ++level) {
+            if (level > 256) throw rt_error(RT_ERR_UNSUPPORTED, "device build: hierarchy too deep");
+            k_lbvh_collapse_level<<<(n_in + 127) / 128, 128, 0, st>>>(out.nodes16, fa, n_in, fb, n2, ctr, nodes32, n2);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            n_in = hc.next_count;
+            const uint32_t zero = 0;
+            CK(cudaMemcpyAsync(&ctr->next_count, &zero, 4, cudaMemcpyHostToDevice, st));
+            std::swap(fa, fb);
+        }
+        if (hc.depth2 > 44 || hc.stack_need > uint32_t(BVH4_STACK) || hc.n_nodes4 > n2)
+            throw rt_error(RT_ERR_UNSUPPORTED, "device build: the linear hierarchy is deeper than the traversal stacks allow");
+        if (wide) {
+            CK(cudaMalloc(&out.nodes32, size_t(hc.n_nodes4) * 128));
+            CK(cudaMemcpyAsync(out.nodes32, nodes32, size_t(hc.n_nodes4) * 128, cudaMemcpyDeviceToDevice, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        out.n_nodes2 = n2; out.n_nodes4 = hc.n_nodes4; out.n_tris = n; out.stack_need = hc.stack_need; out.depth2 = hc.depth2;
+        out.bytes = size_t(n2) * 64 + size_t(n) * 48 + (wide ? size_t(hc.n_nodes4) * 128 : 0);
+        for (int c = 0; c < 3; ++c) { out.root_min[c] = root_box.lo[c] - pad; out.root_max[c] = root_box.hi[c] + pad; }
+        out.seconds = now_s() - t0;
+        out.built = true;
+        s->dev_bvh = out;
+    } catch (...) {
+        fail_free();
+        throw;
+    }
+}
+
+void upload_scene(rt_scene* s) {
+    const double t0 = now_s();
+    select_device(s);
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 
     const DeviceLayout& L = s->layout;
@@ -229,11 +368,20 @@ void upload_scene(rt_scene* s) {
     uint64_t bytes = 0;
     DScene& d = s->d;
     auto keep = [&](auto* p) { s->owned.push_back((void*)p); return p; };
-    d.b_nodes = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.nodes.data(), s->bvh_layout.nodes.size() / 4, bytes)));
-    d.b_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.tris.data(), s->bvh_layout.tris.size() / 4, bytes)));
-    d.w_nodes = s->wide ? reinterpret_cast<const float*>(keep(upload<float4>(s->bvh4_nodes.data(), s->bvh4_nodes.size() / 4, bytes))) : nullptr;
-    std::memcpy(d.b_root_min, s->bvh_layout.root_min, 12);
-    std::memcpy(d.b_root_max, s->bvh_layout.root_max, 12);
+    if (s->dev_bvh.built) {
+        d.b_nodes = reinterpret_cast<const float*>(keep(s->dev_bvh.nodes16));
+        d.b_tris = reinterpret_cast<const float*>(keep(s->dev_bvh.tris12));
+        d.w_nodes = s->wide ? reinterpret_cast<const float*>(keep(s->dev_bvh.nodes32)) : nullptr;
+        bytes += s->dev_bvh.bytes;
+        std::memcpy(d.b_root_min, s->dev_bvh.root_min, 12);
+        std::memcpy(d.b_root_max, s->dev_bvh.root_max, 12);
+    } else {
+        d.b_nodes = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.nodes.data(), s->bvh_layout.nodes.size() / 4, bytes)));
+        d.b_tris = reinterpret_cast<const float*>(keep(upload<float4>(s->bvh_layout.tris.data(), s->bvh_layout.tris.size() / 4, bytes)));
+        d.w_nodes = s->wide ? reinterpret_cast<const float*>(keep(upload<float4>(s->bvh4_nodes.data(), s->bvh4_nodes.size() / 4, bytes))) : nullptr;
+        std::memcpy(d.b_root_min, s->bvh_layout.root_min, 12);
+        std::memcpy(d.b_root_max, s->bvh_layout.root_max, 12);
+    }
     d.nodes32 = keep(upload<float4>(L.nodes32.data(), L.nodes32.size() / 4, bytes));
     d.packets = keep(upload<float4>(L.packets.data(), L.packets.size() / 4, bytes));
     d.tri_index = keep(upload<uint4>(L.tri_index.data(), L.tri_index.size() / 4, bytes));
@@ -278,29 +426,64 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     if (opts) o = *opts;
     if (o.kd_max_depth > 30) throw rt_error(RT_ERR_BAD_ARG, "kd_max_depth > 30");
     if (o.kd_max_leaf_size == 0) throw rt_error(RT_ERR_BAD_ARG, "kd_max_leaf_size == 0");
+    // the accelerated mode's hierarchy: its width (rt_build_opts.accel_width; RT_B200_ACCEL_WIDTH overrides the default for sweeps)
+    // and where it is built (rt_build_opts.accel_build; RT_B200_ACCEL_BUILD likewise)
+    uint32_t leaf = 4;                                                 // RT_B200_BVH_LEAF: tuning sweeps only
+    if (const char* e = std::getenv("RT_B200_BVH_LEAF")) std::sscanf(e, "%u", &leaf);
+    uint32_t width = o.accel_width;
+    if (!width) { width = RT_DEFAULT_ACCEL_WIDTH; if (const char* e = std::getenv("RT_B200_ACCEL_WIDTH")) std::sscanf(e, "%u", &width); }
+    if (width != 2 && width != 4) throw rt_error(RT_ERR_BAD_ARG, "accel_width must be 0 (default), 2 or 4");
+    if (width == 4 && leaf > BVH4_MAX_LEAF) throw rt_error(RT_ERR_BAD_ARG, "accel_width 4 holds at most 7 triangles per leaf");
+    uint32_t where = o.accel_build;
+    if (!where) if (const char* e = std::getenv("RT_B200_ACCEL_BUILD")) std::sscanf(e, "%u", &where);
+    if (where > RT_ACCEL_BUILD_DEVICE) throw rt_error(RT_ERR_BAD_ARG, "accel_build must be RT_ACCEL_BUILD_HOST or RT_ACCEL_BUILD_DEVICE");
+    if (where == RT_ACCEL_BUILD_DEVICE && o.device < 0) throw rt_error(RT_ERR_BAD_ARG, "accel_build = device needs a device");
+    s->wide = width == 4;
+    s->info.accel_width = width;
+    s->device = o.device;
+    s->info.device = o.device;
+    const bool verbose = std::getenv("RT_B200_VERBOSE") != nullptr;
+
     double t0 = now_s();
     s->geom = prepare_geometry(s->host);
+    // the device build runs beside the host build of the reference's kd-tree
+    struct Side {
+        std::thread th;
+        std::exception_ptr err;
+        ~Side() { if (th.joinable()) th.join(); }
+    } side;
+    if (where == RT_ACCEL_BUILD_DEVICE && s->geom.tris.size() > 4 * LBVH_LEAF)
+        side.th = std::thread([&] { try { device_build_bvh(s, s->wide); } catch (...) { side.err = std::current_exception(); } });
     s->tree = build_kd_tree(s->geom, o.kd_max_depth, o.kd_max_leaf_size);
     s->info.build_seconds = now_s() - t0;
     t0 = now_s();
     s->layout = flatten(s->host, s->geom, s->tree);
-    {
+    if (side.th.joinable()) side.th.join();
+    if (side.err) {
+        try { std::rethrow_exception(side.err); }
+        catch (const rt_error& e) {
+            if (e.status != RT_ERR_UNSUPPORTED) throw;
+            if (verbose) std::fprintf(stderr, "[rt_b200] %s; building on the host\n", e.what());
+        }
+    }
+    if (s->dev_bvh.built) {
+        const auto& b = s->dev_bvh;
+        s->info.accel_build = RT_ACCEL_BUILD_DEVICE;
+        s->info.accel_build_seconds = b.seconds;
+        s->info.bvh_n_nodes = b.n_nodes2; s->info.bvh_n_refs = b.n_tris;
+        s->info.bvh_n_leaves = b.n_nodes2 + 1; s->info.bvh_depth = b.depth2;       // every two-wide node has exactly two children
+        if (s->wide) { s->info.bvh4_n_nodes = b.n_nodes4; s->info.bvh4_stack_need = b.stack_need; }
+        if (verbose) std::fprintf(stderr, "[rt_b200] device bvh build %.3f s: %llu two-wide nodes (depth %u), %llu four-wide (stack need %u)\n", b.seconds,
+                                  (unsigned long long)b.n_nodes2, b.depth2, (unsigned long long)b.n_nodes4, b.stack_need);
+    } else {
         const double t3 = now_s();
-        uint32_t leaf = 4;                                             // RT_B200_BVH_LEAF: tuning sweeps only
-        if (const char* e = std::getenv("RT_B200_BVH_LEAF")) std::sscanf(e, "%u", &leaf);
         KdTree bvh = build_bvh(s->geom, leaf);
         const double t4 = now_s();
         s->bvh_layout = flatten_bvh(s->geom, bvh);
-        if (std::getenv("RT_B200_VERBOSE")) std::fprintf(stderr, "[rt_b200] bvh build %.3f s, flatten %.3f s\n", t4 - t3, now_s() - t4);
+        if (verbose) std::fprintf(stderr, "[rt_b200] bvh build %.3f s, flatten %.3f s\n", t4 - t3, now_s() - t4);
+        s->info.accel_build = RT_ACCEL_BUILD_HOST;
         s->info.bvh_n_nodes = s->bvh_layout.n_nodes; s->info.bvh_n_refs = s->bvh_layout.n_refs;
         s->info.bvh_n_leaves = bvh.n_leaves; s->info.bvh_depth = bvh.depth;
-        // the four-wide form of the same hierarchy (rt_build_opts.accel_width; RT_B200_ACCEL_WIDTH overrides the default for sweeps)
-        uint32_t width = o.accel_width;
-        if (!width) { width = RT_DEFAULT_ACCEL_WIDTH; if (const char* e = std::getenv("RT_B200_ACCEL_WIDTH")) std::sscanf(e, "%u", &width); }
-        if (width != 2 && width != 4) throw rt_error(RT_ERR_BAD_ARG, "accel_width must be 0 (default), 2 or 4");
-        if (width == 4 && leaf > BVH4_MAX_LEAF) throw rt_error(RT_ERR_BAD_ARG, "accel_width 4 holds at most 7 triangles per leaf");
-        s->wide = width == 4;
-        s->info.accel_width = width;
         if (s->wide) {
             try { s->bvh4_nodes = bvh4_collapse(s->bvh_layout.nodes.data(), s->bvh_layout.n_nodes); }
             catch (const std::length_error& e) { throw rt_error(RT_ERR_UNSUPPORTED, e.what()); }
@@ -308,7 +491,8 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
             s->info.bvh4_stack_need = bvh4_stack_need(s->bvh4_nodes);
             if (s->info.bvh4_stack_need > uint64_t(BVH4_STACK)) throw rt_error(RT_ERR_UNSUPPORTED, "four-wide hierarchy needs a deeper traversal stack than BVH4_STACK");
         }
-        if (std::getenv("RT_B200_VERBOSE")) std::fprintf(stderr, "[rt_b200] bvh build + flatten %.3f s\n", now_s() - t3);
+        s->info.accel_build_seconds = now_s() - t3;
+        if (verbose) std::fprintf(stderr, "[rt_b200] bvh build + flatten %.3f s\n", now_s() - t3);
     }
     s->info.flatten_seconds = now_s() - t0;
     s->info.width = s->host.width; s->info.height = s->host.height;
@@ -320,8 +504,6 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     s->info.n_packets = s->layout.n_packets;
     s->info.max_leaf_refs = s->tree.max_leaf_refs;
     s->info.tree_depth = s->tree.depth;
-    s->device = o.device;
-    s->info.device = o.device;
     if (o.device >= 0) upload_scene(s);
     *out = s;
     return RT_OK;
@@ -983,7 +1165,7 @@ const char* rt_last_error(void) { return g_last_error.c_str(); }
 
 void rt_default_build_opts(rt_build_opts* o) {
     if (!o) return;
-    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_width = 0;
+    o->kd_max_depth = 8; o->kd_max_leaf_size = 64; o->device = 0; o->accel_width = 0; o->accel_build = RT_ACCEL_BUILD_HOST;
 }
 
 void rt_default_params(rt_params* p) {
@@ -1049,6 +1231,15 @@ int rt_scene_get_device_layout(const rt_scene* s, uint32_t* nodes8, uint32_t* pa
 
 int rt_scene_get_bvh_layout(const rt_scene* s, uint32_t* nodes16, uint32_t* tris12, float* root6) {
     if (!s) return fail(RT_ERR_BAD_ARG, "null scene");
+    if (s->dev_bvh.built) {                      // built on the device: the arrays live there
+        return guarded([&] {
+            CK(cudaSetDevice(s->device));
+            if (nodes16) CK(cudaMemcpy(nodes16, s->dev_bvh.nodes16, size_t(s->dev_bvh.n_nodes2) * 64, cudaMemcpyDeviceToHost));
+            if (tris12) CK(cudaMemcpy(tris12, s->dev_bvh.tris12, size_t(s->dev_bvh.n_tris) * 48, cudaMemcpyDeviceToHost));
+            if (root6) { std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12); }
+            return int(RT_OK);
+        });
+    }
     if (nodes16) std::memcpy(nodes16, s->bvh_layout.nodes.data(), size_t(s->bvh_layout.n_nodes) * 16 * 4);
     if (tris12) std::memcpy(tris12, s->bvh_layout.tris.data(), size_t(s->bvh_layout.n_refs) * 12 * 4);
     if (root6) { std::memcpy(root6, s->geom.root_min, 12); std::memcpy(root6 + 3, s->geom.root_max, 12); }   // the reference's root box (bvh_init)

@@ -534,6 +534,68 @@ def test_accelerated_mode_occluded_and_synthetic(rt, oracle_mod, width):
         assert np.array_equal(s.trace_occluded(rays, max_t, flags=rt.FLAG_ORDERED), want)
 
 
+# ---- the hierarchy built on the device (rt_build_opts.accel_build, csrc/rt_lbvh.cuh) ---------------------------------------
+@pytest.mark.parametrize("width", WIDTHS)
+@pytest.mark.parametrize("name", ["hw09_scene5", "hw11_scene8", "hw15_scene2"])
+def test_device_built_hierarchy_same_hits_and_frames(rt, oracle_mod, golden, name, width):
+    """a different tree (linear BVH from CUDA kernels) under the same queries: hits, frames and ray counts are the reference's,
+    bit for bit; the exported tree covers every triangle exactly once"""
+    data = scene_bytes(name)
+    s = rt.Scene.from_rtsc(data, accel_width=width, accel_build=rt.ACCEL_BUILD_DEVICE)
+    o = oracle_mod.Oracle(data)
+    assert s.info.accel_build == rt.ACCEL_BUILD_DEVICE and s.info.accel_width == width
+    assert s.info.bvh_n_refs == s.info.n_triangles and s.info.bvh_n_nodes >= 1 and s.info.bvh_depth <= 44
+    assert (s.info.bvh4_n_nodes >= 1) == (width == 4) and s.info.bvh4_stack_need <= 136
+    nodes16, tris12, _ = s.bvh_layout()
+    assert np.array_equal(np.sort(tris12[:, 3]), np.arange(s.info.n_triangles, dtype=np.uint32))
+    leaves = nodes16[:, 14:16].reshape(-1)
+    assert int(leaves.sum()) == s.info.n_triangles and int(leaves.max()) <= 4
+    hits = s.trace_primary(rt.default_params(flags=rt.FLAG_ORDERED)).reshape(-1)
+    assert_hits_equal(hits, *o.trace(o.primary_rays(), True))
+    rays = random_rays(200_000, 29)
+    n5, bx, _ = s.tree()
+    rays[:, :3] = rays[:, :3] * (bx[0, 3:] - bx[0, :3]).max() / 2 + (bx[0, :3] + bx[0, 3:]) / 2
+    for cull in (False, True):
+        assert_hits_equal(s.trace_closest(rays, cull, flags=rt.FLAG_ORDERED), *o.trace(rays, cull))
+    max_t = np.random.default_rng(8).uniform(0.01, 6.0, len(rays)).astype(np.float32)
+    want, _ = o.occluded(rays, max_t)
+    assert np.array_equal(s.trace_occluded(rays, max_t, flags=rt.FLAG_ORDERED), want)
+    for cname, key, depth in CONFIGS:
+        if cname != name:
+            continue
+        g = golden["scenes"][name]["configs"][key]
+        img = s.render_frame(rt.default_params(max_ray_depth=depth, flags=rt.FLAG_ORDERED))
+        assert sha(img) == g["sha256_f32"]
+        c = s.counters()
+        assert (c.primary, c.primary_hits) == (g["counts"]["cull"], g["counts"]["cull_hit"])
+        assert c.shadow + c.secondary == g["counts"]["nocull"]
+    s.close()
+
+
+def test_device_built_hierarchy_large_mesh_and_fallback(rt, oracle_mod):
+    """300 K triangles: the device-built and the host-built scene render the same GI frame bit for bit (Philox-keyed rays) and
+    give the oracle's hits; a scene too small for the device builder (<= 16 triangles) is built on the host and says so"""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=300_000, seed=1234, width=480, height=270))
+    kw = dict(samples_per_pixel=2, diffuse_reflection_ray_count=1, max_ray_depth=5, flags=rt.FLAG_ORDERED)
+    a = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64)
+    fa = a.render_frame(rt.default_params(**kw))
+    ca = a.counters()
+    a.close()
+    b = rt.Scene.from_rtsc(data, kd_max_depth=24, kd_max_leaf_size=64, accel_build=rt.ACCEL_BUILD_DEVICE)
+    assert b.info.accel_build == rt.ACCEL_BUILD_DEVICE and b.info.accel_build_seconds < 2.0
+    fb = b.render_frame(rt.default_params(**kw))
+    cb = b.counters()
+    assert np.array_equal(fa.view(np.uint32), fb.view(np.uint32))
+    assert (ca.primary, ca.primary_hits, ca.shadow, ca.secondary, ca.secondary_hits) == (cb.primary, cb.primary_hits, cb.shadow, cb.secondary, cb.secondary_hits)
+    o = oracle_mod.Oracle(data, 24, 64)
+    rays = random_rays(100_000, 3, -1.4, 1.4)
+    assert_hits_equal(b.trace_closest(rays, False, flags=rt.FLAG_ORDERED), *o.trace(rays, False))
+    b.close()
+    small = rt.Scene.from_rtsc(scene_bytes("hw12_scene4"), accel_build=rt.ACCEL_BUILD_DEVICE)
+    assert small.info.n_triangles <= 16 and small.info.accel_build == rt.ACCEL_BUILD_HOST
+    small.close()
+
+
 @pytest.mark.parametrize("width", WIDTHS)
 def test_config5_shape_synthetic_gi_frame(rt, oracle_mod, width):
     """BASELINE.json configs[4] in miniature: a 300 K-triangle random mesh in the diffuse box, kd<24,64>, GI 1, depth 5.

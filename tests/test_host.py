@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(rt):
     assert sorted(names) == sorted(rt.ABI_SYMBOLS)
     for n in names:
         assert hasattr(rt.lib, n), n
-    assert rt.lib.rt_abi_version() == 2
+    assert rt.lib.rt_abi_version() == 3
     assert rt.lib.rt_status_string(2) == b"no usable sm_100 CUDA device"
 
 
