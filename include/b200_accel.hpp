@@ -55,7 +55,7 @@ struct b200_accel {
     mutable std::shared_ptr<float> staging;
 
     explicit b200_accel(std::shared_ptr<const scene<F>> sp, std::uint32_t kd_max_depth = 8, std::uint32_t kd_max_leaf_size = 64,
-                        int device = 0)
+                        int device = 0, std::uint32_t accel_build = RT_ACCEL_BUILD_HOST)
         : scene_ptr(std::move(sp)) {
         const scene<F>& sc = *scene_ptr;
         rt_scene_desc d{};
@@ -150,7 +150,7 @@ struct b200_accel {
 
         rt_build_opts o;
         rt_default_build_opts(&o);
-        o.kd_max_depth = kd_max_depth; o.kd_max_leaf_size = kd_max_leaf_size; o.device = device;
+        o.kd_max_depth = kd_max_depth; o.kd_max_leaf_size = kd_max_leaf_size; o.device = device; o.accel_build = accel_build;
         rt_scene* raw = nullptr;
         const int st = rt_scene_create(&d, &o, &raw);
         if (st != RT_OK) throw std::runtime_error(std::string("b200_accel: ") + rt_status_string(st) + ": " + rt_last_error());
