@@ -346,10 +346,10 @@ def north_star_scaling(rt, args, rank: int, world: int, local: int, flags: int):
         g = group()
         BAND = 16                                                   # rows per band: 135 bands at 4K, so 16 or 17 per rank at N = 8
         bands = rt.row_bands(H, BAND, rank, world)
-        band_params = [rt.default_params(samples_per_pixel=T, y0=y0, y1=y1, flags=flags, **kw) for y0, y1 in bands]
+        # all of the rank's bands in ONE call (rt_params.band_rows / band_period / band_phase): one wavefront over 1/N of the frame
+        band_params = rt.default_params(samples_per_pixel=T, band_rows=BAND, band_period=world, band_phase=rank, flags=flags, **kw)
         def by_bands():
-            for bp in band_params:
-                scene.render_frame_device(bp, g.framebuffer, stream=stream.cuda_stream)
+            scene.render_frame_device(band_params, g.framebuffer, stream=stream.cuda_stream)
             g.combine(1, rt.PEER_OUT_RGB, stream=stream.cuda_stream)      # sum of disjoint bands; dividing by 1 is exact
         # both frame slots of the group must hold this rank's bands and zeros elsewhere: three frames touch both slots
         ms = timed(by_bands, frames=2, warm=2)

@@ -37,7 +37,10 @@ typedef enum rt_status {
     RT_ERR_PARSE = 5,          /* malformed .crtscene / RTSC; unknown material or texture type */
     RT_ERR_OOM = 6,
     RT_ERR_UNSUPPORTED = 7,    /* e.g. a bitmap format the loader cannot decode */
-    RT_FRAME_RERENDERED = 8    /* rt_frame_wait on an rt_render_frame_device_begin ticket: not an error, see there */
+    RT_FRAME_RERENDERED = 8,   /* rt_frame_wait on an rt_render_frame_device_begin ticket: not an error, see there */
+    RT_ERR_TIMEOUT = 9         /* multi-GPU combine: a peer did not signal a frame within RT_B200_PEER_TIMEOUT_MS (default 30 s;
+                                  0 = wait for ever).  The waiting kernels give up instead of spinning on a dead peer, the stream
+                                  drains, and every later rt_peer_* call of the group reports this status */
 } rt_status;
 
 /* ---- scene description: what io/json/loader.hpp:235-265 produces, flattened -------------------------------- */
@@ -121,6 +124,12 @@ typedef struct rt_params {
     uint32_t spp_total;              /* samples of the whole frame (0 = samples_per_pixel); ==1 -> pixel centres */
     uint32_t x0, y0, x1, y1;         /* tile rectangle; x1 == 0 / y1 == 0 mean full width / height */
     uint32_t flags;                  /* RT_FLAG_* */
+    /* row bands - the reference's bucket decomposition (render/tile/bucket.hpp:7-21) for tile-sharded multi-GPU frames, in ONE
+     * call per rank: with band_rows != 0 the call renders the rows y of the frame with (y / band_rows) % band_period ==
+     * band_phase (rank r of N: band_period = N, band_phase = r) and leaves every other row of the device frame untouched.
+     * band_rows must be a multiple of 4; x0..y1 must be 0; only the device-frame entry points take bands (rt_render_frame_device,
+     * rt_render_frame_device_begin) - RT_ERR_BAD_ARG otherwise.  Pixels are the same bits as in a whole-frame render. */
+    uint32_t band_rows, band_period, band_phase;
 } rt_params;
 
 #define RT_FLAG_RAW_SUM       0x1u   /* write the slice's sample sum; the caller divides after combining ranks */
@@ -266,7 +275,10 @@ typedef struct rt_peer_group rt_peer_group;
 RT_API int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t width, uint32_t height, rt_peer_group** out,
                                 uint8_t* handle /* RT_PEER_HANDLE_BYTES, may be null */);
 RT_API int rt_peer_group_connect(rt_peer_group* g, const uint8_t* handles /* world x RT_PEER_HANDLE_BYTES, rank order */);
-/* all ranks inside one process (one GPU emulating several ranks, or several peer GPUs driven by one host thread) */
+/* all ranks inside one process (one GPU emulating several ranks, or several peer GPUs driven by one host thread).  When the
+ * ranks share ONE device and stream, signal every rank (rt_peer_signal_ready) before any rank reduces: a reduce waits on the
+ * device for its peers' flags, and a kernel queued behind it on the same stream cannot set them (the wait then runs out:
+ * RT_ERR_TIMEOUT). */
 RT_API int rt_peer_group_connect_local(rt_peer_group* const* groups, uint32_t world);
 /* Every rank owns TWO frame slots: frame e+1 can be rendered while frame e is being combined.  rt_peer_framebuffer is where
  * the NEXT frame (the one that will be signalled next) is rendered; it flips with every rt_peer_signal_ready.  The result

@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")
 
 RT_OK, RT_ERR_BAD_ARG, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_OOM, RT_ERR_UNSUPPORTED = range(8)
 RT_FRAME_RERENDERED = 8
+RT_ERR_TIMEOUT = 9
 FLAG_RAW_SUM, FLAG_FAST_MATH, FLAG_ORDERED = 1, 2, 4
 DEVICE_HOST_ONLY = -1
 TEX_ALBEDO, TEX_EDGES, TEX_CHECKER, TEX_BITMAP = range(4)
@@ -89,7 +90,8 @@ class Params(C.Structure):
                 ("reflection_bias", C.c_float), ("refraction_bias", C.c_float), ("samples_per_pixel", C.c_uint32),
                 ("max_ray_depth", C.c_uint32), ("diffuse_reflection_ray_count", C.c_uint32), ("seed", C.c_uint32),
                 ("sample_offset", C.c_uint32), ("spp_total", C.c_uint32),
-                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32), ("flags", C.c_uint32)]
+                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32), ("flags", C.c_uint32),
+                ("band_rows", C.c_uint32), ("band_period", C.c_uint32), ("band_phase", C.c_uint32)]
 
 
 class SceneInfo(C.Structure):

@@ -604,7 +604,26 @@ __global__ void k_pass_commit(PassState* ps, FrameCounters* fc, uint32_t* out, u
 
 struct Rect { uint32_t x0, y0, x1, y1; };
 
+// rows of the frame a call with row bands renders (rt_params.band_rows): bands phase, phase + period, ... of band_rows rows each
+uint32_t band_row_count(uint32_t height, const rt_params& p) {
+    const uint32_t n_bands = (height + p.band_rows - 1) / p.band_rows;
+    uint64_t rows = 0;
+    for (uint32_t b = p.band_phase; b < n_bands; b += p.band_period) rows += std::min(p.band_rows, height - b * p.band_rows);
+    return uint32_t(rows);
+}
+
+// entry points that deliver a host image or a hit array take a rectangle only
+void forbid_bands(const rt_params& p) {
+    if (p.band_rows) throw rt_error(RT_ERR_BAD_ARG, "row bands are rendered into a device frame (rt_render_frame_device, rt_render_frame_device_begin)");
+}
+
 Rect rect_of(const rt_scene* s, const rt_params& p) {
+    if (p.band_rows) {
+        if (p.band_rows % 4u || !p.band_period || p.band_phase >= p.band_period) throw rt_error(RT_ERR_BAD_ARG, "band_rows must be a multiple of 4 and band_phase < band_period");
+        if (p.x0 | p.y0 | p.x1 | p.y1) throw rt_error(RT_ERR_BAD_ARG, "row bands and a tile rectangle exclude each other");
+        if (!band_row_count(s->host.height, p)) throw rt_error(RT_ERR_BAD_ARG, "no row band of the frame has this phase");
+        return Rect{0, 0, s->host.width, s->host.height};
+    }
     Rect r{p.x0, p.y0, p.x1 ? p.x1 : s->host.width, p.y1 ? p.y1 : s->host.height};
     r.x1 = std::min(r.x1, s->host.width); r.y1 = std::min(r.y1, s->host.height);
     if (r.x0 >= r.x1 || r.y0 >= r.y1) throw rt_error(RT_ERR_BAD_ARG, "empty tile rectangle");
@@ -620,6 +639,7 @@ FrameParams frame_params(const rt_scene* s, const rt_params& p, const Rect& r) {
     fp.max_ray_depth = p.max_ray_depth; fp.gi_rays = p.diffuse_reflection_ray_count; fp.seed = p.seed;
     fp.spp_total = p.spp_total ? p.spp_total : p.samples_per_pixel;
     fp.x0 = r.x0; fp.y0 = r.y0; fp.tw = r.x1 - r.x0; fp.th = r.y1 - r.y0;
+    if (p.band_rows) { fp.band_rows = p.band_rows; fp.band_period = p.band_period; fp.band_phase = p.band_phase; fp.th = band_row_count(s->host.height, p); }
     fp.tiles_x = (fp.tw + 7) / 8;
     const uint64_t plane = uint64_t(fp.tiles_x) * ((fp.th + 3) / 4) * 32;
     if (plane >= (1ull << 31)) throw rt_error(RT_ERR_BAD_ARG, "tile too large");
@@ -1065,6 +1085,7 @@ void drain_sequence(rt_scene* s) {
 // rgb / rgb8: host frame to download into (frame sequences) or null; d_ext: the caller's device frame or null (then the slot's own)
 void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cudaStream_t st, uint64_t* ticket, uint8_t* rgb8 = nullptr) {
     check_params(p);
+    if (rgb || rgb8) forbid_bands(p);
     const Rect rect = rect_of(s, p);
     // every queued frame of a scene shares its wavefront pools, pass state and counters: two frames in flight on DIFFERENT
     // streams would race on them
@@ -1156,6 +1177,7 @@ const char* rt_status_string(int status) {
         case RT_ERR_PARSE: return "parse error";
         case RT_ERR_OOM: return "out of memory";
         case RT_ERR_UNSUPPORTED: return "unsupported";
+        case RT_ERR_TIMEOUT: return "a peer did not signal in time";
         case RT_FRAME_RERENDERED: return "frame was rendered again (its first, queued attempt outgrew the wavefront pools)";
         default: return "unknown status";
     }
@@ -1340,6 +1362,7 @@ int rt_render_frame(rt_scene* s, const rt_params* p, float* rgb) {
         CK(cudaSetDevice(s->device));
         const size_t n = size_t(s->host.width) * s->host.height * 3;
         s->fb.reserve(n);
+        forbid_bands(*p);
         const Rect r = rect_of(s, *p);
         render_device(s, *p, s->fb.p, s->stream);
         // only the tile rectangle is defined on the device and only it is written to the caller's image
@@ -1361,6 +1384,7 @@ int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8) {
         CK(cudaSetDevice(s->device));
         const size_t n = size_t(s->host.width) * s->host.height * 3;
         s->fb.reserve(n); s->fb8.reserve(n);
+        forbid_bands(*p);
         const Rect r = rect_of(s, *p);
         render_device(s, *p, s->fb.p, s->stream);
         const size_t first = size_t(r.y0) * s->host.width * 3, count = size_t(r.y1 - r.y0) * s->host.width * 3;
@@ -1452,6 +1476,7 @@ int rt_trace_primary(rt_scene* s, const rt_params* p, rt_hit* hits) {
         require_device(s);
         if (!p || !hits) throw rt_error(RT_ERR_BAD_ARG, "null argument");
         check_params(*p);
+        forbid_bands(*p);
         std::lock_guard<std::mutex> lock(s->mtx);
         CK(cudaSetDevice(s->device));
         const Rect r = rect_of(s, *p);
@@ -1519,6 +1544,14 @@ struct rt_peer_group {
     uint32_t host_epoch = 0;                // last frame that was sent to the shared host frame
     uint8_t* stage = nullptr;               // copy-engine gather: this rank's slice of every OTHER rank's raw sums ((world - 1) x stage_stride bytes)
     size_t stage_stride = 0;
+    // bounded waits (rt_peer.cuh PeerWait): a word in mapped host memory the wait kernels write when a peer's flag did not come
+    uint32_t* err_host = nullptr;           // host view; 0 = no wait has timed out
+    PeerWait wait{nullptr, 0};
+    // throws RT_ERR_TIMEOUT once a wait kernel has reported a peer that never signalled (checked by every rt_peer_* call)
+    void check_waits() const {
+        const uint32_t e = err_host ? *reinterpret_cast<volatile const uint32_t*>(err_host) : 0u;
+        if (e) throw rt_error(RT_ERR_TIMEOUT, "a peer did not signal frame " + std::to_string(e) + " in time (RT_B200_PEER_TIMEOUT_MS); the combined frame is not valid");
+    }
     size_t next_slot() const { return size_t(epoch & 1u) * slot_bytes; }           // where the NEXT frame is rendered
     size_t last_slot() const { return size_t((epoch - 1u) & 1u) * slot_bytes; }    // the frame signalled last
 };
@@ -1559,6 +1592,12 @@ int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t wid
         g->bytes = g->off_flags + align256(PEER_FLAG_COUNT * 4);
         CK(cudaMalloc(&g->block, g->bytes));
         CK(cudaMemset(g->block, 0, g->bytes));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&g->err_host), 64, cudaHostAllocMapped));
+        *g->err_host = 0;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g->wait.error), g->err_host, 0));
+        unsigned timeout_ms = 30000;
+        if (const char* e = std::getenv("RT_B200_PEER_TIMEOUT_MS")) std::sscanf(e, "%u", &timeout_ms);
+        g->wait.timeout_ns = 1000000ull * timeout_ms;
         CK(cudaDeviceSynchronize());
         g->peer[rank] = g->block;
         if (handle) {
@@ -1570,7 +1609,7 @@ int rt_peer_group_create(uint32_t world, uint32_t rank, int device, uint32_t wid
         *out = g;
         return int(RT_OK);
     });
-    if (st != RT_OK) { if (g) { if (g->block) cudaFree(g->block); delete g; } *out = nullptr; }
+    if (st != RT_OK) { if (g) { if (g->block) cudaFree(g->block); if (g->err_host) cudaFreeHost(g->err_host); delete g; } *out = nullptr; }
     return st;
 }
 
@@ -1638,6 +1677,7 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
     return guarded([&] {
         if (!g || !g->connected || spp_total == 0) throw rt_error(RT_ERR_BAD_ARG, "bad argument");
         if (g->epoch == 0) throw rt_error(RT_ERR_BAD_ARG, "rt_peer_signal_ready has not been called for this frame");
+        g->check_waits();
         if ((outputs & RT_PEER_OUT_HOST_RGB) && !g->host_dev) throw rt_error(RT_ERR_BAD_ARG, "RT_PEER_OUT_HOST_RGB without rt_peer_host_result_attach");
         CK(cudaSetDevice(g->device));
         const uint64_t n4 = g->n / 4;
@@ -1663,7 +1703,7 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
                 g->stage_stride = align256((g->n / g->world + 8) * sizeof(float));
                 CK(cudaMalloc(&g->stage, g->stage_stride * (g->world - 1)));
             }
-            k_peer_wait_ready<<<1, 32, 0, st>>>(g->table.flags[g->rank], int(g->world), g->epoch);
+            k_peer_wait_ready<<<1, 32, 0, st>>>(g->table.flags[g->rank], int(g->world), g->epoch, g->wait);
             CK(cudaGetLastError());
             uint32_t k = 0;
             for (uint32_t r = 0; r < g->world; ++r) {
@@ -1682,7 +1722,7 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
         uint8_t* root = g->peer[0] + g->last_slot();
 #define PEER_REDUCE(U)                                                                                                                        \
         k_peer_reduce_resolve<U><<<blocks, 256, 0, st>>>(                                                                                     \
-            g->table, src, gather ? 0 : 1, int(g->world), int(g->rank), g0, g1, float(spp_total),                                             \
+            g->table, src, gather ? 0 : 1, g->wait, int(g->world), int(g->rank), g0, g1, float(spp_total),                                            \
             (outputs & 1u) ? reinterpret_cast<float*>(root + g->off_rgb) : nullptr, (outputs & 2u) ? root + g->off_rgb8 : nullptr,            \
             g->epoch, n4 * 4, g->n, (outputs & RT_PEER_OUT_HOST_RGB) ? reinterpret_cast<float*>(g->block + g->last_slot() + g->off_rgb) : nullptr)
         if (unroll == 8) PEER_REDUCE(8); else if (unroll == 4) PEER_REDUCE(4); else if (unroll == 2) PEER_REDUCE(2); else PEER_REDUCE(1);
@@ -1706,11 +1746,12 @@ int rt_peer_reduce_resolve(rt_peer_group* g, uint32_t spp_total, uint32_t output
 int rt_peer_wait_done(rt_peer_group* g, void* stream) {
     return guarded([&] {
         if (!g || !g->connected) throw rt_error(RT_ERR_BAD_ARG, "peer group is not connected");
+        g->check_waits();
         CK(cudaSetDevice(g->device));
-        k_peer_wait_done<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch);
+        k_peer_wait_done<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch, g->wait);
         CK(cudaGetLastError());
         if (g->host_epoch == g->epoch) {          // this frame also goes to the shared host frame: every rank's slice has landed
-            k_peer_wait_host<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch);
+            k_peer_wait_host<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g->table.flags[g->rank], int(g->world), g->epoch, g->wait);
             CK(cudaGetLastError());
         }
         return int(RT_OK);
@@ -1727,6 +1768,7 @@ int rt_peer_combine(rt_peer_group* g, uint32_t spp_total, uint32_t outputs, void
 int rt_peer_download_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* stream) {
     return guarded([&] {
         if (!g || !g->epoch) throw rt_error(RT_ERR_BAD_ARG, "no combined frame yet");
+        g->check_waits();
         CK(cudaSetDevice(g->device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (rgb) CK(cudaMemcpyAsync(rgb, g->block + g->last_slot() + g->off_rgb, g->n * 4, cudaMemcpyDeviceToHost, st));
@@ -1740,6 +1782,7 @@ int rt_peer_read_result(rt_peer_group* g, float* rgb, uint8_t* rgb8, void* strea
     if (st != RT_OK) return st;
     return guarded([&] {
         CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+        g->check_waits();                                   // a wait of THIS frame that ran out is reported here, not a frame later
         return int(RT_OK);
     });
 }
@@ -1780,6 +1823,7 @@ void rt_peer_group_destroy(rt_peer_group* g) {
         if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
     if (g->block) cudaFree(g->block);
     if (g->stage) cudaFree(g->stage);
+    if (g->err_host) cudaFreeHost(g->err_host);
     delete g;
 }
 

@@ -44,6 +44,28 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+// Every wait on a peer's flag is BOUNDED: a peer that died, or never signals, must not leave this rank's GPU spinning for ever.
+// PeerWait::timeout_ns (rt_peer_group: RT_B200_PEER_TIMEOUT_MS, default 30 s; 0 = unbounded) is measured on %globaltimer; a wait
+// that runs out writes the frame number into PeerWait::error - a word in mapped host memory the host side reads at its next
+// rt_peer_* call (RT_ERR_TIMEOUT) - and returns, so the stream drains (with a frame that is not to be used).
+struct PeerWait { uint32_t* error; unsigned long long timeout_ns; };
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void peer_wait_flag(const uint32_t* p, uint32_t epoch, PeerWait w, unsigned sleep_ns) {
+    if (ld_acquire_sys(p) >= epoch) return;
+    const unsigned long long t0 = peer_now_ns();
+    while (ld_acquire_sys(p) < epoch) {
+        __nanosleep(sleep_ns);
+        if (w.timeout_ns && peer_now_ns() - t0 > w.timeout_ns) {
+            if (w.error) { *reinterpret_cast<volatile uint32_t*>(w.error) = epoch; __threadfence_system(); }
+            return;
+        }
+    }
+}
+
 // "my framebuffer holds frame `epoch`": one remote store per peer.  Launched with programmatic stream serialisation like the
 // kernels of a pass (rt_api.cu launch_ks): it is set up while the frame's last kernel drains and waits here for its completion.
 __global__ void k_peer_signal_ready(PeerTable t, int world, int rank, uint32_t epoch) {
@@ -57,16 +79,14 @@ __global__ void k_peer_signal_host(PeerTable t, int world, int rank, uint32_t ep
     const int i = threadIdx.x;
     if (i < world) { __threadfence_system(); st_release_sys(t.flags[i] + PEER_FLAG_HOST + rank, epoch); }
 }
-__global__ void k_peer_wait_host(const uint32_t* my_flags, int world, uint32_t epoch) {
+__global__ void k_peer_wait_host(const uint32_t* my_flags, int world, uint32_t epoch, PeerWait w) {
     const int i = threadIdx.x;
-    if (i < world)
-        while (ld_acquire_sys(my_flags + PEER_FLAG_HOST + i) < epoch) __nanosleep(64);
+    if (i < world) peer_wait_flag(my_flags + PEER_FLAG_HOST + i, epoch, w, 64);
 }
 
-__global__ void k_peer_wait_done(const uint32_t* my_flags, int world, uint32_t epoch) {
+__global__ void k_peer_wait_done(const uint32_t* my_flags, int world, uint32_t epoch, PeerWait w) {
     const int i = threadIdx.x;
-    if (i < world)
-        while (ld_acquire_sys(my_flags + PEER_FLAG_DONE + i) < epoch) __nanosleep(64);
+    if (i < world) peer_wait_flag(my_flags + PEER_FLAG_DONE + i, epoch, w, 64);
 }
 
 __device__ __forceinline__ uint8_t peer_quantise(float c) {          // io/image/ppm.hpp:17-19, product in double
@@ -85,21 +105,19 @@ __device__ __forceinline__ uint8_t peer_quantise(float c) {          // io/image
 struct PeerSources { const float* p[PEER_MAX]; };
 
 // every peer has published "frame `epoch` rendered" (in front of the copy-engine gather, which cannot wait on a flag itself)
-__global__ void k_peer_wait_ready(const uint32_t* my_flags, int world, uint32_t epoch) {
+__global__ void k_peer_wait_ready(const uint32_t* my_flags, int world, uint32_t epoch, PeerWait w) {
     const int i = threadIdx.x;
-    if (i < world)
-        while (ld_acquire_sys(my_flags + PEER_FLAG_READY + i) < epoch) __nanosleep(32);
+    if (i < world) peer_wait_flag(my_flags + PEER_FLAG_READY + i, epoch, w, 32);
 }
 
 template <int U>
-__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, PeerSources src, int wait_ready, int world, int rank, uint64_t g0, uint64_t g1, float div,
+__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PeerTable t, PeerSources src, int wait_ready, PeerWait wait, int world, int rank, uint64_t g0, uint64_t g1, float div,
                                                              float* __restrict__ root_rgb, uint8_t* __restrict__ root_rgb8,
                                                              uint32_t epoch, uint64_t n_tail_begin, uint64_t n_total, float* __restrict__ own_rgb) {
     constexpr int RB = 16 / U;
     // ---- wait until every peer has rendered frame `epoch` (flags are in MY memory, peers store into them) ----
     if (wait_ready) {
-        if (threadIdx.x < world)
-            while (ld_acquire_sys(t.flags[rank] + PEER_FLAG_READY + threadIdx.x) < epoch) __nanosleep(32);
+        if (threadIdx.x < world) peer_wait_flag(t.flags[rank] + PEER_FLAG_READY + threadIdx.x, epoch, wait, 32);
         __syncthreads();
     }
 

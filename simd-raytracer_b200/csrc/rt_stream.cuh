@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
         if (t < n_tiles) {
             lx0 = (t % fp.tiles_x) * 8u; ly0 = (t / fp.tiles_x) * 4u;
             w = min(8u, fp.tw - lx0); h = min(4u, fp.th - ly0);
-            cull = tile_misses_box(cam, sc.root_min, sc.root_max, float(fp.x0 + lx0), float(fp.y0 + ly0), float(fp.x0 + lx0 + w), float(fp.y0 + ly0 + h));
+            const uint32_t fy0 = frame_row(fp, ly0);
+            cull = tile_misses_box(cam, sc.root_min, sc.root_max, float(fp.x0 + lx0), float(fy0), float(fp.x0 + lx0 + w), float(fy0 + h));
         }
         const uint32_t keep = __ballot_sync(FULL, t < n_tiles && !cull);
         uint32_t slot = 0;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(256) k_tile_cull(DScene sc, FrameParams fp, fl
             const uint32_t tw = __shfl_sync(FULL, w, src), tht = __shfl_sync(FULL, h, src);
             if ((lane & 7u) < tw && (lane >> 3) < tht) {
                 if (fb) {                                                           // null in a multi-sample pass: k_accumulate adds the misses
-                    float* q = fb + (size_t(fp.y0 + py) * sc.width + (fp.x0 + px)) * 3;
+                    float* q = fb + (size_t(frame_row(fp, py)) * sc.width + (fp.x0 + px)) * 3;
                     q[0] = miss.x; q[1] = miss.y; q[2] = miss.z;
                 }
                 n_culled += fp.n_samples;

@@ -42,7 +42,18 @@ struct FrameParams {
     uint32_t tiles_x, plane;            // 8x4 pixel tiles per row; entries per sample plane (= tiles * 32)
     uint32_t pool_cap, shadow_cap;
     uint32_t sparse0, reserved;         // sparse0: only the HITS of the camera rays are level-0 entries (k_stream_primary_sparse)
+    // row bands (rt_params.band_rows): the call renders the frame's rows y with (y / band_rows) % band_period == band_phase;
+    // th counts those rows and local row ly is the ly-th of them (frame_row).  band_rows == 0: the rectangle x0, y0, tw, th.
+    uint32_t band_rows, band_period, band_phase;
 };
+
+// local row of the call's rectangle (or of its row bands, in order) -> row of the frame.  band_rows is a multiple of four, so
+// the four rows of an 8x4 tile stay adjacent
+__host__ __device__ __forceinline__ uint32_t frame_row(const FrameParams& fp, uint32_t ly) {
+    if (!fp.band_rows) return fp.y0 + ly;
+    const uint32_t b = ly / fp.band_rows;
+    return (b * fp.band_period + fp.band_phase) * fp.band_rows + (ly - b * fp.band_rows);
+}
 
 struct FrameCounters {                  // device memory, reset at the start of every frame
     unsigned long long primary, primary_hits, shadow, shadow_hits, secondary, secondary_hits;
@@ -183,7 +194,7 @@ __device__ __forceinline__ void primary_sample(const DScene& sc, const FramePara
 __device__ __forceinline__ bool level0_pixel(const FrameParams& fp, uint32_t j, uint32_t& x, uint32_t& y) {
     const uint32_t tile = j >> 5, l = j & 31u;
     const uint32_t lx = (tile % fp.tiles_x) * 8u + (l & 7u), ly = (tile / fp.tiles_x) * 4u + (l >> 3);
-    x = fp.x0 + lx; y = fp.y0 + ly;
+    x = fp.x0 + lx; y = frame_row(fp, ly);
     return lx < fp.tw && ly < fp.th;
 }
 

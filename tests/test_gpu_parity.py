@@ -683,6 +683,75 @@ def test_peer_combine_equals_single_gpu_frame(rt, size):
         g.close()
 
 
+@pytest.mark.parametrize("flags_name", ["exact", "accelerated"])
+def test_row_bands_in_one_call_tile_the_frame(rt, flags_name):
+    """rt_params.band_rows / band_period / band_phase (the reference's bucket rows, render/tile/bucket.hpp:7-21, dealt
+    round-robin to N ranks): ONE call per rank renders all of the rank's bands, touches no other row, and the N device frames
+    add up to the whole-frame render bit for bit - 1 spp, multi-sample GI in several passes, a frame height that is no multiple
+    of the band, and the band-by-band rectangles give the same rows."""
+    import torch
+    flags = rt.FLAG_ORDERED if flags_name == "accelerated" else 0
+    for size, band, world, kw in (((320, 180), 16, 3, dict(max_ray_depth=5)),
+                                  ((322, 182), 8, 4, dict(max_ray_depth=3, samples_per_pixel=4, diffuse_reflection_ray_count=1))):
+        s, _ = gpu_scene(rt, "hw11_scene8", size=size)
+        H, W = size[1], size[0]
+        want = s.render_frame(rt.default_params(flags=flags, **kw))
+        total = np.zeros((H, W, 3), np.float32)
+        for r in range(world):
+            fb = torch.full((H, W, 3), -7.0, dtype=torch.float32, device="cuda")
+            s.render_frame_device(rt.default_params(flags=flags, band_rows=band, band_period=world, band_phase=r, **kw), fb.data_ptr(),
+                                  stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = fb.cpu().numpy()
+            mine = np.zeros(H, bool)
+            for y0, y1 in rt.row_bands(H, band, r, world):
+                mine[y0:y1] = True
+            assert np.all(got[~mine] == -7.0)                                  # rows of other ranks are not touched
+            assert np.array_equal(got[mine].view(np.uint32), want[mine].view(np.uint32))
+            total[mine] = got[mine]
+        assert np.array_equal(total.view(np.uint32), want.view(np.uint32))
+    s, _ = gpu_scene(rt, "hw11_scene8", size=(320, 180))
+    fb = torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda")
+    for bad in (dict(band_rows=6, band_period=2, band_phase=0), dict(band_rows=8, band_period=0, band_phase=0), dict(band_rows=8, band_period=2, band_phase=2),
+                dict(band_rows=8, band_period=2, band_phase=0, y0=8), dict(band_rows=64, band_period=8, band_phase=5)):
+        with pytest.raises(rt.RtError) as e:
+            s.render_frame_device(rt.default_params(**bad), fb.data_ptr())
+        assert e.value.status == rt.RT_ERR_BAD_ARG
+    with pytest.raises(rt.RtError):
+        s.render_frame(rt.default_params(band_rows=8, band_period=2, band_phase=0))     # host images take rectangles only
+
+
+def test_peer_wait_is_bounded(rt, monkeypatch):
+    """a peer that never signals does not leave the GPU spinning: the waiting kernels give up after RT_B200_PEER_TIMEOUT_MS,
+    the stream drains, and the group reports RT_ERR_TIMEOUT (here and at every later call)"""
+    import time
+    import torch
+    size = (64, 36)
+    s, _ = gpu_scene(rt, "hw11_scene8", size=size)
+    st = torch.cuda.current_stream().cuda_stream
+    for gather in ("ce", "kernel"):
+        monkeypatch.setenv("RT_B200_PEER_TIMEOUT_MS", "250")
+        groups = [rt.PeerGroup(2, r, 0, size[0], size[1]) for r in range(2)]
+        rt.PeerGroup.connect_local(groups)
+        s.render_frame_device(rt.default_params(samples_per_pixel=1, spp_total=2, flags=rt.FLAG_RAW_SUM), groups[0].framebuffer, stream=st)
+        groups[0].signal_ready(st)                          # rank 1 never renders, never signals
+        groups[0].reduce_resolve(2, stream=st)
+        t0 = time.perf_counter()
+        with pytest.raises(rt.RtError) as e:
+            groups[0].read_result(st)
+        assert e.value.status == rt.RT_ERR_TIMEOUT
+        assert 0.2 <= time.perf_counter() - t0 < 5.0
+        with pytest.raises(rt.RtError) as e:
+            groups[0].wait_done(st)
+        assert e.value.status == rt.RT_ERR_TIMEOUT
+        for g in groups:
+            g.close()
+        if gather == "ce":
+            break                                           # the gather mode is fixed per process (RT_B200_PEER_GATHER); one pass covers the default
+    img = s.render_frame(rt.default_params())               # the device is fine afterwards
+    assert np.isfinite(img).all()
+
+
 def test_peer_combine_into_the_shared_host_frame(rt):
     """rt_peer_host_result_attach: every rank maps and pins the same POSIX shared-memory frame and stores ITS slice of the
     combined frame straight into it (RT_PEER_OUT_HOST_RGB), so N PCIe links carry the frame and nobody downloads it.  Emulated
