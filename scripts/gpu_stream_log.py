@@ -6,7 +6,7 @@ import ctypes as C, gzip, importlib, os, sys
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, REPO)
 rt = importlib.import_module("simd-raytracer_b200")
-NW = 444 * 8
+NW = 740 * 4
 def report(tag):
     out = (C.c_ulonglong * (NW * 4))()
     rt.lib.rt_debug_stream_log(out, NW)
@@ -20,6 +20,12 @@ def report(tag):
     for frac in (0.5, 0.6, 0.7, 0.8, 0.9):
         print(f"   warps still running at {int(frac*100)} % of the kernel: {(end > frac * total).sum():5d}   (mean queries of those {a[end > frac*total, 2].mean() if (end > frac*total).any() else 0:.1f}, slots {a[end > frac*total, 3].mean() if (end > frac*total).any() else 0:.0f})")
     print(f"   mean queries per warp {a[:,2].mean():.1f}, mean node-step slots per warp {a[:,3].mean():.0f}, max slots {a[:,3].max()}, mean busy time {np.mean(end-start):.1f} us")
+for name, depth in (("hw15_scene2", 5), ("hw11_scene8", 10)):          # configs 1 and 3: the shadow kernel of frames with many levels
+    sx = rt.Scene.from_rtsc(gzip.open(os.path.join(REPO, f"tests/golden/scenes/{name}.rtsc.gz")).read(), device=0)
+    px = rt.default_params(flags=rt.FLAG_ORDERED, max_ray_depth=depth)
+    for _ in range(3): sx.render_frame(px)
+    report(f"{name} depth {depth}: shadow kernel")
+    sx.close()
 data = gzip.open(os.path.join(REPO, "tests/golden/scenes/hw09_scene5.rtsc.gz")).read()
 # shadow kernel last
 s = rt.Scene.from_rtsc(data, device=0)
