@@ -831,10 +831,12 @@ def main() -> None:
         if t_e2e_rgb8 is not None:
             e2e_main_t, e2e_main_bytes = t_e2e_rgb8, int(host.numel())
             e2e_main_api = ("rt_render_frame_rgb8_begin + rt_frame_wait (frame sequence: params in, the 8-bit frame of io/image/ppm.hpp:17-19 - "
-                            "what the reference's main.cpp writes - out to pinned host memory every step, quantised on the device; frame i's "
-                            "download overlaps frame i+1's render; the frames were verified against rt_render_frame_rgb8)")
+                            "what the reference's main.cpp writes - out to pinned host memory every step, quantised on the device; two frames "
+                            "in flight: they render on two streams into two pool sets, so frame i's thinning launches and its download run "
+                            "under frame i+1's render - which is why a frame of the sequence can cost less than ms_per_step, the time of "
+                            "one frame alone on the GPU; the frames were verified against rt_render_frame_rgb8)")
         float_api = ("rt_render_frame_begin + rt_frame_wait (frame sequence: params in, float frame out to pinned host memory "
-                     "every step; frame i's download overlaps frame i+1's render)" if world == 1 else
+                     "every step; two frames in flight on two streams and pool sets, frame i's download overlaps frame i+1's render)" if world == 1 else
                      ("rt_render_frame_device_begin per rank, rt_peer_* combine on a second stream (overlaps frame i+1's render) "
                       "with RT_PEER_OUT_HOST_RGB: every rank copies its slice of the combined float frame into the shared pinned "
                       "host frame over its own PCIe link (rt_peer_host_result_attach); d2h_bytes_per_step is the sum over ranks"

@@ -129,11 +129,19 @@ struct rt_scene {
     std::vector<void*> owned;        // device allocations of the resident scene
 
     // wavefront pools (grow-only, reused across frames)
-    DBuf<Ray> rays; DBuf<Hit> hits; DBuf<Rec> recs; DBuf<ShadowJob> jobs;
-    DBuf<uint32_t> tiles0;           // sparse level 0: the tiles k_tile_cull kept
-    DBuf<uint32_t> mask0;            // sparse level 0: one word per 8x4 pixel tile, bit = the camera ray hit something; zero between passes
-    PassState* ps = nullptr;
-    FrameCounters* fc = nullptr;
+    // Everything a frame in flight writes on the device besides its framebuffer.  Two sets: the two frames of a sequence that are
+    // in flight (rt_render_frame_begin) render on two streams into their own set, so that one frame's thinning launches - a
+    // persistent grid ends when its longest queries end, profiles/r2_stream_tails.txt - run under the other frame's full ones.
+    // `w` is the set the launch helpers below work on; every synchronous call uses set 0.
+    struct Pools {
+        DBuf<Ray> rays; DBuf<Hit> hits; DBuf<Rec> recs; DBuf<ShadowJob> jobs;
+        DBuf<uint32_t> tiles0;       // sparse level 0: the tiles k_tile_cull kept
+        DBuf<uint32_t> mask0;        // sparse level 0: one word per 8x4 pixel tile, bit = the camera ray hit something; zero between passes
+        PassState* ps = nullptr;
+        FrameCounters* fc = nullptr;
+    } pools[2];
+    Pools* w = &pools[0];
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};   // render streams of the two sequence slots (frames queued on the scene's own stream)
     uint32_t* h_flags = nullptr;     // pinned: 4 words per pass of the frame being rendered (k_pass_commit): pool_count, shadow_count, overflow, levels
     size_t h_flags_passes = 0;
     FrameCounters* h_fc = nullptr;   // pinned
@@ -155,7 +163,9 @@ struct rt_scene {
         rt_params params{}, key{};
         float* host_rgb = nullptr;       // download target (frame sequences to the host), or null
         float* target = nullptr;         // device frame the slot renders into: its own `fb`, or the caller's (rt_render_frame_device_begin)
-        cudaStream_t stream = nullptr;
+        cudaStream_t stream = nullptr;   // the stream the frame renders on
+        cudaStream_t asked = nullptr;    // the stream the caller queued it on (the scene's own: `stream` is the slot's render stream)
+        int pool = 0;                    // the pool set it uses
         bool rerendered = false;         // the frame overflowed its pools when first queued and was rendered again at wait time
         uint64_t n0 = 0;
         uint32_t launches = 0;
@@ -185,6 +195,7 @@ struct rt_scene {
         if (device >= 0) {
             cudaSetDevice(device);
             if (stream) cudaStreamSynchronize(stream);
+            for (cudaStream_t t : slot_stream) if (t) cudaStreamSynchronize(t);
             for (void* p : owned) cudaFree(p);
             if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
             for (SeqSlot& q : seq) {
@@ -193,10 +204,14 @@ struct rt_scene {
                 if (q.h_fc) cudaFreeHost(q.h_fc);
                 q.fb.release(); q.fb8.release();
             }
-            rays.release(); hits.release(); recs.release(); jobs.release(); mask0.release(); tiles0.release(); fb.release(); fb8.release();
+            for (Pools& q : pools) {
+                q.rays.release(); q.hits.release(); q.recs.release(); q.jobs.release(); q.mask0.release(); q.tiles0.release();
+                if (q.ps) cudaFree(q.ps);
+                if (q.fc) cudaFree(q.fc);
+            }
+            for (cudaStream_t t : slot_stream) if (t) cudaStreamDestroy(t);
+            fb.release(); fb8.release();
             q_rays.release(); q_maxt.release(); q_hits.release(); q_occ.release();
-            if (ps) cudaFree(ps);
-            if (fc) cudaFree(fc);
             if (h_flags) cudaFreeHost(h_flags);
             if (h_fc) cudaFreeHost(h_fc);
             for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
@@ -407,8 +422,10 @@ void upload_scene(rt_scene* s) {
     std::memcpy(d.root_max, s->geom.root_max, 12);
     d.has_transmissive = L.has_transmissive ? 1 : 0;
 
-    CK(cudaMalloc(&s->ps, sizeof(PassState)));
-    CK(cudaMalloc(&s->fc, sizeof(FrameCounters)));
+    for (rt_scene::Pools& q : s->pools) {
+        CK(cudaMalloc(&q.ps, sizeof(PassState)));
+        CK(cudaMalloc(&q.fc, sizeof(FrameCounters)));
+    }
     CK(cudaMallocHost(&s->h_flags, 4 * sizeof(uint32_t)));
     s->h_flags_passes = 1;
     CK(cudaMallocHost(&s->h_fc, sizeof(FrameCounters)));
@@ -781,7 +798,7 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     const uint32_t launched = P.launched, levels = P.levels;
     const uint32_t n0 = fp.plane * fp.n_samples;
     int slot = 0;
-    launch_k(k_pass_init, 1, 256, st, s->ps, n0, P.first_of_frame);
+    launch_k(k_pass_init, 1, 256, st, s->w->ps, n0, P.first_of_frame);
     CK(cudaGetLastError());
     // a camera outside the scene's root box: tiles whose rays cannot reach the box are finished by k_tile_cull (rt_stream.cuh)
     bool cull_tiles = false;
@@ -789,31 +806,31 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         for (int k = 0; k < 3; ++k) cull_tiles = cull_tiles || !(s->d.root_min[k] <= s->d.cam_pos[k] && s->d.cam_pos[k] <= s->d.root_max[k]);
     if (cull_tiles)
         launch(TC_PRIMARY, [&] {
-            launch_k(k_tile_cull, std::min<unsigned>((fp.plane / 32 + 255) / 256, unsigned(s->g_resolve)), 256, st, s->d, fp, miss_fb, P.divide, s->ps, s->tiles0.p);
+            launch_k(k_tile_cull, std::min<unsigned>((fp.plane / 32 + 255) / 256, unsigned(s->g_resolve)), 256, st, s->d, fp, miss_fb, P.divide, s->w->ps, s->w->tiles0.p);
         });
     launch(TC_PRIMARY, [&] {
         if (fp.sparse0) {
-            const uint32_t* tiles = cull_tiles ? s->tiles0.p : nullptr;
-            STREAM_LAUNCH(k_stream_primary_sparse, s->gs_sparse[fi], s->d, fp, s->rays.p, s->hits.p, s->mask0.p, miss_fb, P.divide, s->ps, slot, tiles);
+            const uint32_t* tiles = cull_tiles ? s->w->tiles0.p : nullptr;
+            STREAM_LAUNCH(k_stream_primary_sparse, s->gs_sparse[fi], s->d, fp, s->w->rays.p, s->w->hits.p, s->w->mask0.p, miss_fb, P.divide, s->w->ps, slot, tiles);
         } else if (m.ordered) {
-            STREAM_LAUNCH(k_stream_primary, s->gs_primary[fi], s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-        } else if (m.fast) launch_k(k_primary<true, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
-        else launch_k(k_primary<false, false>, s->g_primary[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, slot);
+            STREAM_LAUNCH(k_stream_primary, s->gs_primary[fi], s->d, fp, s->w->rays.p, s->w->hits.p, s->w->ps, slot);
+        } else if (m.fast) launch_k(k_primary<true, false>, s->g_primary[mi], 256, st, s->d, fp, s->w->rays.p, s->w->hits.p, s->w->ps, slot);
+        else launch_k(k_primary<false, false>, s->g_primary[mi], 256, st, s->d, fp, s->w->rays.p, s->w->hits.p, s->w->ps, slot);
     });
     ++slot;
     for (uint32_t lvl = 0; lvl < launched; ++lvl) {
         if (lvl > 0) {
             launch(TC_SECONDARY, [&] {
                 if (m.ordered) {
-                    STREAM_LAUNCH(k_stream_level, s->gs_level[fi], s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                } else if (m.fast) launch_k(k_trace_level<true, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
-                else launch_k(k_trace_level<false, false>, s->g_trace[mi], 256, st, s->d, fp, s->rays.p, s->hits.p, s->ps, int(lvl), slot);
+                    STREAM_LAUNCH(k_stream_level, s->gs_level[fi], s->d, fp, s->w->rays.p, s->w->hits.p, s->w->ps, int(lvl), slot);
+                } else if (m.fast) launch_k(k_trace_level<true, false>, s->g_trace[mi], 256, st, s->d, fp, s->w->rays.p, s->w->hits.p, s->w->ps, int(lvl), slot);
+                else launch_k(k_trace_level<false, false>, s->g_trace[mi], 256, st, s->d, fp, s->w->rays.p, s->w->hits.p, s->w->ps, int(lvl), slot);
             });
             ++slot;
         }
         launch(TC_SHADE, [&] {
-            if (has_gi) launch_k(k_shade<true>, s->g_shade[1], 256, st, s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
-            else launch_k(k_shade<false>, s->g_shade[0], 256, st, s->d, fp, s->rays.p, s->hits.p, s->recs.p, s->jobs.p, s->ps, int(lvl), slot, s->mask0.p);
+            if (has_gi) launch_k(k_shade<true>, s->g_shade[1], 256, st, s->d, fp, s->w->rays.p, s->w->hits.p, s->w->recs.p, s->w->jobs.p, s->w->ps, int(lvl), slot, s->w->mask0.p);
+            else launch_k(k_shade<false>, s->g_shade[0], 256, st, s->d, fp, s->w->rays.p, s->w->hits.p, s->w->recs.p, s->w->jobs.p, s->w->ps, int(lvl), slot, s->w->mask0.p);
         });
         ++slot;
     }
@@ -821,14 +838,14 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
         launch(TC_SHADOW, [&] {
             if (m.ordered) {
                 const int g = s->gs_shadow[fi * 2 + tr];
-                if (tr) { STREAM_LAUNCH_T(k_stream_shadow, true, g, s->d, fp, s->jobs.p, s->ps, slot); }
-                else { STREAM_LAUNCH_T(k_stream_shadow, false, g, s->d, fp, s->jobs.p, s->ps, slot); }
+                if (tr) { STREAM_LAUNCH_T(k_stream_shadow, true, g, s->d, fp, s->w->jobs.p, s->w->ps, slot); }
+                else { STREAM_LAUNCH_T(k_stream_shadow, false, g, s->d, fp, s->w->jobs.p, s->w->ps, slot); }
             } else {
                 const int g = s->g_shadow[mi * 2 + tr];
-                if (tr) { if (m.fast) launch_k(k_shadow<true, true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
-                          else launch_k(k_shadow<true, false, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
-                else { if (m.fast) launch_k(k_shadow<false, true, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot);
-                       else launch_k(k_shadow<false, false, false>, g, 256, st, s->d, fp, s->jobs.p, s->ps, slot); }
+                if (tr) { if (m.fast) launch_k(k_shadow<true, true, false>, g, 256, st, s->d, fp, s->w->jobs.p, s->w->ps, slot);
+                          else launch_k(k_shadow<true, false, false>, g, 256, st, s->d, fp, s->w->jobs.p, s->w->ps, slot); }
+                else { if (m.fast) launch_k(k_shadow<false, true, false>, g, 256, st, s->d, fp, s->w->jobs.p, s->w->ps, slot);
+                       else launch_k(k_shadow<false, false, false>, g, 256, st, s->d, fp, s->w->jobs.p, s->w->ps, slot); }
             }
         });
         ++slot;
@@ -836,19 +853,19 @@ void enqueue_pass(rt_scene* s, const PassLaunch& P, float* d_rgb, uint32_t* h_fl
     for (int lvl = int(launched) - 1; lvl >= 0; --lvl) {
         launch(TC_RESOLVE, [&] {
             if (lvl == 0 && fuse_acc)
-                launch_k(k_resolve<true>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
-                                                              launched, levels, s->mask0.p);
+                launch_k(k_resolve<true>, s->g_resolve, 256, st, s->d, fp, s->w->recs.p, s->w->jobs.p, s->w->ps, lvl, slot, d_rgb, P.first_pass, P.divide,
+                                                              launched, levels, s->w->mask0.p);
             else
-                launch_k(k_resolve<false>, s->g_resolve, 256, st, s->d, fp, s->recs.p, s->jobs.p, s->ps, lvl, slot, nullptr, 0, 0, launched, levels, s->mask0.p);
+                launch_k(k_resolve<false>, s->g_resolve, 256, st, s->d, fp, s->w->recs.p, s->w->jobs.p, s->w->ps, lvl, slot, nullptr, 0, 0, launched, levels, s->w->mask0.p);
         });
         ++slot;
     }
-    launch_k(k_pass_commit, 1, 1, st, s->ps, s->fc, h_flags, launched, levels);
+    launch_k(k_pass_commit, 1, 1, st, s->w->ps, s->w->fc, h_flags, launched, levels);
     CK(cudaGetLastError());
     // the accumulate kernel skips itself on the device when the pass overflowed its pools
     if (!fuse_acc)
         launch(TC_RESOLVE, [&] {
-            launch_k(k_accumulate, (fp.plane + 255) / 256, 256, st, s->d, fp, s->recs.p, d_rgb, s->ps, P.first_pass, P.divide, s->mask0.p);
+            launch_k(k_accumulate, (fp.plane + 255) / 256, 256, st, s->d, fp, s->w->recs.p, d_rgb, s->w->ps, P.first_pass, P.divide, s->w->mask0.p);
         });
 }
 
@@ -859,16 +876,16 @@ void reserve_pools(rt_scene* s, FrameParams& fp, uint64_t n0, uint32_t levels) {
     if (pool_cap >= (1ull << 32) || shadow_cap >= (1ull << 32)) throw rt_error(RT_ERR_OOM, "wavefront pool exceeds 2^32 entries; lower samples per pass");
     // a pool that has to grow is freed and allocated again: frames still in flight (a queued frame of a sequence) use the old
     // one, so wait for them explicitly instead of leaning on cudaFree's implicit device synchronisation
-    if (pool_cap > s->rays.cap || shadow_cap > s->jobs.cap || n0 / 32 + 1 > s->tiles0.cap || n0 / 32 + 1 > s->mask0.cap) CK(cudaDeviceSynchronize());
-    s->rays.reserve(pool_cap); s->hits.reserve(pool_cap); s->recs.reserve(pool_cap); s->jobs.reserve(shadow_cap);
-    s->tiles0.reserve(n0 / 32 + 1);
-    if (s->mask0.cap < n0 / 32 + 1) {
-        s->mask0.reserve(n0 / 32 + 1);
-        CK(cudaMemset(s->mask0.p, 0, s->mask0.cap * sizeof(uint32_t)));
+    if (pool_cap > s->w->rays.cap || shadow_cap > s->w->jobs.cap || n0 / 32 + 1 > s->w->tiles0.cap || n0 / 32 + 1 > s->w->mask0.cap) CK(cudaDeviceSynchronize());
+    s->w->rays.reserve(pool_cap); s->w->hits.reserve(pool_cap); s->w->recs.reserve(pool_cap); s->w->jobs.reserve(shadow_cap);
+    s->w->tiles0.reserve(n0 / 32 + 1);
+    if (s->w->mask0.cap < n0 / 32 + 1) {
+        s->w->mask0.reserve(n0 / 32 + 1);
+        CK(cudaMemset(s->w->mask0.p, 0, s->w->mask0.cap * sizeof(uint32_t)));
         CK(cudaDeviceSynchronize());                      // the render streams do not synchronise with the null stream
     }
-    fp.pool_cap = uint32_t(std::min<uint64_t>(s->rays.cap, 0xFFFFFFFFull));
-    fp.shadow_cap = uint32_t(std::min<uint64_t>(s->jobs.cap, 0xFFFFFFFFull));
+    fp.pool_cap = uint32_t(std::min<uint64_t>(s->w->rays.cap, 0xFFFFFFFFull));
+    fp.shadow_cap = uint32_t(std::min<uint64_t>(s->w->jobs.cap, 0xFFFFFFFFull));
 }
 
 // a truncated pass reports lower bounds of what it needed: grow past them (the pass is deterministic and is rendered again)
@@ -931,12 +948,12 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     const uint32_t levels = level_count(s, p);
     const bool raw = (p.flags & RT_FLAG_RAW_SUM) != 0;
 
-    if (drain) drain_sequence(s);                 // frames of a sequence still in flight use the same pools
+    if (drain) { drain_sequence(s); s->w = &s->pools[0]; }   // frames of a sequence still in flight use the pools
     // finish the bookkeeping of the previous frame before its events are reused
     fetch_counters(s);
     s->events_used = 0; s->spans.clear();
     s->launches = 0; s->passes = 0; s->pool_hwm = 0; s->shadow_hwm = 0;
-    CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
+    CK(cudaMemsetAsync(s->w->fc, 0, sizeof(FrameCounters), st));
     CK(cudaEventRecord(s->frame_a, st));
 
     const uint32_t spp = p.samples_per_pixel;
@@ -997,7 +1014,7 @@ void render_device(rt_scene* s, const rt_params& p, float* d_rgb, cudaStream_t s
     }
     if (s->levels_hint == 0 || levels_seen > s->levels_hint) s->levels_hint = std::max<uint32_t>(levels_seen, 1);
     CK(cudaEventRecord(s->frame_b, st));
-    CK(cudaMemcpyAsync(s->h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_fc, s->w->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s->frame_c, st));
     s->counters_pending = true;
 }
@@ -1049,7 +1066,8 @@ void finalize_slot(rt_scene* s, int k) {
     }
     if (bad < q.n_passes) {
         grow_pools_after_overflow(s, q.h_flags + 4 * size_t(bad), q.n0);
-        CK(cudaStreamSynchronize(q.stream));                   // the other frame in flight uses the pools that are about to grow
+        CK(cudaStreamSynchronize(q.stream));                   // (frames that share this set: the pools are about to grow)
+        s->w = &s->pools[q.pool];
         render_device(s, q.params, q.target, q.stream, false);
         if (q.host_rgb) copy_rect_to_host(s, rect_of(s, q.params), q.target, q.host_rgb, q.stream);
         if (q.host_rgb8) {
@@ -1083,14 +1101,29 @@ void drain_sequence(rt_scene* s) {
 }
 
 // rgb / rgb8: host frame to download into (frame sequences) or null; d_ext: the caller's device frame or null (then the slot's own)
+// RT_B200_SEQ_OVERLAP=0: the two frames of a sequence share one stream and one pool set (A/B runs)
+bool sequence_overlap() {
+    static const bool on = [] { const char* e = std::getenv("RT_B200_SEQ_OVERLAP"); return !(e && std::atoi(e) == 0); }();
+    return on;
+}
+
 void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cudaStream_t st, uint64_t* ticket, uint8_t* rgb8 = nullptr) {
     check_params(p);
     if (rgb || rgb8) forbid_bands(p);
     const Rect rect = rect_of(s, p);
-    // every queued frame of a scene shares its wavefront pools, pass state and counters: two frames in flight on DIFFERENT
-    // streams would race on them
+    // the frames a caller queues on ITS stream are ordered by that stream and share pool set 0: two of them in flight on
+    // different streams would race on it
     for (const rt_scene::SeqSlot& o : s->seq)
-        if (o.in_flight && o.stream != st) throw rt_error(RT_ERR_BAD_ARG, "all queued frames of a scene must use the same stream");
+        if (o.in_flight && o.asked != st) throw rt_error(RT_ERR_BAD_ARG, "all queued frames of a scene must use the same stream");
+    const cudaStream_t asked = st;
+    const int slot = int(s->seq_issued & 1);
+    // frames queued on the scene's own stream are independent of anything the caller does: the two slots render on two streams
+    // into two pool sets, and a frame's tail overlaps the next frame's start
+    const bool overlap = st == s->stream && sequence_overlap();
+    if (overlap) {
+        if (!s->slot_stream[slot]) CK(cudaStreamCreateWithFlags(&s->slot_stream[slot], cudaStreamNonBlocking));
+        st = s->slot_stream[slot];
+    }
     if (!s->copy_stream) {
         CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
         for (rt_scene::SeqSlot& q : s->seq) {
@@ -1106,6 +1139,7 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
     const int k = int(s->seq_issued & 1);
     rt_scene::SeqSlot& q = s->seq[k];
     finalize_slot(s, k);                                       // the frame two tickets back (normally long complete)
+    s->w = &s->pools[overlap ? slot : 0];                      // (after it: a frame that has to be rendered again uses its own set)
     if (!d_ext) q.fb.reserve(size_t(s->host.width) * s->host.height * 3);
     if (rgb8) q.fb8.reserve(size_t(s->host.width) * s->host.height * 3);
     float* const target = d_ext ? d_ext : q.fb.p;
@@ -1132,7 +1166,7 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
         reserve_pools(s, fp, n0, levels);
         uint32_t launches = 0;
         if (q.used) CK(cudaStreamWaitEvent(st, q.copied, 0));   // the device frame of this slot has been downloaded
-        CK(cudaMemsetAsync(s->fc, 0, sizeof(FrameCounters), st));
+        CK(cudaMemsetAsync(s->w->fc, 0, sizeof(FrameCounters), st));
         CK(cudaEventRecord(q.a, st));
         for (uint32_t k = 0; k < n_passes; ++k) {
             const uint32_t done = k * per_pass, ns = std::min(per_pass, spp - done);
@@ -1143,7 +1177,7 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
             enqueue_pass(s, P, target, q.h_flags + 4 * size_t(k), st, [&](int, auto&& launch) { launch(); CK(cudaGetLastError()); ++launches; });
         }
         CK(cudaEventRecord(q.b, st));
-        CK(cudaMemcpyAsync(q.h_fc, s->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(q.h_fc, s->w->fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
         q.deferred = true; q.params = p; q.key = key; q.n0 = n0; q.launches = launches; q.n_passes = n_passes; q.per_pass = per_pass;
     }
     if (rgb8) quantise_rows(s, rect, target, q.fb8.p, st);     // 6.2 MB instead of 24.9 MB over PCIe for a 1080p frame
@@ -1156,7 +1190,7 @@ void begin_frame(rt_scene* s, const rt_params& p, float* rgb, float* d_ext, cuda
     } else {
         CK(cudaEventRecord(q.copied, st));                     // "complete" = rendered
     }
-    q.host_rgb = rgb; q.host_rgb8 = rgb8; q.target = target; q.stream = st; q.in_flight = true; q.used = true;
+    q.host_rgb = rgb; q.host_rgb8 = rgb8; q.target = target; q.stream = st; q.asked = asked; q.pool = overlap ? slot : 0; q.in_flight = true; q.used = true;
     *ticket = s->seq_issued++;
 }
 
