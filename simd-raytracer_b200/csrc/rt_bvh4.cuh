@@ -42,6 +42,10 @@ constexpr uint32_t BVH4_MAX_REF = 0x1FFFFFFDu;  // ref lives in 29 bits; BVH_SKI
 // (bvh4_stack_need, a few dozen) and scene creation refuses a tree that would need more.
 constexpr int BVH4_STACK = 3 * 44 + 4;
 
+#ifndef RT_BVH4_LOAD256
+#define RT_BVH4_LOAD256 1                // fetch a node with four 256-bit loads (rt_tri.cuh kd_load_row_pair) instead of seven 128-bit ones
+#endif
+
 RT_HD uint32_t bvh4_child(uint32_t ref, uint32_t cnt) { return (ref << 3) | cnt; }
 
 struct Bvh4ArrayStack {
@@ -80,9 +84,15 @@ RT_HD void bvh4_node_step(BvhState& s, Stack& stack, const float* __restrict__ n
     if (!pop) {
         BVH_COUNT_NODE();
         const float* p = nodes + size_t(s.ref) * BVH4_NODE_FLOATS;
+#if RT_BVH4_LOAD256
+        KdRow lox, loy, loz, hix, hiy, hiz, cc, unused;
+        kd_load_row_pair(p, lox, loy); kd_load_row_pair(p + 8, loz, hix); kd_load_row_pair(p + 16, hiy, hiz); kd_load_row_pair(p + 24, cc, unused);
+        (void)unused;
+#else
         const KdRow lox = kd_load_row(p), loy = kd_load_row(p + 4), loz = kd_load_row(p + 8);
         const KdRow hix = kd_load_row(p + 12), hiy = kd_load_row(p + 16), hiz = kd_load_row(p + 20);
         const KdRow cc = kd_load_row(p + 24);
+#endif
         const float ix = kd_rcp_estimate(s.dx), iy = kd_rcp_estimate(s.dy), iz = kd_rcp_estimate(s.dz);
         const float cx = -(s.ox * ix), cy = -(s.oy * iy), cz = -(s.oz * iz);
         const uint32_t c0 = uint32_t(kd_as_int(cc.x)), c1 = uint32_t(kd_as_int(cc.y)), c2 = uint32_t(kd_as_int(cc.z)), c3 = uint32_t(kd_as_int(cc.w));

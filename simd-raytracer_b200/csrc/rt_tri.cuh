@@ -124,6 +124,18 @@ RT_HD KdRow kd_load_row(const float* p) {
     return KdRow{p[0], p[1], p[2], p[3]};
 #endif
 }
+// two adjacent 16-byte rows with ONE 256-bit load (sm_100: LDG.E.256; p must be 32-byte aligned).  A lane's rows of a node sit
+// in one cache line, but every load instruction of a warp whose lanes stand at different nodes costs one L1 wavefront per lane:
+// fetching a 128-byte node as four 256-bit loads instead of seven 128-bit ones nearly halves the node traffic through L1, which
+// is what bounds the traversal of scenes beyond L2.
+RT_HD void kd_load_row_pair(const float* p, KdRow& a, KdRow& b) {
+#if defined(__CUDA_ARCH__)
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = KdRow{p[0], p[1], p[2], p[3]}; b = KdRow{p[4], p[5], p[6], p[7]};
+#endif
+}
 RT_HD int kd_as_int(float f) {
 #if defined(__CUDA_ARCH__)
     return __float_as_int(f);
