@@ -233,7 +233,10 @@ RT_API int rt_render_frame_rgb8(rt_scene* s, const rt_params* p, uint8_t* rgb8);
  * render_frame per camera pose / parameter set, src/main.cpp:13-25).  rt_render_frame_begin renders the frame into one of two
  * device frames and queues its download into `rgb` on a copy stream, so frame i's PCIe transfer overlaps frame i+1's render;
  * rt_frame_wait blocks until `rgb` of that ticket is complete.  `rgb` should be pinned for the overlap to take place and must
- * stay valid until waited for.  Frames complete in ticket order.                                                   */
+ * stay valid until waited for.  At most two frames are in flight (a third rt_*_begin waits for the older one); they render on
+ * two internal streams into two sets of wavefront pools, so one frame's last, thinning launches run under the next frame's
+ * first ones - a frame of a sequence costs less than a frame alone - and nothing orders their completion
+ * but rt_frame_wait.                                                                                              */
 RT_API int rt_render_frame_begin(rt_scene* s, const rt_params* p, float* rgb, uint64_t* ticket);
 RT_API int rt_frame_wait(rt_scene* s, uint64_t ticket);
 /* The same sequence with the PPM writer's quantisation (io/image/ppm.hpp:17-19) fused on the device: the frame that crosses PCIe
@@ -242,9 +245,10 @@ RT_API int rt_render_frame_rgb8_begin(rt_scene* s, const rt_params* p, uint8_t* 
 /* page-locked host memory for the frames of a sequence, for hosts that do not link the CUDA runtime themselves */
 RT_API void* rt_alloc_pinned(uint64_t bytes);           /* null on failure */
 RT_API void rt_free_pinned(void* p);
-/* The same queued render into the CALLER's device frame (no download), asynchronous on `stream` (all queued frames of a
- * scene must use the same stream).  Work queued behind it on that stream (a peer combine, a copy) runs without a host round
- * trip.  rt_frame_wait then returns RT_OK, or RT_FRAME_RERENDERED when the queued attempt outgrew the wavefront pools (first
+/* The same queued render into the CALLER's device frame (no download), asynchronous on `stream`.  All frames of a scene that are
+ * in flight must have been queued on the same stream (RT_ERR_BAD_ARG otherwise): frames on a caller's stream are ordered by it
+ * and share one set of pools; null = the scene's own streams, as above.  Work queued behind the frame on `stream` (a peer
+ * combine, a copy) runs without a host round trip.  rt_frame_wait then returns RT_OK, or RT_FRAME_RERENDERED when the queued attempt outgrew the wavefront pools (first
  * frames of a scene): d_rgb has been rendered again and is correct now, but whatever consumed it before must be redone.      */
 RT_API int rt_render_frame_device_begin(rt_scene* s, const rt_params* p, float* d_rgb, void* stream, uint64_t* ticket);
 /* device framebuffer (for the multi-GPU combine): d_rgb = height*width*3 floats in HBM; asynchronous on stream */
