@@ -902,7 +902,8 @@ def main() -> None:
                       "device_bytes": int(scene.info.device_bytes), "host_build_s": round(t_build, 3),
                       "accel_build": "device" if int(scene.info.accel_build) == rt.ACCEL_BUILD_DEVICE else "host",
                       "accel_build_s": round(float(scene.info.accel_build_seconds), 4),
-                      "kd_build_s": round(float(scene.info.build_seconds), 3), "bvh4_stack_need": int(scene.info.bvh4_stack_need)},
+                      "kd_build_s": round(float(scene.info.build_seconds), 3), "bvh4_stack_need": int(scene.info.bvh4_stack_need),
+                      "bvh_leaf_size": int(scene.info.bvh_leaf_size)},
         }
         if world == 1 and not args.no_cpu_baseline:
             if w.get("synthetic"):

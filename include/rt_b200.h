@@ -155,7 +155,7 @@ typedef struct rt_scene_info {
     uint64_t device_bytes;           /* resident scene bytes in HBM */
     double build_seconds, flatten_seconds, upload_seconds;
     int32_t device;
-    uint32_t reserved1;
+    uint32_t bvh_leaf_size;          /* most triangles per leaf of the backend's hierarchy: 4, or 1 for scenes far beyond L2 */
     uint64_t bvh_n_nodes, bvh_n_refs, bvh_n_leaves, bvh_depth;   /* the bounding-volume hierarchy (64-byte two-child nodes) */
     uint32_t accel_width, accel_build;                           /* 2 or 4: what the accelerated mode walks; RT_ACCEL_BUILD_* that built it */
     uint64_t bvh4_n_nodes, bvh4_stack_need;                      /* four-wide collapse: nodes, worst-case traversal stack entries */

@@ -100,7 +100,7 @@ class SceneInfo(C.Structure):
                 ("n_leaf_refs", C.c_uint64), ("n_packets", C.c_uint64), ("max_leaf_refs", C.c_uint64), ("tree_depth", C.c_uint64),
                 ("device_bytes", C.c_uint64), ("build_seconds", C.c_double), ("flatten_seconds", C.c_double),
                 ("upload_seconds", C.c_double), ("device", C.c_int32),
-                ("reserved1", C.c_uint32),
+                ("bvh_leaf_size", C.c_uint32),
                 ("bvh_n_nodes", C.c_uint64), ("bvh_n_refs", C.c_uint64), ("bvh_n_leaves", C.c_uint64), ("bvh_depth", C.c_uint64),
                 ("accel_width", C.c_uint32), ("accel_build", C.c_uint32), ("bvh4_n_nodes", C.c_uint64), ("bvh4_stack_need", C.c_uint64),
                 ("accel_build_seconds", C.c_double)]

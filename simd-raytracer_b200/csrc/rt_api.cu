@@ -264,12 +264,13 @@ struct DevTmp {
     ~DevTmp() { for (void* q : p) cudaFree(q); }
 };
 
-void device_build_bvh(rt_scene* s, bool wide) {
+void device_build_bvh(rt_scene* s, bool wide, uint32_t leaf) {
     const double t0 = now_s();
     select_device(s);
     const auto& tris = s->geom.tris;
     const uint64_t n64 = tris.size();
-    if (n64 <= 4 * LBVH_LEAF || n64 >= (1ull << 29)) throw rt_error(RT_ERR_UNSUPPORTED, "device build: triangle count outside (16, 2^29)");
+    if (n64 <= 4 * LBVH_MAX_LEAF || n64 >= (1ull << 29)) throw rt_error(RT_ERR_UNSUPPORTED, "device build: triangle count outside (16, 2^29)");
+    leaf = std::min(std::max(leaf, 1u), LBVH_MAX_LEAF);
     const uint32_t n = uint32_t(n64), n_inner = n - 1;
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -311,7 +312,7 @@ void device_build_bvh(rt_scene* s, bool wide) {
         k_lbvh_boxes<<<G, B, 0, st>>>(d_tri9, sids, int(n), left, right, parent_inner, parent_leaf, leaf_box, inner_box, arrived);
         CK(cudaGetLastError());
         uint32_t *kept = tmp.get<uint32_t>(n), *dense = tmp.get<uint32_t>(n);
-        k_lbvh_mark<<<G, B, 0, st>>>(first, last, int(n_inner), kept);
+        k_lbvh_mark<<<G, B, 0, st>>>(first, last, int(n_inner), leaf, kept);
         CK(cudaGetLastError());
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, kept, dense, int(n_inner), st));
@@ -445,8 +446,14 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     if (o.kd_max_leaf_size == 0) throw rt_error(RT_ERR_BAD_ARG, "kd_max_leaf_size == 0");
     // the accelerated mode's hierarchy: its width (rt_build_opts.accel_width; RT_B200_ACCEL_WIDTH overrides the default for sweeps)
     // and where it is built (rt_build_opts.accel_build; RT_B200_ACCEL_BUILD likewise)
-    uint32_t leaf = 4;                                                 // RT_B200_BVH_LEAF: tuning sweeps only
+    // Triangles per leaf of the backend's hierarchy.  A scene that stays in L1 / L2 is bound by instruction issue and wants few,
+    // full leaves (4: a node visit costs more instructions than a triangle test); a scene far beyond L2 pays a 48-byte fetch
+    // from L2 / HBM for every triangle it tests and wants one triangle per leaf (config 5: -5 % at 10 M triangles with either
+    // builder, profiles/r2_sweeps.txt).  The switch is the L2 capacity against ~176 bytes of hierarchy per triangle (126 MB:
+    // ~750 K triangles).  RT_B200_BVH_LEAF overrides (sweeps).
+    uint32_t leaf = s->host.triangle_count() * 176ull > (126ull << 20) ? 1u : 4u;
     if (const char* e = std::getenv("RT_B200_BVH_LEAF")) std::sscanf(e, "%u", &leaf);
+    if (leaf == 0) throw rt_error(RT_ERR_BAD_ARG, "RT_B200_BVH_LEAF must be >= 1");
     uint32_t width = o.accel_width;
     if (!width) { width = RT_DEFAULT_ACCEL_WIDTH; if (const char* e = std::getenv("RT_B200_ACCEL_WIDTH")) std::sscanf(e, "%u", &width); }
     if (width != 2 && width != 4) throw rt_error(RT_ERR_BAD_ARG, "accel_width must be 0 (default), 2 or 4");
@@ -457,6 +464,7 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     if (where == RT_ACCEL_BUILD_DEVICE && o.device < 0) throw rt_error(RT_ERR_BAD_ARG, "accel_build = device needs a device");
     s->wide = width == 4;
     s->info.accel_width = width;
+    s->info.bvh_leaf_size = leaf;
     s->device = o.device;
     s->info.device = o.device;
     const bool verbose = std::getenv("RT_B200_VERBOSE") != nullptr;
@@ -469,8 +477,8 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         std::exception_ptr err;
         ~Side() { if (th.joinable()) th.join(); }
     } side;
-    if (where == RT_ACCEL_BUILD_DEVICE && s->geom.tris.size() > 4 * LBVH_LEAF)
-        side.th = std::thread([&] { try { device_build_bvh(s, s->wide); } catch (...) { side.err = std::current_exception(); } });
+    if (where == RT_ACCEL_BUILD_DEVICE && s->geom.tris.size() > 4 * LBVH_MAX_LEAF)
+        side.th = std::thread([&] { try { device_build_bvh(s, s->wide, leaf); } catch (...) { side.err = std::current_exception(); } });
     s->tree = build_kd_tree(s->geom, o.kd_max_depth, o.kd_max_leaf_size);
     s->info.build_seconds = now_s() - t0;
     t0 = now_s();

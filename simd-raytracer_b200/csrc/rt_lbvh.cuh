@@ -1,7 +1,7 @@
 // csrc/rt_lbvh.cuh - device-side builder of the backend's bounding-volume hierarchy ("device-side
 // or parallel host builder").  The host builder (host/bvh_build.cpp, binned SAH on the task-parallel driver) needs ~6 s for
 // 10 M triangles on 16 host threads; this one builds the same KIND of structure - two-wide 64-byte nodes over 48-byte triangle
-// records with <= 4 triangles per leaf, plus the four-wide collapse - in tens of milliseconds on the GPU.  Only the backend's
+// records with at most `leaf` (1..4) triangles per leaf, plus the four-wide collapse - in tens of milliseconds on the GPU.  Only the backend's
 // OWN hierarchy can be built this way: the reference's kd-tree must stay the reference's (host/kd_build.cpp).  The answer of a
 // query does not depend on the hierarchy (rt_tri.cuh), so the parity tests apply unchanged; what a different tree changes is
 // the number of node visits.
@@ -10,8 +10,8 @@
 // (code, triangle) pairs (cub::DeviceRadixSort - library plumbing, not a hot path); (3) the binary radix tree over the sorted
 // codes, every inner node found independently from the common prefixes of its neighbours (Karras 2012), codes made unique by
 // the position in the sorted order; (4) boxes bottom-up, the second thread to arrive at a node merges its children; (5) every
-// radix-tree node that spans more than LEAF triangles becomes a two-wide node (numbered densely by a prefix sum), one that
-// spans <= LEAF a leaf over a contiguous run of the SORTED triangle records; (6) the four-wide collapse level by level from the
+// radix-tree node that spans more than `leaf` triangles becomes a two-wide node (numbered densely by a prefix sum), one that
+// spans <= `leaf` a leaf over a contiguous run of the SORTED triangle records; (6) the four-wide collapse level by level from the
 // root (the greedy rule of host/bvh4_collapse.hpp), which also yields the tree depth and the worst-case stack need that scene
 // creation checks.  Boxes carry the same absolute padding as the host builder's (2e-5 of the scene's largest coordinate).
 #pragma once
@@ -24,7 +24,7 @@
 
 namespace rtb {
 
-constexpr uint32_t LBVH_LEAF = 4;               // triangles per leaf (the host builder's default)
+constexpr uint32_t LBVH_MAX_LEAF = 4;           // most triangles a leaf can hold (the leaf size is a build parameter, 1..LBVH_MAX_LEAF)
 constexpr uint32_t LBVH_NONE = 0xFFFFFFFFu;
 
 struct LbvhBox { float lo[3], hi[3]; };
@@ -131,11 +131,11 @@ __global__ void k_lbvh_boxes(const float* __restrict__ tri9, const uint32_t* __r
     }
 }
 
-// kept[i] = 1 when radix-tree node i spans more than LBVH_LEAF triangles: it becomes a two-wide node (dense index = exclusive
+// kept[i] = 1 when radix-tree node i spans more than `leaf` triangles: it becomes a two-wide node (dense index = exclusive
 // prefix sum of kept, computed by the host glue with cub::DeviceScan)
-__global__ void k_lbvh_mark(const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, int n_inner, uint32_t* __restrict__ kept) {
+__global__ void k_lbvh_mark(const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, int n_inner, uint32_t leaf, uint32_t* __restrict__ kept) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_inner) kept[i] = (last[i] - first[i] + 1u > LBVH_LEAF) ? 1u : 0u;
+    if (i < n_inner) kept[i] = (last[i] - first[i] + 1u > leaf) ? 1u : 0u;
 }
 
 // the 64-byte two-wide nodes of csrc/rt_bvh.cuh: { c0.min.xyz, c0.max.xyz, c1.min.xyz, c1.max.xyz, ref0, ref1, cnt0, cnt1 }

@@ -73,10 +73,10 @@ bool same_tree4(const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb) 
 }  // namespace
 
 // returns 0, or a negative code naming the first step that went wrong; sizes through out6 = { n2, n4, stack_need, depth2, same-as-host-collapse, host stack need }
-extern "C" int lbvh_build_host(const float* tri9, uint32_t n, const float* root6, uint32_t* out6) {
+extern "C" int lbvh_build_host(const float* tri9, uint32_t n, const float* root6, uint32_t leaf, uint32_t* out6) {
     using namespace rtb;
     Built b;
-    if (n <= 4 * LBVH_LEAF) return -1;
+    if (n <= 4 * LBVH_MAX_LEAF || leaf < 1 || leaf > LBVH_MAX_LEAF) return -1;
     const uint32_t n_inner = n - 1;
     std::vector<uint64_t> keys(n);
     std::vector<uint32_t> ids(n);
@@ -94,7 +94,7 @@ extern "C" int lbvh_build_host(const float* tri9, uint32_t n, const float* root6
                            inner_box.data(), arrived.data()));
     for (uint32_t i = 0; i < n_inner; ++i) if (arrived[i] != 2u) return -2;          // every inner node was completed exactly once
     std::vector<uint32_t> kept(n, 0u), dense(n, 0u);
-    LAUNCH(n, k_lbvh_mark(first.data(), last.data(), int(n_inner), kept.data()));
+    LAUNCH(n, k_lbvh_mark(first.data(), last.data(), int(n_inner), leaf, kept.data()));
     uint32_t run = 0;
     for (uint32_t i = 0; i < n_inner; ++i) { dense[i] = run; run += kept[i]; }
     const uint32_t n2 = run;

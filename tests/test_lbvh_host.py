@@ -25,7 +25,7 @@ def libs(tmp_path_factory):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
                                os.path.join(REPO, "tests", "helpers", name + ".cpp"), "-o", str(so)])
         out[name] = C.CDLL(str(so))
-    out["lbvh_host"].lbvh_build_host.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    out["lbvh_host"].lbvh_build_host.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     out["lbvh_host"].lbvh_fetch_host.argtypes = [C.c_void_p] * 4
     k = out["kd8_host"]
     k.bvh_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float,
@@ -35,12 +35,12 @@ def libs(tmp_path_factory):
     return out
 
 
-def build(libs, scene):
+def build(libs, scene, leaf=4):
     tri9, _, _ = scene.geometry()
     _, bx, _ = scene.tree()
     root6 = np.ascontiguousarray(bx[0], np.float32)
     out6 = np.zeros(6, np.uint32)
-    rc = libs["lbvh_host"].lbvh_build_host(tri9.ctypes.data, len(tri9), root6.ctypes.data, out6.ctypes.data)
+    rc = libs["lbvh_host"].lbvh_build_host(tri9.ctypes.data, len(tri9), root6.ctypes.data, leaf, out6.ctypes.data)
     assert rc == 0, rc
     n2, n4, need, depth2, same, host_need = (int(v) for v in out6)
     nodes16 = np.zeros((n2, 16), np.uint32)
@@ -48,7 +48,7 @@ def build(libs, scene):
     nodes32 = np.zeros((n4, 32), np.uint32)
     root = np.zeros(6, np.float32)
     libs["lbvh_host"].lbvh_fetch_host(nodes16.ctypes.data, tris12.ctypes.data, nodes32.ctypes.data, root.ctypes.data)
-    return dict(tri9=tri9, nodes16=nodes16, tris12=tris12, nodes32=nodes32, root=root, need=need, depth2=depth2, same=same, host_need=host_need)
+    return dict(leaf=leaf, tri9=tri9, nodes16=nodes16, tris12=tris12, nodes32=nodes32, root=root, need=need, depth2=depth2, same=same, host_need=host_need)
 
 
 def check_structure(b):
@@ -74,7 +74,7 @@ def check_structure(b):
         order.append(i)
         for s in range(2):
             ref, cnt = int(nodes16[i, 12 + s]), int(nodes16[i, 14 + s])
-            assert cnt != 0xFFFFFFFF and cnt <= 4
+            assert cnt != 0xFFFFFFFF and cnt <= b["leaf"]
             if cnt == 0:
                 todo.append(ref)
     assert np.all(seen == 1)
@@ -140,11 +140,13 @@ def test_device_builder_on_fixture_scenes(rt, oracle_mod, libs, name):
     check_hits(libs, b, o, scene_rays(o, s, 40_000), False)
 
 
-def test_device_builder_on_a_synthetic_mesh(rt, oracle_mod, libs):
+@pytest.mark.parametrize("leaf", [4, 1])
+def test_device_builder_on_a_synthetic_mesh(rt, oracle_mod, libs, leaf):
+    """leaf = 1 is what a scene beyond L2 is built with (one triangle per leaf, rt_api.cu finish_create)"""
     data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=20_000, seed=9, width=160, height=120))
     s = rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY)
     o = oracle_mod.Oracle(data)
-    b = build(libs, s)
+    b = build(libs, s, leaf)
     check_structure(b)
     check_hits(libs, b, o, o.primary_rays(), True)
     check_hits(libs, b, o, scene_rays(o, s, 40_000), False)
