@@ -572,6 +572,31 @@ def test_device_built_hierarchy_same_hits_and_frames(rt, oracle_mod, golden, nam
     s.close()
 
 
+@pytest.mark.parametrize("build", ["host", "device"])
+def test_one_triangle_per_leaf_same_hits_and_frames(rt, oracle_mod, golden, monkeypatch, build):
+    """the leaf size scenes beyond L2 are built with (finish_create; forced here on a small scene with RT_B200_BVH_LEAF=1),
+    both builders: every leaf holds one triangle, hits and the frame are the reference's"""
+    monkeypatch.setenv("RT_B200_BVH_LEAF", "1")
+    name = "hw09_scene5"
+    data = scene_bytes(name)
+    s = rt.Scene.from_rtsc(data, accel_build=rt.ACCEL_BUILD_DEVICE if build == "device" else rt.ACCEL_BUILD_HOST)
+    monkeypatch.delenv("RT_B200_BVH_LEAF")
+    o = oracle_mod.Oracle(data)
+    assert s.info.bvh_leaf_size == 1
+    nodes16, tris12, _ = s.bvh_layout()
+    cnt = nodes16[:, 14:16].reshape(-1)
+    assert set(np.unique(cnt[cnt != 0xFFFFFFFF]).tolist()) <= {0, 1} and int((cnt == 1).sum()) == s.info.n_triangles
+    hits = s.trace_primary(rt.default_params(flags=rt.FLAG_ORDERED)).reshape(-1)
+    assert_hits_equal(hits, *o.trace(o.primary_rays(), True))
+    rays = random_rays(100_000, 31)
+    n5, bx, _ = s.tree()
+    rays[:, :3] = rays[:, :3] * (bx[0, 3:] - bx[0, :3]).max() / 2 + (bx[0, :3] + bx[0, 3:]) / 2
+    assert_hits_equal(s.trace_closest(rays, False, flags=rt.FLAG_ORDERED), *o.trace(rays, False))
+    img = s.render_frame(rt.default_params(flags=rt.FLAG_ORDERED))
+    assert sha(img) == golden["scenes"][name]["configs"]["s1d5g0"]["sha256_f32"]
+    s.close()
+
+
 def test_device_built_hierarchy_large_mesh_and_fallback(rt, oracle_mod):
     """300 K triangles: the device-built and the host-built scene render the same GI frame bit for bit (Philox-keyed rays) and
     give the oracle's hits; a scene too small for the device builder (<= 16 triangles) is built on the host and says so"""
@@ -710,6 +735,19 @@ def test_row_bands_in_one_call_tile_the_frame(rt, flags_name):
             assert np.array_equal(got[mine].view(np.uint32), want[mine].view(np.uint32))
             total[mine] = got[mine]
         assert np.array_equal(total.view(np.uint32), want.view(np.uint32))
+    # queued on the scene's own streams (two frames in flight): the bands of two ranks, rendered as two frames of a sequence
+    s, _ = gpu_scene(rt, "hw11_scene8", size=(320, 180))
+    want = s.render_frame(rt.default_params(flags=flags))
+    fbs = [torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()                                     # the frames render on the scene's streams, not torch's
+    tickets = [s.render_frame_device_begin(rt.default_params(flags=flags, band_rows=16, band_period=2, band_phase=r), fbs[r].data_ptr()) for r in range(2)]
+    for t in tickets:
+        s.frame_wait(t)
+    got = np.zeros_like(want)
+    for r in range(2):
+        for y0, y1 in rt.row_bands(180, 16, r, 2):
+            got[y0:y1] = fbs[r][y0:y1].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     s, _ = gpu_scene(rt, "hw11_scene8", size=(320, 180))
     fb = torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda")
     for bad in (dict(band_rows=6, band_period=2, band_phase=0), dict(band_rows=8, band_period=0, band_phase=0), dict(band_rows=8, band_period=2, band_phase=2),
