@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "kd_build.hpp"
 #include "kd_parallel.hpp"
@@ -45,55 +47,123 @@ struct Box {
     bool valid() const { return lo[0] <= hi[0]; }
 };
 
+// The builder reads nothing of a triangle but its box, and a node's triangles are scattered all over the scene's arrays: gathered
+// by triangle id, every access of a 10 M-triangle build is a cache miss (one thread: 200 ns per triangle and tree level).  So
+// the work lists carry the boxes WITH the ids - 28 bytes per reference - and every pass of the build streams through memory.
+struct TriBox { uint32_t id; float lo[3], hi[3]; };
+inline float box_centroid(const TriBox& t, int c) { return 0.5f * t.lo[c] + 0.5f * t.hi[c]; }
+
 struct BvhPolicy {
     struct Work {
         uint64_t depth = 0;
         float lo[3], hi[3];
-        std::vector<uint32_t> tris;
+        float clo[3], chi[3];            // bounds of the triangles' box centres (filled by the parent's partition pass)
+        std::vector<TriBox> tris;
         size_t size() const { return tris.size(); }
         bool empty() const { return tris.empty(); }
     };
-    const Geometry& g;
     uint32_t max_leaf, max_depth;
 
-    static float centroid(const TriGeom& t, int c) { return 0.5f * t.bmin[c] + 0.5f * t.bmax[c]; }
+    // Two passes over the node's triangles: (1) bin the box centres on all three axes at once, (2) partition, which also
+    // yields the children's boxes and centre bounds.  A big node (the top of a 10 M-triangle tree) splits both passes over the
+    // build threads: counts and boxes merge by + / min / max and the partition keeps the list order (per-chunk counts, then
+    // every chunk writes at its offsets), so the tree does not depend on the thread count.
+    static constexpr size_t PARALLEL_NODE = size_t(1) << 18;
+
+    // bins of the three axes; a bin's box is written when its first triangle arrives (most nodes of a tree are small: filling and
+    // sweeping 48 empty boxes per node was most of a 10 M-triangle build)
+    struct RawBox { float lo[3], hi[3]; };
+    static void grow(RawBox& b, const float* lo, const float* hi) {
+        for (int c = 0; c < 3; ++c) { b.lo[c] = std::min(b.lo[c], lo[c]); b.hi[c] = std::max(b.hi[c], hi[c]); }
+    }
+    struct Bins {
+        uint32_t cnt[3][BVH_BINS];
+        RawBox bb[3][BVH_BINS];
+        Bins() { std::memset(cnt, 0, sizeof cnt); }
+        void put(int a, int b, const float* lo, const float* hi) {
+            if (cnt[a][b]++ == 0) { std::memcpy(bb[a][b].lo, lo, 12); std::memcpy(bb[a][b].hi, hi, 12); }
+            else grow(bb[a][b], lo, hi);
+        }
+        void merge(const Bins& o) {
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < BVH_BINS; ++b) {
+                    if (!o.cnt[a][b]) continue;
+                    if (!cnt[a][b]) bb[a][b] = o.bb[a][b]; else grow(bb[a][b], o.bb[a][b].lo, o.bb[a][b].hi);
+                    cnt[a][b] += o.cnt[a][b];
+                }
+        }
+    };
+    static int bin_of(float centre, double lo, double scale) {
+        const int b = int((double(centre) - lo) * scale);
+        return std::min(std::max(b, 0), BVH_BINS - 1);
+    }
+    void bin_range(const TriBox* refs, size_t n, const float* clo, const double* scale, Bins& out) const {
+        for (size_t k = 0; k < n; ++k) {
+            const TriBox& t = refs[k];
+            for (int a = 0; a < 3; ++a) {
+                if (!(scale[a] > 0)) continue;
+                out.put(a, bin_of(box_centroid(t, a), clo[a], scale[a]), t.lo, t.hi);
+            }
+        }
+    }
+    struct Side { Box box, centres; };
+    // the references [refs, refs + n) go left (bin <= best_bin) or right, appended at out0 / out1 in order; returns how many went left
+    size_t partition_range(const TriBox* refs, size_t n, int axis, double lo, double scale, int best_bin, TriBox* out0, TriBox* out1,
+                           Side& s0, Side& s1) const {
+        size_t n0 = 0, n1 = 0;
+        for (size_t k = 0; k < n; ++k) {
+            const TriBox& t = refs[k];
+            const float c[3] = {box_centroid(t, 0), box_centroid(t, 1), box_centroid(t, 2)};
+            const bool left = bin_of(c[axis], lo, scale) <= best_bin;
+            Side& sd = left ? s0 : s1;
+            sd.box.add(t.lo, t.hi); sd.centres.add(c, c);
+            if (left) out0[n0++] = t; else out1[n1++] = t;
+        }
+        return n0;
+    }
+    static void finish_child(Work& c, const Side& sd) {
+        std::memcpy(c.lo, sd.box.lo, 12); std::memcpy(c.hi, sd.box.hi, 12);
+        std::memcpy(c.clo, sd.centres.lo, 12); std::memcpy(c.chi, sd.centres.hi, 12);
+    }
 
     bool expand(Work& w, uint32_t& axis_out, float& split_out, Work& c0, Work& c1) const {
         const size_t N = w.tris.size();
         if (N <= 1 || w.depth >= max_depth) return false;
-        float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (uint32_t id : w.tris)
-            for (int c = 0; c < 3; ++c) {
-                const float x = centroid(g.tris[id], c);
-                clo[c] = std::min(clo[c], x); chi[c] = std::max(chi[c], x);
-            }
+        const float* clo = w.clo; const float* chi = w.chi;
         const double area = half_area(w.lo, w.hi);
+        double scale[3];
+        for (int a = 0; a < 3; ++a) { const double width = double(chi[a]) - clo[a]; scale[a] = width > 0 ? BVH_BINS / width : 0.0; }
+        const bool wide_node = N >= PARALLEL_NODE && build_threads() > 1;
+        Bins bins;
+        if (wide_node) {
+            std::mutex m;
+            parallel_for(N, PARALLEL_NODE / 8, [&](uint64_t b, uint64_t e) {
+                Bins local;
+                bin_range(w.tris.data() + b, size_t(e - b), clo, scale, local);
+                std::lock_guard<std::mutex> g(m);
+                bins.merge(local);
+            });
+        } else bin_range(w.tris.data(), N, clo, scale, bins);
         int best_axis = -1, best_bin = 0;
         double best_cost = DBL_MAX;
         for (int axis = 0; axis < 3; ++axis) {
-            const double width = double(chi[axis]) - clo[axis];
-            if (!(width > 0)) continue;
-            uint32_t cnt[BVH_BINS] = {0};
-            Box bb[BVH_BINS];
-            const double scale = BVH_BINS / width;
-            for (uint32_t id : w.tris) {
-                const TriGeom& t = g.tris[id];
-                int b = int((double(centroid(t, axis)) - clo[axis]) * scale);
-                b = std::min(std::max(b, 0), BVH_BINS - 1);
-                ++cnt[b]; bb[b].add(t.bmin, t.bmax);
-            }
-            // sweep: right-to-left suffix boxes, then left-to-right
-            Box suf[BVH_BINS]; uint32_t sufn[BVH_BINS];
-            Box acc; uint32_t n = 0;
-            for (int b = BVH_BINS - 1; b >= 0; --b) { if (cnt[b]) acc.add(bb[b]); n += cnt[b]; suf[b] = acc; sufn[b] = n; }
-            Box left; uint32_t nl = 0;
-            for (int b = 0; b + 1 < BVH_BINS; ++b) {
-                if (cnt[b]) left.add(bb[b]);
-                nl += cnt[b];
-                const uint32_t nr = sufn[b + 1];
-                if (nl == 0 || nr == 0) continue;
-                const double cost = half_area(left.lo, left.hi) * nl + half_area(suf[b + 1].lo, suf[b + 1].hi) * nr;
-                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            if (!(scale[axis] > 0)) continue;
+            const uint32_t* cnt = bins.cnt[axis];
+            const RawBox* bb = bins.bb[axis];
+            // the occupied bins, ascending.  A split behind an EMPTY bin costs exactly what the split behind the last occupied
+            // bin before it costs (same two boxes, same counts), and the first of equal costs wins: only occupied bins compete
+            int occ[BVH_BINS], n_occ = 0;
+            for (int b = 0; b < BVH_BINS; ++b) if (cnt[b]) occ[n_occ++] = b;
+            if (n_occ < 2) continue;
+            RawBox suf[BVH_BINS]; uint32_t sufn[BVH_BINS];                  // indexed like occ: everything from occ[k] on
+            suf[n_occ - 1] = bb[occ[n_occ - 1]]; sufn[n_occ - 1] = cnt[occ[n_occ - 1]];
+            for (int k = n_occ - 2; k >= 1; --k) { suf[k] = suf[k + 1]; grow(suf[k], bb[occ[k]].lo, bb[occ[k]].hi); sufn[k] = sufn[k + 1] + cnt[occ[k]]; }
+            RawBox left = bb[occ[0]]; uint32_t nl = 0;
+            for (int k = 0; k + 1 < n_occ; ++k) {
+                if (k) grow(left, bb[occ[k]].lo, bb[occ[k]].hi);
+                nl += cnt[occ[k]];
+                const double cost = half_area(left.lo, left.hi) * nl + half_area(suf[k + 1].lo, suf[k + 1].hi) * sufn[k + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = occ[k]; }
             }
         }
         if (best_axis >= 0 && N <= max_leaf && area > 0) {
@@ -103,42 +173,86 @@ struct BvhPolicy {
         c0.depth = c1.depth = w.depth + 1;
         c0.tris.clear(); c1.tris.clear();
         if (best_axis >= 0) {
-            const double scale = BVH_BINS / (double(chi[best_axis]) - clo[best_axis]);
-            for (uint32_t id : w.tris) {
-                int b = int((double(centroid(g.tris[id], best_axis)) - clo[best_axis]) * scale);
-                b = std::min(std::max(b, 0), BVH_BINS - 1);
-                (b <= best_bin ? c0 : c1).tris.push_back(id);
+            const double lo = clo[best_axis], sc = scale[best_axis];
+            Side s0, s1;
+            if (wide_node) {
+                // chunk-wise: count, place the chunks at their offsets, partition again into place (the list order is kept)
+                const uint64_t threads = std::max<uint64_t>(1, std::min<uint64_t>(build_threads(), N / (PARALLEL_NODE / 8)));
+                const uint64_t step = (N + threads - 1) / threads, chunks = (N + step - 1) / step;
+                std::vector<size_t> left_of(chunks, 0);
+                parallel_for(chunks, 1, [&](uint64_t cb, uint64_t ce) {
+                    for (uint64_t c = cb; c < ce; ++c) {
+                        const size_t b = size_t(c * step), e = std::min(N, size_t((c + 1) * step));
+                        size_t n0 = 0;
+                        for (size_t k = b; k < e; ++k) n0 += bin_of(box_centroid(w.tris[k], best_axis), lo, sc) <= best_bin;
+                        left_of[c] = n0;
+                    }
+                });
+                std::vector<size_t> off0(chunks + 1, 0), off1(chunks + 1, 0);
+                for (uint64_t c = 0; c < chunks; ++c) {
+                    const size_t b = size_t(c * step), e = std::min(N, size_t((c + 1) * step));
+                    off0[c + 1] = off0[c] + left_of[c]; off1[c + 1] = off1[c] + (e - b - left_of[c]);
+                }
+                c0.tris.resize(off0[chunks]); c1.tris.resize(off1[chunks]);
+                std::vector<Side> side0(chunks), side1(chunks);
+                parallel_for(chunks, 1, [&](uint64_t cb, uint64_t ce) {
+                    for (uint64_t c = cb; c < ce; ++c) {
+                        const size_t b = size_t(c * step), e = std::min(N, size_t((c + 1) * step));
+                        partition_range(w.tris.data() + b, e - b, best_axis, lo, sc, best_bin, c0.tris.data() + off0[c], c1.tris.data() + off1[c],
+                                        side0[c], side1[c]);
+                    }
+                });
+                for (uint64_t c = 0; c < chunks; ++c) {
+                    if (side0[c].box.valid()) { s0.box.add(side0[c].box); s0.centres.add(side0[c].centres); }
+                    if (side1[c].box.valid()) { s1.box.add(side1[c].box); s1.centres.add(side1[c].centres); }
+                }
+            } else {
+                size_t n0 = 0;
+                for (int b = 0; b <= best_bin; ++b) n0 += bins.cnt[best_axis][b];
+                c0.tris.resize(n0); c1.tris.resize(N - n0);                   // the bins know how many go left
+                partition_range(w.tris.data(), N, best_axis, lo, sc, best_bin, c0.tris.data(), c1.tris.data(), s0, s1);
             }
+            finish_child(c0, s0); finish_child(c1, s1);
             axis_out = uint32_t(best_axis);
-            split_out = float(clo[best_axis] + (best_bin + 1) / scale);
+            split_out = float(clo[best_axis] + (best_bin + 1) / sc);
         } else {
             if (N <= max_leaf) return false;                                 // all centroids coincide: nothing to separate
             c0.tris.assign(w.tris.begin(), w.tris.begin() + N / 2);          // ... but too many for one leaf: halve the list
             c1.tris.assign(w.tris.begin() + N / 2, w.tris.end());
             axis_out = 0; split_out = clo[0];
-        }
-        for (Work* c : {&c0, &c1}) {
-            Box b;
-            for (uint32_t id : c->tris) b.add(g.tris[id].bmin, g.tris[id].bmax);
-            std::memcpy(c->lo, b.lo, 12); std::memcpy(c->hi, b.hi, 12);
+            for (Work* c : {&c0, &c1}) {
+                Side sd;
+                for (const TriBox& t : c->tris) {
+                    const float cc[3] = {box_centroid(t, 0), box_centroid(t, 1), box_centroid(t, 2)};
+                    sd.box.add(t.lo, t.hi); sd.centres.add(cc, cc);
+                }
+                finish_child(*c, sd);
+            }
         }
         return true;
     }
-    void emit(const Work& w, std::vector<uint32_t>& refs) const { refs.insert(refs.end(), w.tris.begin(), w.tris.end()); }
+    void emit(const Work& w, std::vector<uint32_t>& refs) const { for (const TriBox& t : w.tris) refs.push_back(t.id); }
 };
 
 }  // namespace
 
 KdTree build_bvh(const Geometry& g, uint32_t max_leaf) {
-    BvhPolicy pol{g, std::max<uint32_t>(1, std::min<uint32_t>(max_leaf, 255)), 44};
+    const size_t n = g.tris.size();
+    BvhPolicy pol{std::max<uint32_t>(1, std::min<uint32_t>(max_leaf, 255)), 44};
     BvhPolicy::Work root;
     root.depth = 0;
-    Box b;
-    for (const TriGeom& t : g.tris) b.add(t.bmin, t.bmax);
+    root.tris.resize(n);
+    parallel_for(n, 1 << 16, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) { root.tris[i].id = uint32_t(i); std::memcpy(root.tris[i].lo, g.tris[i].bmin, 12); std::memcpy(root.tris[i].hi, g.tris[i].bmax, 12); }
+    });
+    Box b, centres;
+    for (const TriBox& t : root.tris) {
+        const float c[3] = {box_centroid(t, 0), box_centroid(t, 1), box_centroid(t, 2)};
+        b.add(t.lo, t.hi); centres.add(c, c);
+    }
     if (!b.valid()) { std::memcpy(b.lo, g.root_min, 12); std::memcpy(b.hi, g.root_max, 12); }
     std::memcpy(root.lo, b.lo, 12); std::memcpy(root.hi, b.hi, 12);
-    root.tris.resize(g.tris.size());
-    for (uint32_t i = 0; i < root.tris.size(); ++i) root.tris[i] = i;
+    std::memcpy(root.clo, centres.lo, 12); std::memcpy(root.chi, centres.hi, 12);
     return kd_build_parallel(pol, std::move(root));
 }
 

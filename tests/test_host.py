@@ -307,3 +307,20 @@ def test_parallel_builder_is_thread_invariant(rt, oracle_mod, kd, monkeypatch):
                        [(s.info.bvh_n_nodes, s.info.bvh_n_leaves, s.info.bvh_n_refs, s.info.bvh_depth, s.info.bvh4_n_nodes, s.info.bvh4_stack_need)])
         s.close()
     assert layouts[0] == layouts[1] == layouts[2]
+
+
+def test_bvh_builder_big_nodes_are_thread_invariant(rt, monkeypatch):
+    """the top nodes of a big scene (>= 2^18 triangles) are binned and partitioned by all build threads (host/bvh_build.cpp):
+    counts and boxes merge by + / min / max and the partition keeps the list order, so the tree must not depend on the
+    thread count - one thread (everything sequential) against three and eight"""
+    data = crtscene.to_rtsc_bytes(crtscene.synthetic_scene(n_tris=600_000, seed=5, width=64, height=48))
+    layouts = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RT_B200_BUILD_THREADS", threads)
+        s = rt.Scene.from_rtsc(data, kd_max_depth=4, kd_max_leaf_size=64, device=rt.DEVICE_HOST_ONLY)
+        layouts.append([np.ascontiguousarray(a).tobytes() for a in s.bvh_layout()] +
+                       [(s.info.bvh_n_nodes, s.info.bvh_n_leaves, s.info.bvh_n_refs, s.info.bvh_depth, s.info.bvh4_n_nodes, s.info.bvh4_stack_need)])
+        ids = s.bvh_layout()[1][:, 3]
+        assert np.array_equal(np.sort(ids), np.arange(s.info.n_triangles, dtype=np.uint32))
+        s.close()
+    assert layouts[0] == layouts[1] == layouts[2]
