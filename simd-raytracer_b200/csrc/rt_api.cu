@@ -471,6 +471,7 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
 
     double t0 = now_s();
     s->geom = prepare_geometry(s->host);
+    const double t_prepared = now_s();
     // the device build runs beside the host build of the reference's kd-tree
     struct Side {
         std::thread th;
@@ -483,6 +484,8 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
     s->info.build_seconds = now_s() - t0;
     t0 = now_s();
     s->layout = flatten(s->host, s->geom, s->tree);
+    if (verbose) std::fprintf(stderr, "[rt_b200] geometry %.3f s, reference kd-tree %.3f s, its flattening %.3f s\n", t_prepared - (t0 - s->info.build_seconds),
+                              s->info.build_seconds - (t_prepared - (t0 - s->info.build_seconds)), now_s() - t0);
     if (side.th.joinable()) side.th.join();
     if (side.err) {
         try { std::rethrow_exception(side.err); }
