@@ -513,10 +513,11 @@ int finish_create(rt_scene* s, const rt_build_opts* opts, rt_scene** out) {
         s->info.bvh_n_nodes = s->bvh_layout.n_nodes; s->info.bvh_n_refs = s->bvh_layout.n_refs;
         s->info.bvh_n_leaves = bvh.n_leaves; s->info.bvh_depth = bvh.depth;
         if (s->wide) {
-            try { s->bvh4_nodes = bvh4_collapse(s->bvh_layout.nodes.data(), s->bvh_layout.n_nodes); }
+            uint32_t need = 0;
+            try { s->bvh4_nodes = bvh4_collapse(s->bvh_layout.nodes.data(), s->bvh_layout.n_nodes, &need); }
             catch (const std::length_error& e) { throw rt_error(RT_ERR_UNSUPPORTED, e.what()); }
             s->info.bvh4_n_nodes = s->bvh4_nodes.size() / 32;
-            s->info.bvh4_stack_need = bvh4_stack_need(s->bvh4_nodes);
+            s->info.bvh4_stack_need = need;
             if (s->info.bvh4_stack_need > uint64_t(BVH4_STACK)) throw rt_error(RT_ERR_UNSUPPORTED, "four-wide hierarchy needs a deeper traversal stack than BVH4_STACK");
         }
         s->info.accel_build_seconds = now_s() - t3;

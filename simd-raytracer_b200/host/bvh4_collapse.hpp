@@ -29,12 +29,17 @@ inline float bvh4_area(const Bvh4Child& c) {
 
 // nodes16: the two-wide nodes (16 words each), node 0 the root; returns the four-wide nodes (32 words each), node 0 the root.
 // Throws std::length_error when a leaf or an index does not fit the packed child word (ref << 3 | cnt).
-inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_nodes2) {
+// stack_need (optional): the worst-case traversal stack of the result, as bvh4_stack_need below computes it - the collapse visits
+// every node anyway, so scene creation gets the figure without a second pass over a 10 M-triangle tree.
+inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_nodes2, uint32_t* stack_need = nullptr) {
     constexpr uint32_t NO_CHILD = 0xFFFFFFFFu, MAX_LEAF = 7u, MAX_REF = 0x1FFFFFFDu;       // csrc/rt_bvh4.cuh
     std::vector<uint32_t> out;
+    if (stack_need) *stack_need = 0;
     if (!n_nodes2) return out;
-    struct Todo { uint32_t node2, slot; };            // two-wide subtree root -> where its four-wide node index has to be written
-    std::vector<Todo> todo{{0u, NO_CHILD}};
+    out.reserve(size_t(n_nodes2) * 16);               // a four-wide tree has about half the nodes of the two-wide one
+    struct Todo { uint32_t node2, slot, sp; };        // two-wide subtree root -> where its four-wide node index has to be written; stack entries below it
+    std::vector<Todo> todo{{0u, NO_CHILD, 0u}};
+    uint32_t need = 0;
     while (!todo.empty()) {
         const Todo t = todo.back();
         todo.pop_back();
@@ -75,10 +80,14 @@ inline std::vector<uint32_t> bvh4_collapse(const uint32_t* nodes16, uint64_t n_n
         }
         std::memcpy(out.data() + base, f, sizeof f);
         std::memcpy(out.data() + base + 24, child, sizeof child);
+        // a visit of a node with n children leaves n - 1 entries below the child it descends into (bvh4_stack_need)
+        const uint32_t below = t.sp + uint32_t(n ? n - 1 : 0);
+        need = std::max(need, below);
         // inner children: pushed in reverse so that child 0 comes next
         for (int k = n - 1; k >= 0; --k)
-            if (c[k].cnt == 0) todo.push_back({c[k].ref, uint32_t(base + 24 + k)});
+            if (c[k].cnt == 0) todo.push_back({c[k].ref, uint32_t(base + 24 + k), below});
     }
+    if (stack_need) *stack_need = need;
     return out;
 }
 
