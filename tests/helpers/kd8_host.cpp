@@ -78,7 +78,10 @@ extern "C" uint64_t bvh4_node_count(const float* nodes16, uint64_t n_nodes2) { r
 // worst-case traversal stack entries of the collapsed hierarchy (what scene creation checks against BVH4_STACK), and that bound
 extern "C" uint64_t bvh4_stack_need_host(const float* nodes16, uint64_t n_nodes2, uint64_t* capacity) {
     if (capacity) *capacity = uint64_t(rtb::BVH4_STACK);
-    return rtb::bvh4_stack_need(rtb::bvh4_collapse(reinterpret_cast<const uint32_t*>(nodes16), n_nodes2));
+    uint32_t in_the_same_walk = 0;                  // what scene creation uses: must be the figure of the separate pass
+    const std::vector<uint32_t> nodes4 = rtb::bvh4_collapse(reinterpret_cast<const uint32_t*>(nodes16), n_nodes2, &in_the_same_walk);
+    const uint32_t need = rtb::bvh4_stack_need(nodes4);
+    return need == in_the_same_walk ? uint64_t(need) : ~uint64_t(0);
 }
 extern "C" void bvh4_trace_batch(const float* nodes16, uint64_t n_nodes2, const float* tris, const float* root6, const float* rays6, uint64_t n,
                                  int cull, int fast, float eps, const float* t_far, int any_hit, float* tuv, int32_t* tri, uint8_t* tie,

@@ -138,6 +138,11 @@ def test_device_builder_on_fixture_scenes(rt, oracle_mod, libs, name):
     check_structure(b)
     check_hits(libs, b, o, o.primary_rays(), True)
     check_hits(libs, b, o, scene_rays(o, s, 40_000), False)
+    # the host-built tree of the same scene: the stack need scene creation computed inside the collapse = the separate pass over the result
+    n16, _, _ = s.bvh_layout()
+    libs["kd8_host"].bvh4_stack_need_host.restype = C.c_uint64
+    libs["kd8_host"].bvh4_stack_need_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    assert libs["kd8_host"].bvh4_stack_need_host(n16.ctypes.data, len(n16), None) == s.info.bvh4_stack_need
 
 
 @pytest.mark.parametrize("leaf", [4, 1])
