@@ -77,19 +77,19 @@ struct BvhPolicy {
         for (int c = 0; c < 3; ++c) { b.lo[c] = std::min(b.lo[c], lo[c]); b.hi[c] = std::max(b.hi[c], hi[c]); }
     }
     struct Bins {
+        uint32_t mask[3] = {0, 0, 0};                 // bit b: bin b of the axis holds something; cnt / bb of the other bins are not initialised
         uint32_t cnt[3][BVH_BINS];
         RawBox bb[3][BVH_BINS];
-        Bins() { std::memset(cnt, 0, sizeof cnt); }
         void put(int a, int b, const float* lo, const float* hi) {
-            if (cnt[a][b]++ == 0) { std::memcpy(bb[a][b].lo, lo, 12); std::memcpy(bb[a][b].hi, hi, 12); }
-            else grow(bb[a][b], lo, hi);
+            if (!((mask[a] >> b) & 1u)) { mask[a] |= 1u << b; cnt[a][b] = 1; std::memcpy(bb[a][b].lo, lo, 12); std::memcpy(bb[a][b].hi, hi, 12); }
+            else { ++cnt[a][b]; grow(bb[a][b], lo, hi); }
         }
         void merge(const Bins& o) {
             for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < BVH_BINS; ++b) {
-                    if (!o.cnt[a][b]) continue;
-                    if (!cnt[a][b]) bb[a][b] = o.bb[a][b]; else grow(bb[a][b], o.bb[a][b].lo, o.bb[a][b].hi);
-                    cnt[a][b] += o.cnt[a][b];
+                for (uint32_t m = o.mask[a]; m; m &= m - 1u) {
+                    const int b = __builtin_ctz(m);
+                    if (!((mask[a] >> b) & 1u)) { mask[a] |= 1u << b; cnt[a][b] = o.cnt[a][b]; bb[a][b] = o.bb[a][b]; }
+                    else { cnt[a][b] += o.cnt[a][b]; grow(bb[a][b], o.bb[a][b].lo, o.bb[a][b].hi); }
                 }
         }
     };
@@ -153,7 +153,7 @@ struct BvhPolicy {
             // the occupied bins, ascending.  A split behind an EMPTY bin costs exactly what the split behind the last occupied
             // bin before it costs (same two boxes, same counts), and the first of equal costs wins: only occupied bins compete
             int occ[BVH_BINS], n_occ = 0;
-            for (int b = 0; b < BVH_BINS; ++b) if (cnt[b]) occ[n_occ++] = b;
+            for (uint32_t m = bins.mask[axis]; m; m &= m - 1u) occ[n_occ++] = __builtin_ctz(m);
             if (n_occ < 2) continue;
             RawBox suf[BVH_BINS]; uint32_t sufn[BVH_BINS];                  // indexed like occ: everything from occ[k] on
             suf[n_occ - 1] = bb[occ[n_occ - 1]]; sufn[n_occ - 1] = cnt[occ[n_occ - 1]];
@@ -208,7 +208,7 @@ struct BvhPolicy {
                 }
             } else {
                 size_t n0 = 0;
-                for (int b = 0; b <= best_bin; ++b) n0 += bins.cnt[best_axis][b];
+                for (uint32_t m = bins.mask[best_axis] & ((2u << best_bin) - 1u); m; m &= m - 1u) n0 += bins.cnt[best_axis][__builtin_ctz(m)];
                 c0.tris.resize(n0); c1.tris.resize(N - n0);                   // the bins know how many go left
                 partition_range(w.tris.data(), N, best_axis, lo, sc, best_bin, c0.tris.data(), c1.tris.data(), s0, s1);
             }
