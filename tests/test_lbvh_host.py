@@ -174,3 +174,39 @@ def test_device_build_needs_a_device_and_valid_option(rt):
         rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY, accel_build=rt.ACCEL_BUILD_DEVICE)
     with pytest.raises(rt.RtError):
         rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY, accel_build=7)
+
+
+@pytest.mark.parametrize("shape", ["strip", "clusters", "coincident", "plane"])
+def test_device_builder_on_degenerate_distributions(rt, oracle_mod, libs, shape):
+    """distributions a Morton-code builder could trip over: every triangle on one line (two of three code axes constant), two tight
+    clusters far apart (long common prefixes), 3,000 copies of ONE triangle (equal codes, told apart by position only), a flat
+    plane - the tree must stay valid, within the traversal's depth / stack limits, and give the oracle's hits"""
+    rng = np.random.default_rng(17)
+    n = 6000
+    base = crtscene.synthetic_scene(n_tris=n, seed=21, width=96, height=64)
+    m = base.meshes[0]
+    v = np.asarray(m.vertices, np.float32).reshape(n, 3, 3).copy()
+    size = 0.02
+    if shape == "strip":
+        c = np.zeros((n, 1, 3), np.float32); c[:, 0, 0] = np.linspace(-1, 1, n)
+    elif shape == "clusters":
+        c = (rng.uniform(-1, 1, (n, 1, 3)) * 1e-3).astype(np.float32); c[: n // 2, 0, :] += 1.0; c[n // 2:, 0, :] -= 1.0
+        size = 1e-3
+    elif shape == "coincident":
+        c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    else:
+        c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32); c[:, 0, 1] = 0.25
+    v = (c + size * rng.uniform(-1, 1, (n, 3, 3))).astype(np.float32)
+    if shape == "coincident":
+        v[: n // 2] = v[0]
+    if shape == "plane":
+        v[:, :, 1] = 0.25
+    m.vertices = v.reshape(-1, 3)
+    data = crtscene.to_rtsc_bytes(base)
+    s = rt.Scene.from_rtsc(data, device=rt.DEVICE_HOST_ONLY)
+    o = oracle_mod.Oracle(data)
+    for leaf in (4, 1):
+        b = build(libs, s, leaf)
+        check_structure(b)
+        check_hits(libs, b, o, o.primary_rays(), True)
+        check_hits(libs, b, o, scene_rays(o, s, 20_000), False)
